@@ -1,0 +1,767 @@
+// GPU BVH builder for triangle scenes (sm_100a).
+//
+// Replaces, on the device, the reference's CPU build path
+//   createPrimRefArray            kernels/builders/primrefgen.cpp:35-57, scene_triangle_mesh.h:131-153,208-221
+//   BVHNBuilderSAH<8,Triangle4>   kernels/bvh/bvh_builder_sah.cpp:85-191
+//   GeneralBVHBuilder::recurse    kernels/builders/bvh_builder_sah.h:222-319 (greedy 8-wide widening by SAH)
+//   BVHBuilderMorton              kernels/builders/bvh_builder_morton.h:70-104,300-433 (Morton front end)
+//   radix_sort_u32                common/algorithms/parallel_sort.h
+//   BVHNStatistics                kernels/bvh/bvh_statistics.cpp:41-160 (SAH figure)
+// with a pipeline designed for the GPU rather than translated:
+//   1. k_setup_prims   one thread per triangle: validity filter (index range, |v| < 1.844e18),
+//                      48-byte triangle record, scene + centroid bounds (warp shuffles + atomics)
+//   2. k_morton        63-bit Morton code of the box centre (21 bits per axis)
+//   3. radix sort      LSD, 8 bits per pass, stable warp-match ranking (hand written, no CUB)
+//   4. k_hierarchy     binary radix tree over the sorted codes (one thread per inner node)
+//   5. k_refit_dp      bottom-up: exact bounds + SAH dynamic programme that decides, per binary
+//                      node and per forest size 1..7, how to cut the binary tree into 8-wide nodes
+//   6. k_emit          top-down, one level per launch: materialise 128-byte quantised 8-wide
+//                      nodes, octant-ordered child slots, leaf triangles copied into leaf order
+// All traffic is streaming/coalesced except the unavoidable gathers (vertex fetch, leaf copy).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <float.h>
+#include <vector>
+#include "rq_device.h"
+
+#define RQ_FLT_LARGE 1.844E18f      // common/math/constants.h:34 (vertex validity bound)
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = (int)e_; goto fail; } } while (0)
+
+static unsigned long long g_launches = 0;
+unsigned long long rqLaunchCount(void) { return g_launches; }
+void rqCountLaunch(unsigned n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+namespace {
+
+// ----------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(float f) {          // order-preserving float -> uint
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t u) {
+  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  union { uint32_t u; float f; } c; c.u = u; return c.f;
+#endif
+}
+__device__ __forceinline__ float warpMin(float v) {
+  for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warpMax(float v) {
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__host__ __device__ __forceinline__ float halfArea(float dx, float dy, float dz) {
+  return dx * (dy + dz) + dy * dz;                            // common/math/vec3.h halfArea
+}
+
+struct Bounds12 {                                             // 12 ordered-uint slots in global memory
+  uint32_t sceneLo[3], sceneHi[3], centLo[3], centHi[3];
+};
+
+// ----------------------------------------------------------------------------------------------
+// 1. primitive setup
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_setup_prims(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t N,
+              RQTri* __restrict__ trisIn, Bounds12* bounds, uint32_t* invalidCount) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  bool valid = false;
+  if (g < N) {
+    int a = 0, b = numGeoms - 1;                              // last mesh with primBase <= g
+    while (a < b) { int m = (a + b + 1) >> 1; if (geoms[m].primBase <= g) a = m; else b = m - 1; }
+    const RQGeomDesc G = geoms[a];
+    const uint32_t local = g - G.primBase;
+    const uint32_t* ip = (const uint32_t*)(G.indices + (size_t)local * G.indexStride);
+    const uint32_t i0 = ip[0], i1 = ip[1], i2 = ip[2];
+    RQTri t;
+    t.primID = local; t.geomID = G.geomID; t.pad = 1;
+    for (int k = 0; k < 3; k++) { t.v0[k] = 0.f; t.v1[k] = 0.f; t.v2[k] = 0.f; }
+    if (i0 < G.numVerts && i1 < G.numVerts && i2 < G.numVerts) {
+      const float* p0 = (const float*)(G.vertices + (size_t)i0 * G.vertexStride);
+      const float* p1 = (const float*)(G.vertices + (size_t)i1 * G.vertexStride);
+      const float* p2 = (const float*)(G.vertices + (size_t)i2 * G.vertexStride);
+      valid = true;
+      for (int k = 0; k < 3; k++) {
+        t.v0[k] = p0[k]; t.v1[k] = p1[k]; t.v2[k] = p2[k];
+        valid &= (t.v0[k] > -RQ_FLT_LARGE) & (t.v0[k] < RQ_FLT_LARGE);   // NaN fails both
+        valid &= (t.v1[k] > -RQ_FLT_LARGE) & (t.v1[k] < RQ_FLT_LARGE);
+        valid &= (t.v2[k] > -RQ_FLT_LARGE) & (t.v2[k] < RQ_FLT_LARGE);
+      }
+      if (valid) {
+        t.pad = 0;
+        for (int k = 0; k < 3; k++) {
+          lo[k] = fminf(fminf(t.v0[k], t.v1[k]), t.v2[k]);
+          hi[k] = fmaxf(fmaxf(t.v0[k], t.v1[k]), t.v2[k]);
+          clo[k] = chi[k] = 0.5f * lo[k] + 0.5f * hi[k];
+        }
+      }
+    }
+    // three 16-byte stores
+    float4* dst = (float4*)(trisIn + g);
+    dst[0] = make_float4(t.v0[0], t.v0[1], t.v0[2], t.v1[0]);
+    dst[1] = make_float4(t.v1[1], t.v1[2], t.v2[0], t.v2[1]);
+    dst[2] = make_float4(t.v2[2], __uint_as_float(t.primID), __uint_as_float(t.geomID), __uint_as_float(t.pad));
+  }
+  // block reduction: warp shuffles, then one atomic per warp and slot
+  const unsigned nInvalid = __popc(__ballot_sync(0xffffffffu, (g < N) && !valid));
+  for (int k = 0; k < 3; k++) {
+    lo[k] = warpMin(lo[k]); hi[k] = warpMax(hi[k]); clo[k] = warpMin(clo[k]); chi[k] = warpMax(chi[k]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (lo[0] <= hi[0]) {
+      for (int k = 0; k < 3; k++) {
+        atomicMin(&bounds->sceneLo[k], f2ord(lo[k])); atomicMax(&bounds->sceneHi[k], f2ord(hi[k]));
+        atomicMin(&bounds->centLo[k], f2ord(clo[k])); atomicMax(&bounds->centHi[k], f2ord(chi[k]));
+      }
+    }
+    if (nInvalid) atomicAdd(invalidCount, nInvalid);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// 2. Morton codes
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t expand21(uint32_t v) {    // spread 21 bits to every third bit
+  uint64_t x = v & 0x1FFFFFull;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8)  & 0x100F00F00F00F00Full;
+  x = (x | x << 4)  & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2)  & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void __launch_bounds__(256)
+k_morton(const RQTri* __restrict__ trisIn, uint32_t N, const Bounds12* __restrict__ bounds,
+         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  const float4* src = (const float4*)(trisIn + g);
+  const float4 a = src[0], b = src[1], c = src[2];
+  uint64_t key = ~0ull;                                       // invalid primitives sort to the end
+  if (__float_as_uint(c.w) == 0) {
+    const float v0[3] = {a.x, a.y, a.z}, v1[3] = {a.w, b.x, b.y}, v2[3] = {b.z, b.w, c.x};
+    uint32_t q[3];
+    for (int k = 0; k < 3; k++) {
+      const float lo = fminf(fminf(v0[k], v1[k]), v2[k]), hi = fmaxf(fmaxf(v0[k], v1[k]), v2[k]);
+      const float cen = 0.5f * lo + 0.5f * hi;
+      const float cl = ord2f(bounds->centLo[k]), ch = ord2f(bounds->centHi[k]);
+      const float ext = ch - cl;
+      float x = ext > 0.f ? (cen - cl) / ext : 0.f;
+      x = fminf(fmaxf(x, 0.f), 1.f);
+      q[k] = min(2097151u, (uint32_t)(x * 2097152.0f));
+    }
+    key = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+  }
+  keys[g] = key;
+  vals[g] = g;
+}
+
+// ----------------------------------------------------------------------------------------------
+// 3. LSD radix sort, 8-bit digits.  Tile = 8 warps x 8 items x 32 lanes = 2048 keys, laid out
+//    warp-major (warp w owns keys [w*256, w*256+256) of the tile, item-major inside) so that the
+//    per-warp running digit counters give a stable rank.
+// ----------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_hist(const uint64_t* __restrict__ keys, uint32_t N, int shift, uint32_t numTiles,
+            uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * SORT_TILE;
+  #pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    const uint32_t idx = base + i * SORT_THREADS + threadIdx.x;
+    if (idx < N) atomicAdd(&h[(uint32_t)(keys[idx] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * numTiles + blockIdx.x] = h[threadIdx.x];   // digit-major
+}
+
+// one block per digit: exclusive scan of that digit's row, row total to digitTotal
+__global__ void __launch_bounds__(256)
+k_sort_scan_rows(uint32_t* __restrict__ hist, uint32_t numTiles, uint32_t* __restrict__ digitTotal) {
+  __shared__ uint32_t part[256];
+  uint32_t* row = hist + (size_t)blockIdx.x * numTiles;
+  const uint32_t chunk = (numTiles + 255u) / 256u;
+  const uint32_t b = threadIdx.x * chunk, e = min(b + chunk, numTiles);
+  uint32_t s = 0;
+  for (uint32_t i = b; i < e; i++) s += row[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {                          // Hillis-Steele inclusive scan
+    uint32_t v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - s;                        // exclusive prefix of this chunk
+  for (uint32_t i = b; i < e; i++) { const uint32_t v = row[i]; row[i] = run; run += v; }
+  if (threadIdx.x == 255) digitTotal[blockIdx.x] = part[255];
+}
+
+__global__ void __launch_bounds__(256)
+k_sort_scan_digits(uint32_t* __restrict__ digitTotal) {          // 256 totals -> exclusive bases
+  __shared__ uint32_t part[256];
+  const uint32_t s = digitTotal[threadIdx.x];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    uint32_t v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  digitTotal[threadIdx.x] = part[threadIdx.x] - s;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_scatter(const uint64_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+               uint64_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t N, int shift,
+               uint32_t numTiles, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ digitBase) {
+  __shared__ uint32_t cnt[SORT_THREADS / 32][256];
+  __shared__ uint32_t gbase[256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (SORT_THREADS / 32) * 256; i += SORT_THREADS) (&cnt[0][0])[i] = 0;
+  gbase[threadIdx.x] = digitBase[threadIdx.x] + hist[threadIdx.x * numTiles + blockIdx.x];
+  __syncthreads();
+  const uint32_t wbase = blockIdx.x * SORT_TILE + warp * (32 * SORT_ITEMS);
+  uint64_t key[SORT_ITEMS]; uint32_t val[SORT_ITEMS], rank[SORT_ITEMS];
+  #pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    const uint32_t idx = wbase + i * 32 + lane;
+    const bool ok = idx < N;
+    key[i] = ok ? keysIn[idx] : 0; val[i] = ok ? valsIn[idx] : 0; rank[i] = 0;
+    const unsigned vmask = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+      const unsigned peers = __match_any_sync(vmask, d);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader) { old = cnt[warp][d]; cnt[warp][d] = old + __popc(peers); }
+      old = __shfl_sync(peers, old, leader);
+      rank[i] = old + __popc(peers & ((1u << lane) - 1u));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  {                                                             // exclusive prefix over the 8 warps
+    uint32_t run = 0;
+    #pragma unroll
+    for (int w = 0; w < SORT_THREADS / 32; w++) { const uint32_t t = cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = run; run += t; }
+  }
+  __syncthreads();
+  #pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    const uint32_t idx = wbase + i * 32 + lane;
+    if (idx < N) {
+      const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+      const uint32_t pos = gbase[d] + cnt[warp][d] + rank[i];
+      keysOut[pos] = key[i]; valsOut[pos] = val[i];
+    }
+  }
+}
+
+// NOTE: k_sort_hist tiles keys as base + i*256 + thread (order inside a tile is irrelevant for a
+// histogram); k_sort_scatter uses the same tile range [blockIdx*2048, +2048).
+
+// ----------------------------------------------------------------------------------------------
+// 4. binary radix tree (Karras 2012) over sorted 63-bit codes, ties broken by position.
+//    Node ids: inner i in [0, n-1), leaf k -> (n-1)+k.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const uint64_t a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(i ^ j);
+  return __clzll((long long)(a ^ b));
+}
+
+__global__ void __launch_bounds__(256)
+k_hierarchy(const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ left, uint32_t* __restrict__ right,
+            uint32_t* __restrict__ parent, uint32_t* __restrict__ rangeFirst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = delta(keys, n, i, j);
+  int s = 0, t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int gamma = i + s * d + min(d, 0);
+  const int lo = min(i, j), hi = max(i, j);
+  const uint32_t L = (lo == gamma) ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
+  const uint32_t R = (hi == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+  left[i] = L; right[i] = R; rangeFirst[i] = (uint32_t)lo;
+  parent[L] = (uint32_t)i; parent[R] = (uint32_t)i;
+  if (i == 0) parent[0] = RQ_INVALID;
+}
+
+// ----------------------------------------------------------------------------------------------
+// 5. bottom-up refit + SAH collapse programme.
+//    For binary node x and forest size i (1..7):  C(x,i) = cheapest way to represent x's subtree
+//    as at most i roots of the 8-wide tree.
+//      leaf(x)      = A(x) * T(x) * costTri            if T(x) <= maxLeafTris
+//      split(x,j)   = min_k C(left,k) + C(right,j-k)
+//      C(x,1)       = min(leaf(x), split(x,8) + A(x)*costNode)
+//      C(x,i)       = min(split(x,i), C(x,i-1))
+//    dec word: bit0 = "C(x,1) is an inner node"; bits [3(j-1), 3(j-1)+2] for j=2..8 = k chosen
+//    for split(x,j) (0 = fall back to C(x,j-1)).
+// ----------------------------------------------------------------------------------------------
+struct B2 {                    // binary-tree arrays (2n-1 nodes unless noted)
+  float4* lo;                  // xyz = lower, w = half area
+  float4* hi;                  // xyz = upper, w = triangle count (uint bits)
+  float*  cost;                // 8 floats per node, [0..6] = C(x,1..7)
+  uint32_t* dec;
+  uint32_t* left;              // n-1
+  uint32_t* right;             // n-1
+  uint32_t* parent;            // 2n-1
+  uint32_t* rangeFirst;        // n-1
+  uint32_t* flag;              // n-1 arrival counters
+};
+
+__global__ void __launch_bounds__(256)
+k_refit_dp(B2 t, int n, const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals,
+           float costNode, float costTri, int maxLeafTris) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  uint32_t node = (uint32_t)(n - 1 + k);
+  {
+    const float4* src = (const float4*)(trisIn + vals[k]);
+    const float4 a = src[0], b = src[1], c = src[2];
+    const float lx = fminf(fminf(a.x, a.w), b.z), ly = fminf(fminf(a.y, b.x), b.w), lz = fminf(fminf(a.z, b.y), c.x);
+    const float hx = fmaxf(fmaxf(a.x, a.w), b.z), hy = fmaxf(fmaxf(a.y, b.x), b.w), hz = fmaxf(fmaxf(a.z, b.y), c.x);
+    const float A = halfArea(hx - lx, hy - ly, hz - lz);
+    t.lo[node] = make_float4(lx, ly, lz, A);
+    t.hi[node] = make_float4(hx, hy, hz, __uint_as_float(1u));
+    const float cl = A * costTri;
+    float4* cp = (float4*)(t.cost + (size_t)node * 8);
+    cp[0] = make_float4(cl, cl, cl, cl);
+    cp[1] = make_float4(cl, cl, cl, 0.f);
+    t.dec[node] = 0;
+  }
+  __threadfence();
+  uint32_t cur = t.parent[node];
+  while (cur != RQ_INVALID) {
+    if (atomicAdd(&t.flag[cur], 1u) == 0u) return;             // first arrival: sibling not ready yet
+    __threadfence();
+    const uint32_t L = t.left[cur], R = t.right[cur];
+    // data produced by other SMs in this launch: read through L2 (ld.cg), never L1
+    const float4 llo = __ldcg(t.lo + L), lhi = __ldcg(t.hi + L), rlo = __ldcg(t.lo + R), rhi = __ldcg(t.hi + R);
+    const float4 l0 = __ldcg((const float4*)(t.cost + (size_t)L * 8)), l1 = __ldcg((const float4*)(t.cost + (size_t)L * 8) + 1);
+    const float4 r0 = __ldcg((const float4*)(t.cost + (size_t)R * 8)), r1 = __ldcg((const float4*)(t.cost + (size_t)R * 8) + 1);
+    const float cl[8] = {0.f, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z};
+    const float cr[8] = {0.f, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z};
+    const float lx = fminf(llo.x, rlo.x), ly = fminf(llo.y, rlo.y), lz = fminf(llo.z, rlo.z);
+    const float hx = fmaxf(lhi.x, rhi.x), hy = fmaxf(lhi.y, rhi.y), hz = fmaxf(lhi.z, rhi.z);
+    const float A = halfArea(hx - lx, hy - ly, hz - lz);
+    const uint32_t T = __float_as_uint(lhi.w) + __float_as_uint(rhi.w);
+    float dist[9]; uint32_t kb[9];
+    #pragma unroll
+    for (int j = 2; j <= 8; j++) {
+      float best = FLT_MAX; uint32_t bk = 1;
+      #pragma unroll
+      for (int kk = 1; kk <= 7; kk++) {
+        if (kk < j && j - kk <= 7) {
+          const float v = cl[kk] + cr[j - kk];
+          if (v < best) { best = v; bk = kk; }
+        }
+      }
+      dist[j] = best; kb[j] = bk;
+    }
+    const float leafCost = (T <= (uint32_t)maxLeafTris) ? A * (float)T * costTri : FLT_MAX;
+    const float innerCost = dist[8] + A * costNode;
+    float c[8];
+    uint32_t dec = (kb[8] << 21);
+    if (T > (uint32_t)maxLeafTris || innerCost < leafCost) { c[1] = innerCost; dec |= 1u; } else c[1] = leafCost;
+    #pragma unroll
+    for (int i = 2; i <= 7; i++) {
+      if (dist[i] < c[i - 1]) { c[i] = dist[i]; dec |= kb[i] << (3 * (i - 1)); }
+      else c[i] = c[i - 1];
+    }
+    t.lo[cur] = make_float4(lx, ly, lz, A);
+    t.hi[cur] = make_float4(hx, hy, hz, __uint_as_float(T));
+    float4* cp = (float4*)(t.cost + (size_t)cur * 8);
+    cp[0] = make_float4(c[1], c[2], c[3], c[4]);
+    cp[1] = make_float4(c[5], c[6], c[7], 0.f);
+    t.dec[cur] = dec;
+    __threadfence();
+    cur = t.parent[cur];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// 6. top-down emission of 8-wide nodes, one tree level per launch.
+// ----------------------------------------------------------------------------------------------
+struct EmitCounters {
+  uint32_t nodeCount;          // 8-wide nodes allocated so far
+  uint32_t triCount;           // leaf triangles allocated so far
+  uint32_t nextCount;          // entries written to the next-level queue
+  uint32_t leafSlots;
+  double sahInnerQ, sahLeafQ;  // reference SAH terms on de-quantised boxes
+  double sahInnerX, sahLeafX;  // same on exact boxes
+};
+
+__device__ __forceinline__ uint8_t expForExtent(float ext) {
+  // smallest biased exponent eb with ext <= 255 * 2^(eb-127); 2^(eb-127) must be a normal float
+  if (!(ext > 0.f)) return 1;
+  int ex; frexpf(ext * (1.0f / 255.0f), &ex);                  // ext/255 = m * 2^ex, m in [0.5,1)
+  int eb = ex + 127;                                           // 2^ex >= ext/255
+  if (eb < 1) eb = 1;
+  if (eb > 254) eb = 254;
+  return (uint8_t)eb;
+}
+
+__device__ __forceinline__ void
+emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2* __restrict__ nextQueue,
+         EmitCounters* ctr, RQNode* __restrict__ nodes, RQTri* __restrict__ trisOut,
+         const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals, uint32_t level,
+         const uint32_t* __restrict__ parentOf, uint32_t* __restrict__ nextParentOf, double sahOut[4]) {
+  const uint32_t b = queue[q].x, w = queue[q].y;
+  const uint32_t firstLeaf = (uint32_t)(n - 1);
+
+  // ---- gather the <= 8 children by replaying the DP decisions ----
+  uint32_t child[8]; bool inner[8]; int nc = 0;
+  if (b >= firstLeaf) {                                        // degenerate scene: a single triangle
+    child[0] = b; inner[0] = false; nc = 1;
+  } else {
+    uint32_t stN[16]; int stI[16]; int sp = 0;
+    const uint32_t k8 = (t.dec[b] >> 21) & 7u;
+    stN[sp] = t.right[b]; stI[sp++] = 8 - (int)k8;
+    stN[sp] = t.left[b];  stI[sp++] = (int)k8;
+    while (sp > 0) {
+      const uint32_t m = stN[--sp]; int i = stI[sp];
+      if (m >= firstLeaf) { child[nc] = m; inner[nc++] = false; continue; }
+      const uint32_t dec = t.dec[m];
+      while (i > 1 && ((dec >> (3 * (i - 1))) & 7u) == 0u) i--;
+      if (i == 1) { child[nc] = m; inner[nc++] = (dec & 1u) != 0u; continue; }
+      const int kk = (int)((dec >> (3 * (i - 1))) & 7u);
+      stN[sp] = t.right[m]; stI[sp++] = i - kk;
+      stN[sp] = t.left[m];  stI[sp++] = kk;
+    }
+  }
+
+  // ---- node box and child boxes ----
+  const float4 nlo = t.lo[b], nhi = t.hi[b];
+  float clo[8][3], chi[8][3]; uint32_t ctris[8];
+  for (int c = 0; c < nc; c++) {
+    const float4 a = t.lo[child[c]], h = t.hi[child[c]];
+    clo[c][0] = a.x; clo[c][1] = a.y; clo[c][2] = a.z; chi[c][0] = h.x; chi[c][1] = h.y; chi[c][2] = h.z;
+    ctris[c] = __float_as_uint(h.w);
+  }
+
+  // ---- slot assignment: slot s (bit a set = "towards +axis a") takes the child whose centre lies
+  //      furthest in that diagonal direction; greedy maximum over the 8x8 score table ----
+  const float ncx = 0.5f * (nlo.x + nhi.x), ncy = 0.5f * (nlo.y + nhi.y), ncz = 0.5f * (nlo.z + nhi.z);
+  int slotOf[8]; int childAt[8];
+  for (int s = 0; s < 8; s++) childAt[s] = -1;
+  for (int c = 0; c < nc; c++) slotOf[c] = -1;
+  for (int r = 0; r < nc; r++) {
+    float best = -FLT_MAX; int bc = -1, bs = -1;
+    for (int c = 0; c < nc; c++) {
+      if (slotOf[c] >= 0) continue;
+      const float dx = 0.5f * (clo[c][0] + chi[c][0]) - ncx, dy = 0.5f * (clo[c][1] + chi[c][1]) - ncy,
+                  dz = 0.5f * (clo[c][2] + chi[c][2]) - ncz;
+      for (int s = 0; s < 8; s++) {
+        if (childAt[s] >= 0) continue;
+        const float sc = ((s & 1) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 4) ? dz : -dz);
+        if (sc > best) { best = sc; bc = c; bs = s; }
+      }
+    }
+    slotOf[bc] = bs; childAt[bs] = bc;
+  }
+
+  // ---- allocate children / triangles ----
+  uint32_t numInner = 0, numLeafTris = 0, numLeaves = 0;
+  for (int c = 0; c < nc; c++) { if (inner[c]) numInner++; else { numLeafTris += ctris[c]; numLeaves++; } }
+  const uint32_t childBase = numInner ? atomicAdd(&ctr->nodeCount, numInner) : 0u;
+  const uint32_t triBase = numLeafTris ? atomicAdd(&ctr->triCount, numLeafTris) : 0u;
+  const uint32_t qBase = numInner ? atomicAdd(&ctr->nextCount, numInner) : 0u;
+  if (numLeaves) atomicAdd(&ctr->leafSlots, numLeaves);
+
+  // ---- quantisation grid ----
+  RQNode N;
+  N.p[0] = nlo.x; N.p[1] = nlo.y; N.p[2] = nlo.z;
+  const float ext[3] = {__fsub_ru(nhi.x, nlo.x), __fsub_ru(nhi.y, nlo.y), __fsub_ru(nhi.z, nlo.z)};
+  float inv[3], step[3];
+  for (int a = 0; a < 3; a++) {
+    uint8_t eb = expForExtent(ext[a]);
+    // make sure the far face is representable: ceil(ext / 2^e) <= 255
+    while (eb < 254 && __fmul_ru(ext[a], __uint_as_float((uint32_t)(254 - eb) << 23)) > 255.0f) eb++;
+    N.e[a] = eb;
+    step[a] = __uint_as_float((uint32_t)eb << 23);             // 2^(eb-127)
+    inv[a] = __uint_as_float((uint32_t)(254 - eb) << 23);       // 2^(127-eb)
+  }
+  N.imask = 0; N.childBase = childBase; N.triBase = triBase;
+  for (int s = 0; s < 8; s++) {
+    N.meta[s] = 0;
+    for (int a = 0; a < 3; a++) { N.qlo[a][s] = 255; N.qhi[a][s] = 0; }
+  }
+  uint32_t innerRank = 0, triOff = 0;
+  double sahInnerQ = 0, sahLeafQ = 0, sahInnerX = 0, sahLeafX = 0;
+  for (int s = 0; s < 8; s++) {
+    const int c = childAt[s];
+    if (c < 0) continue;
+    float dq[3];
+    for (int a = 0; a < 3; a++) {
+      // floor / ceil with directed rounding: decoded box always contains the exact one
+      float fl = floorf(__fmul_rd(__fsub_rd(clo[c][a], N.p[a]), inv[a]));
+      float fh = ceilf(__fmul_ru(__fsub_ru(chi[c][a], N.p[a]), inv[a]));
+      fl = fminf(fmaxf(fl, 0.f), 255.f); fh = fminf(fmaxf(fh, 0.f), 255.f);
+      N.qlo[a][s] = (uint8_t)fl; N.qhi[a][s] = (uint8_t)fh;
+      dq[a] = (fh - fl) * step[a];
+    }
+    const double Aq = (double)halfArea(dq[0], dq[1], dq[2]);
+    const double Ax = (double)halfArea(chi[c][0] - clo[c][0], chi[c][1] - clo[c][1], chi[c][2] - clo[c][2]);
+    if (inner[c]) {
+      N.imask |= (uint8_t)(1u << s);
+      N.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
+      nextQueue[qBase + innerRank] = make_uint2(child[c], childBase + innerRank);
+      nextParentOf[qBase + innerRank] = w;
+      innerRank++;
+      sahInnerQ += Aq; sahInnerX += Ax;
+    } else {
+      const uint32_t nt = ctris[c];                           // 1..3
+      N.meta[s] = (uint8_t)((((1u << nt) - 1u) << 5) | triOff);
+      const uint32_t first = child[c] >= firstLeaf ? child[c] - firstLeaf : t.rangeFirst[child[c]];
+      for (uint32_t j = 0; j < nt; j++) {
+        const float4* src = (const float4*)(trisIn + vals[first + j]);
+        float4* dst = (float4*)(trisOut + triBase + triOff + j);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+      }
+      triOff += nt;
+      sahLeafQ += Aq * (double)((nt + 3) / 4); sahLeafX += Ax * (double)((nt + 3) / 4);
+    }
+  }
+  N.lo[0] = nlo.x; N.lo[1] = nlo.y; N.lo[2] = nlo.z; N.hi[0] = nhi.x; N.hi[1] = nhi.y; N.hi[2] = nhi.z;
+  N.parent = parentOf ? parentOf[q] : RQ_INVALID;
+  N.numTris = __float_as_uint(nhi.w); N.level = level; N.pad[0] = N.pad[1] = N.pad[2] = 0;
+  {
+    const uint4* s4 = (const uint4*)&N; uint4* d4 = (uint4*)(nodes + w);
+    #pragma unroll
+    for (int i = 0; i < 8; i++) d4[i] = s4[i];
+  }
+  if (level == 0) { sahInnerQ += (double)nlo.w; sahInnerX += (double)nlo.w; }   // the root's own box
+  sahOut[0] = sahInnerQ; sahOut[1] = sahLeafQ; sahOut[2] = sahInnerX; sahOut[3] = sahLeafX;
+}
+
+__global__ void __launch_bounds__(128)
+k_emit(B2 t, int n, const uint2* __restrict__ queue, uint32_t count, uint2* __restrict__ nextQueue,
+       EmitCounters* ctr, RQNode* __restrict__ nodes, RQTri* __restrict__ trisOut,
+       const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals, uint32_t level,
+       const uint32_t* __restrict__ parentOf /* wide parent per queue entry */, uint32_t* __restrict__ nextParentOf) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  if (q < count)
+    emit_one(t, n, q, queue, nextQueue, ctr, nodes, trisOut, trisIn, vals, level, parentOf, nextParentOf, s);
+  #pragma unroll
+  for (int k = 0; k < 4; k++)
+    for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&ctr->sahInnerQ, s[0]); atomicAdd(&ctr->sahLeafQ, s[1]);
+    atomicAdd(&ctr->sahInnerX, s[2]); atomicAdd(&ctr->sahLeafX, s[3]);
+  }
+}
+
+__global__ void k_empty_root(RQNode* nodes) {                 // scene without valid triangles
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    RQNode N;
+    memset(&N, 0, sizeof(N));
+    N.e[0] = N.e[1] = N.e[2] = 1; N.parent = RQ_INVALID;
+    for (int s = 0; s < 8; s++) for (int a = 0; a < 3; a++) { N.qlo[a][s] = 255; N.qhi[a][s] = 0; }
+    nodes[0] = N;
+  }
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+inline unsigned blocksFor(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+void rqFreeImage(RQDeviceImage* img) {
+  if (img && img->base) { cudaFree(img->base); img->base = nullptr; }
+}
+
+int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const RQBuildParams* params,
+               rqStream stream_, RQDeviceImage* out, RQBuildStats* stats) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int err = 0;
+  RQBuildParams P = {1.0f, 0.3f, 3, 0};
+  if (params) P = *params;
+  if (P.maxLeafTris < 1) P.maxLeafTris = 1;
+  if (P.maxLeafTris > 3) P.maxLeafTris = 3;
+
+  uint64_t total = 0;
+  std::vector<RQGeomDesc> hg(geoms, geoms + numGeoms);
+  for (auto& g : hg) { g.primBase = (uint32_t)total; total += g.numTris; }
+  if (total >= 0x7FFFFFF0ull) return (int)cudaErrorInvalidValue;
+  const uint32_t N = (uint32_t)total;
+
+  cudaEvent_t ev[7]; for (auto& e : ev) e = nullptr;
+  DevBuf<RQGeomDesc> dGeoms; DevBuf<RQTri> trisIn, trisOut; DevBuf<uint64_t> keys0, keys1;
+  DevBuf<uint32_t> vals0, vals1, hist, digitTotal, left, right, parent, rangeFirst, flag, dec, qParent0, qParent1;
+  DevBuf<float4> blo, bhi; DevBuf<float> cost; DevBuf<uint2> queue0, queue1; DevBuf<RQNode> nodes;
+  DevBuf<Bounds12> dBounds; DevBuf<uint32_t> dInvalid; DevBuf<EmitCounters> dCtr;
+  Bounds12 hb; uint32_t hInvalid = 0; EmitCounters hc;
+  uint32_t n = 0, depth = 0, numNodes = 1, numTris = 0;
+  RQImageHeader H;
+  void* image = nullptr;
+  memset(&hc, 0, sizeof(hc));
+  memset(&H, 0, sizeof(H));
+
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(ev[0], stream));
+  CK(dBounds.alloc(1)); CK(dInvalid.alloc(1)); CK(dCtr.alloc(1));
+  for (int k = 0; k < 3; k++) { hb.sceneLo[k] = hb.centLo[k] = 0xFFFFFFFFu; hb.sceneHi[k] = hb.centHi[k] = 0u; }
+  CK(cudaMemcpyAsync(dBounds.p, &hb, sizeof(hb), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemsetAsync(dInvalid.p, 0, 4, stream));
+
+  if (N > 0) {
+    CK(dGeoms.alloc(numGeoms));
+    CK(cudaMemcpyAsync(dGeoms.p, hg.data(), sizeof(RQGeomDesc) * numGeoms, cudaMemcpyHostToDevice, stream));
+    CK(trisIn.alloc(N)); CK(keys0.alloc(N)); CK(keys1.alloc(N)); CK(vals0.alloc(N)); CK(vals1.alloc(N));
+    k_setup_prims<<<blocksFor(N, 256), 256, 0, stream>>>(dGeoms.p, numGeoms, N, trisIn.p, dBounds.p, dInvalid.p);
+    k_morton<<<blocksFor(N, 256), 256, 0, stream>>>(trisIn.p, N, dBounds.p, keys0.p, vals0.p);
+    rqCountLaunch(2);
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(ev[1], stream));
+
+  if (N > 0) {                                                  // ---- radix sort ----
+    const uint32_t numTiles = blocksFor(N, SORT_TILE);
+    CK(hist.alloc((size_t)256 * numTiles)); CK(digitTotal.alloc(256));
+    uint64_t *kin = keys0.p, *kout = keys1.p; uint32_t *vin = vals0.p, *vout = vals1.p;
+    for (int pass = 0; pass < 8; pass++) {
+      const int shift = pass * 8;
+      k_sort_hist<<<numTiles, SORT_THREADS, 0, stream>>>(kin, N, shift, numTiles, hist.p);
+      k_sort_scan_rows<<<256, 256, 0, stream>>>(hist.p, numTiles, digitTotal.p);
+      k_sort_scan_digits<<<1, 256, 0, stream>>>(digitTotal.p);
+      k_sort_scatter<<<numTiles, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, N, shift, numTiles, hist.p, digitTotal.p);
+      rqCountLaunch(4);
+      std::swap(kin, kout); std::swap(vin, vout);
+    }
+    CK(cudaGetLastError());
+    // 8 passes: result is back in keys0/vals0
+  }
+  CK(cudaEventRecord(ev[2], stream));
+  CK(cudaMemcpyAsync(&hInvalid, dInvalid.p, 4, cudaMemcpyDeviceToHost, stream));
+  CK(cudaMemcpyAsync(&hb, dBounds.p, sizeof(hb), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  n = N - hInvalid;
+
+  {                                                             // ---- hierarchy + refit ----
+    B2 t; memset(&t, 0, sizeof(t));
+    const size_t n2 = n ? 2 * (size_t)n - 1 : 1;
+    CK(nodes.alloc(n ? (size_t)n : 1));
+    if (n > 0) {
+      CK(blo.alloc(n2)); CK(bhi.alloc(n2)); CK(cost.alloc(n2 * 8)); CK(dec.alloc(n2));
+      CK(left.alloc(n)); CK(right.alloc(n)); CK(parent.alloc(n2)); CK(rangeFirst.alloc(n)); CK(flag.alloc(n));
+      CK(trisOut.alloc(n)); CK(queue0.alloc(n)); CK(queue1.alloc(n)); CK(qParent0.alloc(n)); CK(qParent1.alloc(n));
+      t.lo = blo.p; t.hi = bhi.p; t.cost = cost.p; t.dec = dec.p; t.left = left.p; t.right = right.p;
+      t.parent = parent.p; t.rangeFirst = rangeFirst.p; t.flag = flag.p;
+      CK(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t) * n, stream));
+      CK(cudaMemsetAsync(parent.p, 0xFF, sizeof(uint32_t) * n2, stream));
+      if (n > 1) { k_hierarchy<<<blocksFor(n - 1, 256), 256, 0, stream>>>(keys0.p, (int)n, left.p, right.p, parent.p, rangeFirst.p); rqCountLaunch(1); }
+      CK(cudaEventRecord(ev[3], stream));
+      k_refit_dp<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costNode, P.costTri, P.maxLeafTris);
+      rqCountLaunch(1);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(ev[4], stream));
+
+      // ---- emission, level by level ----
+      hc.nodeCount = 1;
+      CK(cudaMemcpyAsync(dCtr.p, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream));
+      const uint2 rootEntry = make_uint2(n > 1 ? 0u : 0u /* n==1: node 0 is the leaf */, 0u);
+      CK(cudaMemcpyAsync(queue0.p, &rootEntry, sizeof(uint2), cudaMemcpyHostToDevice, stream));
+      uint2 *qin = queue0.p, *qout = queue1.p; uint32_t *pin = qParent0.p, *pout = qParent1.p;
+      uint32_t count = 1;
+      while (count > 0) {
+        k_emit<<<blocksFor(count, 128), 128, 0, stream>>>(t, (int)n, qin, count, qout, dCtr.p, nodes.p, trisOut.p,
+                                                       trisIn.p, vals0.p, depth, depth ? pin : nullptr, pout);
+        rqCountLaunch(1);
+        CK(cudaMemcpyAsync(&hc, dCtr.p, sizeof(hc), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        count = hc.nextCount;
+        depth++;
+        if (count) CK(cudaMemsetAsync(&dCtr.p->nextCount, 0, 4, stream));
+        std::swap(qin, qout); std::swap(pin, pout);
+        if (depth > 200) { err = (int)cudaErrorUnknown; goto fail; }
+      }
+      numNodes = hc.nodeCount; numTris = hc.triCount;
+    } else {
+      CK(cudaEventRecord(ev[3], stream)); CK(cudaEventRecord(ev[4], stream));
+      k_empty_root<<<1, 32, 0, stream>>>(nodes.p); rqCountLaunch(1);
+      depth = 1; numNodes = 1; numTris = 0;
+    }
+    CK(cudaEventRecord(ev[5], stream));
+  }
+
+  {                                                             // ---- final image ----
+    H.magic = RQ_IMAGE_MAGIC; H.numNodes = numNodes; H.numTris = numTris; H.depth = depth; H.flags = sceneFlags;
+    for (int k = 0; k < 3; k++) {
+      H.lo[k] = n ? ord2f(hb.sceneLo[k]) : INFINITY; H.hi[k] = n ? ord2f(hb.sceneHi[k]) : -INFINITY;
+    }
+    H.lo[3] = H.hi[3] = 0.f;
+    H.nodesOffset = 128;
+    H.trisOffset = H.nodesOffset + (uint64_t)numNodes * sizeof(RQNode);
+    H.totalBytes = (H.trisOffset + (uint64_t)numTris * sizeof(RQTri) + 127ull) & ~127ull;
+    const double rootA = n ? (double)halfArea(H.hi[0] - H.lo[0], H.hi[1] - H.lo[1], H.hi[2] - H.lo[2]) : 0.0;
+    H.sah = rootA > 0 ? (hc.sahInnerQ + hc.sahLeafQ) / rootA : 0.0;
+    CK(cudaMalloc(&image, H.totalBytes));
+    CK(cudaMemsetAsync(image, 0, H.totalBytes, stream));
+    CK(cudaMemcpyAsync(image, &H, sizeof(H), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync((char*)image + H.nodesOffset, nodes.p, (size_t)numNodes * sizeof(RQNode), cudaMemcpyDeviceToDevice, stream));
+    if (numTris) CK(cudaMemcpyAsync((char*)image + H.trisOffset, trisOut.p, (size_t)numTris * sizeof(RQTri), cudaMemcpyDeviceToDevice, stream));
+    CK(cudaEventRecord(ev[6], stream));
+    CK(cudaStreamSynchronize(stream));
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->numPrimsIn = N; stats->numPrimsValid = n; stats->numNodes = numNodes; stats->numTris = numTris;
+      stats->depth = depth; stats->numLeaves = hc.leafSlots; stats->sah = H.sah;
+      stats->sahExact = rootA > 0 ? (hc.sahInnerX + hc.sahLeafX) / rootA : 0.0;
+      stats->bytes = H.totalBytes;
+      cudaEventElapsedTime(&stats->msTotal, ev[0], ev[6]);
+      cudaEventElapsedTime(&stats->msPrims, ev[0], ev[1]);
+      cudaEventElapsedTime(&stats->msSort, ev[1], ev[2]);
+      cudaEventElapsedTime(&stats->msHierarchy, ev[2], ev[3]);
+      cudaEventElapsedTime(&stats->msRefit, ev[3], ev[4]);
+      cudaEventElapsedTime(&stats->msEmit, ev[4], ev[6]);
+    }
+    out->base = image; out->header = H; image = nullptr;
+  }
+  for (auto& e : ev) if (e) cudaEventDestroy(e);
+  return 0;
+
+fail:
+  for (auto& e : ev) if (e) cudaEventDestroy(e);
+  if (image) cudaFree(image);
+  cudaGetLastError();
+  return err ? err : (int)cudaErrorUnknown;
+}

@@ -1,0 +1,61 @@
+// Internal interface between the host API (api_*.cpp) and the CUDA side (rq_build.cu, rq_trace.cu).
+// Plain functions, plain pointers; every function returns a cudaError_t-compatible int (0 = ok).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "rq_types.h"
+
+typedef struct CUstream_st* rqStream;
+
+struct RQBuildParams {
+  float costNode;        // SAH cost of visiting one 8-wide node           (default 1.0)
+  float costTri;         // SAH cost of testing one triangle               (default 0.3)
+  int   maxLeafTris;     // triangles per leaf slot, 1..3                  (default 3)
+  int   verbose;
+};
+
+// A committed BVH living in device memory: one allocation, header first.
+struct RQDeviceImage {
+  void*         base;       // device pointer to the image (RQImageHeader at offset 0)
+  RQImageHeader header;     // host copy of the header
+};
+
+// Builds the BVH for the given meshes on `stream` (geoms is a HOST array whose index/vertex
+// pointers must be device-readable).  On success *out owns a new device allocation.
+int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const RQBuildParams* params,
+               rqStream stream, RQDeviceImage* out, RQBuildStats* stats);
+void rqFreeImage(RQDeviceImage* img);
+
+// Ray-stream kernels.  `rays` is device-readable AoS memory: RTCRayHit (intersect) or RTCRay
+// (occluded) records `stride` bytes apart.  instID0 is written to hit.instID[0] on a hit.
+struct RQTraceArgs {
+  const void* image;       // device image base
+  uint64_t    nodesOffset; // header.nodesOffset / header.trisOffset
+  uint64_t    trisOffset;
+  uint32_t    depth;       // header.depth
+  uint32_t    robust;      // 1 = Pluecker (RTC_SCENE_FLAG_ROBUST), 0 = Moeller-Trumbore
+  void*       rays;
+  uint32_t    numRays;
+  size_t      stride;
+  uint32_t    instID0;
+  uint32_t    streamSemantics;  // occluded only: 1 = stream entry rules (M>1), 0 = single-ray rules
+  RQTraceCounters* counters;    // device pointer or NULL (NULL = fast kernel)
+  unsigned int* workCounter;    // device scratch word (zeroed by the launcher)
+};
+int rqLaunchIntersect(const RQTraceArgs* a, rqStream stream);
+int rqLaunchOccluded(const RQTraceArgs* a, rqStream stream);
+
+// Layout adapters for the non-AoS entry points (SoA packets / pointer streams): gather into a
+// dense AoS scratch buffer, trace, scatter results back.
+struct RQSoAView {              // device-readable field pointers, element i at ptr[i]
+  float *org_x, *org_y, *org_z, *tnear, *dir_x, *dir_y, *dir_z, *time, *tfar;
+  unsigned int *mask, *id, *flags;
+  float *Ng_x, *Ng_y, *Ng_z, *u, *v;
+  unsigned int *primID, *geomID, *instID0;
+};
+int rqGatherSoA(const RQSoAView* v, const int* valid, uint32_t n, void* aosRayHit, rqStream stream);
+int rqScatterSoA(const RQSoAView* v, uint32_t n, const void* aosRayHit, int occluded, rqStream stream);
+
+// Number of kernel launches issued by this library since load (bench.py's gpu_launches claim).
+unsigned long long rqLaunchCount(void);
+void rqCountLaunch(unsigned n);

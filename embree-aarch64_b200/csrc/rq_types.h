@@ -1,0 +1,108 @@
+// Device-resident data layout of the committed scene (plain PODs shared by host C++ and CUDA).
+//
+// What these replace in the reference (read-only, /root/reference):
+//   RQNode  <- AABBNode_t<NodeRef,8> (256 B, kernels/bvh/bvh_node_aabb.h:199-206) and
+//              QuantizedNode_t (136 B, kernels/bvh/bvh_node_qaabb.h:120-205)
+//   RQTri   <- TriangleM<4> / TriangleMv<4> leaf blocks (176 B per 4 triangles,
+//              kernels/geometry/triangle.h:13-161, trianglev.h)
+//   the flat, offset-based image replaces the pointer-based BVHN<8> (kernels/bvh/bvh.h:41-231)
+#pragma once
+#include <stdint.h>
+
+#define RQ_INVALID 0xFFFFFFFFu
+
+// One 8-wide node = one 128-byte, 128-byte-aligned line.
+// Traversal reads only the first 80 bytes (five 16-byte loads, three 32-byte sectors):
+//   child box k, axis a:  lo = p[a] + qlo[a][k] * 2^(e[a]-127),  hi = p[a] + qhi[a][k] * 2^(e[a]-127)
+//   (floor/ceil quantised: the decoded box always contains the exact child box)
+// meta[k]: 0 = empty slot
+//          inner child: 0b001sssss with sssss = 24 + k
+//          leaf child : high 3 bits = unary triangle count (001,011,111 = 1,2,3),
+//                       low 5 bits = offset of its first triangle relative to triBase (0..23)
+// inner child k lives at node index childBase + popcount(imask & ((1<<k)-1)).
+// The remaining 48 bytes are "cold": exact bounds and bookkeeping for statistics / refit.
+struct alignas(128) RQNode {
+  float    p[3];            //  0  origin of the quantisation grid (= exact lower corner)
+  uint8_t  e[3];            // 12  biased exponents of the grid step per axis
+  uint8_t  imask;           // 15  bit k set <=> slot k holds an inner node
+  uint32_t childBase;       // 16
+  uint32_t triBase;         // 20
+  uint8_t  meta[8];         // 24
+  uint8_t  qlo[3][8];       // 32  qlo[axis][slot]
+  uint8_t  qhi[3][8];       // 56
+  // ---- cold part (never touched by traversal) ----
+  float    lo[3];           // 80  exact fp32 bounds of this node
+  float    hi[3];           // 92
+  uint32_t parent;          // 104 parent node index, RQ_INVALID for the root
+  uint32_t numTris;         // 108 triangles below this node
+  uint32_t level;           // 112 depth (root = 0)
+  uint32_t pad[3];          // 116
+};
+static_assert(sizeof(RQNode) == 128, "RQNode must be one 128-byte line");
+
+// One triangle = 48 bytes = three 16-byte loads.  Vertices are stored verbatim (fp32 bits of the
+// user's vertex buffer) so that e1 = v0-v1, e2 = v2-v0, Ng = cross(e2,e1) reproduce the reference's
+// precomputed TriangleM<4>::e1/e2 bit for bit (triangle.h:45-51) and the watertight test can use
+// v0,v1,v2 directly (trianglev.h).
+struct alignas(16) RQTri {
+  float    v0[3];
+  float    v1[3];
+  float    v2[3];
+  uint32_t primID;
+  uint32_t geomID;
+  uint32_t pad;
+};
+static_assert(sizeof(RQTri) == 48, "RQTri must be 48 bytes");
+
+// One triangle mesh as the builder sees it (device-readable pointers, arbitrary 4-byte-multiple strides).
+struct RQGeomDesc {
+  const uint8_t* indices;    // RTC_FORMAT_UINT3 records
+  const uint8_t* vertices;   // RTC_FORMAT_FLOAT3 records
+  uint32_t indexStride;
+  uint32_t vertexStride;
+  uint32_t numTris;
+  uint32_t numVerts;
+  uint32_t primBase;         // first global primitive number of this mesh
+  uint32_t geomID;
+};
+
+// Flat image of a committed BVH: header + nodes + triangles, all offset based, so a byte copy
+// (cudaMemcpyPeer / NCCL broadcast) yields a usable replica on another GPU.
+struct RQImageHeader {
+  uint64_t magic;            // 'RQB200v1'
+  uint32_t numNodes;
+  uint32_t numTris;
+  uint32_t depth;            // levels of 8-wide nodes (stack bound)
+  uint32_t flags;            // RTCSceneFlags the scene was committed with
+  float    lo[4];
+  float    hi[4];
+  uint64_t nodesOffset;      // byte offsets from the start of the image (128-aligned)
+  uint64_t trisOffset;
+  uint64_t totalBytes;
+  double   sah;              // SAH cost, reference formula (bvh_statistics.h:36-38,99-101)
+  uint64_t pad[5];
+};
+static_assert(sizeof(RQImageHeader) == 128, "header is one line");
+#define RQ_IMAGE_MAGIC 0x3176303032425152ull
+
+struct RQBuildStats {
+  uint32_t numPrimsIn;       // triangles submitted
+  uint32_t numPrimsValid;    // after dropping out-of-range indices / non-finite vertices
+  uint32_t numNodes;
+  uint32_t numTris;
+  uint32_t depth;
+  uint32_t numLeaves;        // leaf slots
+  double   sah;              // reference formula on de-quantised boxes
+  double   sahExact;         // same with the exact fp32 child boxes
+  float    msTotal, msPrims, msSort, msHierarchy, msRefit, msEmit;
+  uint64_t bytes;
+};
+
+// Per-call traversal counters (instrumented kernel variant only).
+struct RQTraceCounters {
+  unsigned long long rays;        // active rays traced
+  unsigned long long nodes;       // 8-wide node records fetched
+  unsigned long long tris;        // triangle records fetched
+  unsigned long long hits;        // rays that report a hit / are occluded
+  unsigned long long stackMax;    // deepest traversal stack seen
+};

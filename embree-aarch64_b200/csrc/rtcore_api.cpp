@@ -1,0 +1,954 @@
+// Host side of the drop-in boundary: the rtc* C entry points of include/embree3/rtcore.h and the
+// small object model behind them.  Mirrors, for the triangle / ray-stream path only, the reference's
+//   kernels/common/rtcore.cpp      (entry points, RTC_CATCH error convention: rtcore.h:28-54)
+//   kernels/common/device.cpp      (config string, first-error-wins slot + callback: :258-316)
+//   kernels/common/scene.cpp       (bind/detach with lowest-free geomID: :595-653, commit: :655-913)
+//   kernels/common/geometry.cpp    (MODIFIED/COMMITTED state: :80-107)
+//   kernels/common/scene_triangle_mesh.cpp (buffer rules: :35-80)
+// All computation happens in CUDA (rq_build.cu, rq_trace.cu); there is no CPU fallback: without a
+// usable CUDA device rtcNewDevice fails.
+#define RTC_EXPORT_API
+#include "../../include/rq_b200.h"
+#include "rq_device.h"
+
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <new>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct rtc_error : public std::exception {
+  RTCError code; std::string msg;
+  rtc_error(RTCError c, const std::string& m) : code(c), msg(m) {}
+  const char* what() const noexcept override { return msg.c_str(); }
+};
+[[noreturn]] void fail(RTCError c, const char* m) { throw rtc_error(c, m); }
+
+void cudaCheck(int e, const char* what) {
+  if (e == 0) return;
+  const cudaError_t ce = (cudaError_t)e;
+  cudaGetLastError();
+  std::string m = std::string("CUDA error in ") + what + ": " + cudaGetErrorString(ce);
+  throw rtc_error(ce == cudaErrorMemoryAllocation ? RTC_ERROR_OUT_OF_MEMORY : RTC_ERROR_UNKNOWN, m);
+}
+
+thread_local RTCError g_threadError = RTC_ERROR_NONE;
+std::mutex g_apiMutex;                                   // device create/retain/release (rtcore.cpp:20-36)
+
+struct RefCounted {
+  std::atomic<long> refs{1};
+  virtual ~RefCounted() {}
+  void retain() { refs.fetch_add(1); }
+  void release() { if (refs.fetch_sub(1) == 1) delete this; }
+};
+
+// --------------------------------------------------------------------------------------------
+struct Device : RefCounted {
+  int ordinal = 0;
+  bool hasGpu = false;
+  int verbose = 0, benchmark = 0, async = 0;
+  size_t chunkRays = 1u << 20;
+  RQBuildParams build{1.0f, 0.3f, 3, 0};
+  cudaStream_t ownStream = nullptr, userStream = nullptr;
+  std::mutex errMutex;
+  RTCError error = RTC_ERROR_NONE;
+  RTCErrorFunction errFn = nullptr; void* errPtr = nullptr;
+  RTCMemoryMonitorFunction memFn = nullptr; void* memPtr = nullptr;
+  // staging for host-resident ray streams: a small ring of (stream, device buffer) pairs
+  static const int kRing = 4;
+  std::mutex stageMutex;
+  cudaStream_t ringStream[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  void* ringBuf[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  size_t ringCap[kRing] = {0, 0, 0, 0};
+  RQTraceCounters* dCounters = nullptr;
+
+  cudaStream_t stream() const { return userStream ? userStream : ownStream; }
+  void bind() const { if (hasGpu) cudaSetDevice(ordinal); }
+
+  ~Device() override {
+    if (hasGpu) {
+      cudaSetDevice(ordinal);
+      for (int i = 0; i < kRing; i++) { if (ringBuf[i]) cudaFree(ringBuf[i]); if (ringStream[i]) cudaStreamDestroy(ringStream[i]); }
+      if (dCounters) cudaFree(dCounters);
+      if (ownStream) cudaStreamDestroy(ownStream);
+    }
+  }
+};
+
+void processError(Device* dev, RTCError code, const char* msg) {
+  if (dev) {
+    if (dev->verbose >= 1) fprintf(stderr, "b200-rayquery error %d: %s\n", (int)code, msg);
+    RTCErrorFunction fn; void* p;
+    {
+      std::lock_guard<std::mutex> l(dev->errMutex);
+      if (dev->error == RTC_ERROR_NONE) dev->error = code;      // first error wins (device.cpp:258-271)
+      fn = dev->errFn; p = dev->errPtr;
+    }
+    if (fn) fn(p, code, msg);
+  } else {
+    if (g_threadError == RTC_ERROR_NONE) g_threadError = code;
+  }
+}
+
+#define RTC_TRY try {
+#define RTC_CATCH(dev)                                                                              \
+  } catch (const rtc_error& e) { processError((dev), e.code, e.what());                             \
+  } catch (const std::bad_alloc&) { processError((dev), RTC_ERROR_OUT_OF_MEMORY, "out of memory");  \
+  } catch (const std::exception& e) { processError((dev), RTC_ERROR_UNKNOWN, e.what());             \
+  } catch (...) { processError((dev), RTC_ERROR_UNKNOWN, "unknown exception caught"); }
+#define VERIFY_HANDLE(h) do { if ((h) == nullptr) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid argument"); } while (0)
+
+// key=value[,key=value...] -- same grammar as the reference's device config (state.cpp:256-449);
+// unknown keys are ignored like the reference ignores keys of disabled features.
+void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
+  if (!cfg) return;
+  std::string s(cfg);
+  size_t i = 0;
+  while (i < s.size()) {
+    size_t j = s.find_first_of(", \t\n", i);
+    if (j == std::string::npos) j = s.size();
+    std::string tok = s.substr(i, j - i);
+    i = j + 1;
+    size_t eq = tok.find('=');
+    if (tok.empty() || eq == std::string::npos) continue;
+    const std::string k = tok.substr(0, eq), v = tok.substr(eq + 1);
+    if (k == "verbose") d->verbose = atoi(v.c_str());
+    else if (k == "benchmark") d->benchmark = atoi(v.c_str());
+    else if (k == "gpu") d->ordinal = atoi(v.c_str());
+    else if (k == "async") d->async = atoi(v.c_str());
+    else if (k == "chunk_rays") d->chunkRays = (size_t)std::max(1024ll, atoll(v.c_str()));
+    else if (k == "cost_node") d->build.costNode = (float)atof(v.c_str());
+    else if (k == "cost_tri") d->build.costTri = (float)atof(v.c_str());
+    else if (k == "leaf_tris") d->build.maxLeafTris = atoi(v.c_str());
+    else if (k == "allow_no_gpu") *allowNoGpu = atoi(v.c_str()) != 0;
+  }
+  d->build.verbose = d->verbose;
+}
+
+// --------------------------------------------------------------------------------------------
+struct Buffer : RefCounted {
+  Device* dev; char* ptr; size_t bytes; bool shared;
+  Buffer(Device* d, size_t n, void* sharedPtr) : dev(d), ptr((char*)sharedPtr), bytes(n), shared(sharedPtr != nullptr) {
+    dev->retain();
+    if (!shared) {
+      if (dev->memFn && !dev->memFn(dev->memPtr, (ssize_t)bytes, false)) { dev->release(); fail(RTC_ERROR_OUT_OF_MEMORY, "memory monitor forced termination"); }
+      if (posix_memalign((void**)&ptr, 64, bytes ? bytes : 64) != 0) { dev->release(); throw std::bad_alloc(); }
+    }
+  }
+  ~Buffer() override {
+    if (!shared) { free(ptr); if (dev->memFn) dev->memFn(dev->memPtr, -(ssize_t)bytes, true); }
+    dev->release();
+  }
+};
+
+struct BufferView {
+  Buffer* buf = nullptr; size_t offset = 0, stride = 0; unsigned count = 0; RTCFormat format = RTC_FORMAT_UNDEFINED;
+  void set(Buffer* b, size_t off, size_t st, unsigned n, RTCFormat f) {
+    b->retain(); if (buf) buf->release();
+    buf = b; offset = off; stride = st; count = n; format = f;
+  }
+  void clear() { if (buf) buf->release(); buf = nullptr; }
+  const char* data() const { return buf ? buf->ptr + offset : nullptr; }
+};
+
+struct Geometry : RefCounted {
+  Device* dev; RTCGeometryType type;
+  BufferView vertices, indices;
+  bool committed = false, enabled = true;
+  unsigned modCounter = 0, mask = 0xFFFFFFFFu;
+  void* userPtr = nullptr;
+  RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
+  Geometry(Device* d, RTCGeometryType t) : dev(d), type(t) { dev->retain(); }
+  ~Geometry() override { vertices.clear(); indices.clear(); dev->release(); }
+  void update() { ++modCounter; committed = false; }
+};
+
+struct Scene : RefCounted {
+  Device* dev;
+  std::mutex geomMutex, buildMutex;
+  std::vector<Geometry*> geoms;                          // index = geomID
+  std::set<unsigned> freeIDs; unsigned nextID = 0;       // lowest-free-first (common/sys/alloc.h:100-125)
+  std::vector<unsigned> seenMod;
+  RTCSceneFlags flags = RTC_SCENE_FLAG_NONE; RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
+  bool modified = true, everCommitted = false;
+  RQDeviceImage image{nullptr, {}};
+  RQBuildStats stats{};
+  RTCProgressMonitorFunction progress = nullptr; void* progressPtr = nullptr;
+  explicit Scene(Device* d) : dev(d) { dev->retain(); memset(&stats, 0, sizeof(stats)); }
+  ~Scene() override {
+    for (Geometry* g : geoms) if (g) g->release();
+    if (image.base) { dev->bind(); rqFreeImage(&image); }
+    dev->release();
+  }
+};
+
+bool isDevicePointer(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+struct TempDev {                                         // device copies of host geometry buffers, freed after the build
+  std::vector<void*> ptrs;
+  ~TempDev() { for (void* p : ptrs) cudaFree(p); }
+  const uint8_t* upload(const char* src, size_t bytes, cudaStream_t s) {
+    void* d = nullptr;
+    cudaCheck(cudaMalloc(&d, bytes ? bytes : 16), "geometry upload (alloc)");
+    ptrs.push_back(d);
+    if (bytes) cudaCheck(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s), "geometry upload (copy)");
+    return (const uint8_t*)d;
+  }
+};
+
+void commitScene(Scene* sc) {
+  Device* dev = sc->dev;
+  std::unique_lock<std::mutex> lock(sc->buildMutex);     // one committer at a time; joiners simply wait
+  {
+    std::lock_guard<std::mutex> gl(sc->geomMutex);
+    bool changed = sc->modified || !sc->everCommitted;
+    if (sc->seenMod.size() != sc->geoms.size()) { sc->seenMod.resize(sc->geoms.size(), 0xFFFFFFFFu); changed = true; }
+    for (size_t i = 0; i < sc->geoms.size(); i++) {
+      Geometry* g = sc->geoms[i];
+      if (!g) continue;
+      if (g->enabled && !g->committed) fail(RTC_ERROR_INVALID_OPERATION, "geometry not committed");   // geometry.cpp:103-107
+      if (g->modCounter != sc->seenMod[i]) changed = true;
+    }
+    if (!changed) return;
+  }
+  if (!dev->hasGpu) fail(RTC_ERROR_UNKNOWN, "no CUDA device: cannot build (there is no CPU fallback)");
+  dev->bind();
+  cudaStream_t s = dev->stream();
+  if (sc->progress && !sc->progress(sc->progressPtr, 0.0)) fail(RTC_ERROR_CANCELLED, "progress monitor forced termination");
+
+  std::vector<RQGeomDesc> descs;
+  TempDev tmp;
+  {
+    std::lock_guard<std::mutex> gl(sc->geomMutex);
+    for (size_t i = 0; i < sc->geoms.size(); i++) {
+      Geometry* g = sc->geoms[i];
+      if (!g) continue;
+      sc->seenMod[i] = g->modCounter;
+      if (!g->enabled || g->indices.count == 0) continue;
+      RQGeomDesc d; memset(&d, 0, sizeof(d));
+      const char* ip = g->indices.data(); const char* vp = g->vertices.data();
+      const size_t ibytes = (size_t)(g->indices.count - 1) * g->indices.stride + 12;
+      const size_t vbytes = g->vertices.count ? (size_t)(g->vertices.count - 1) * g->vertices.stride + 12 : 0;
+      d.indices = isDevicePointer(ip) ? (const uint8_t*)ip : tmp.upload(ip, ibytes, s);
+      d.vertices = (vp && isDevicePointer(vp)) ? (const uint8_t*)vp : tmp.upload(vp, vbytes, s);
+      d.indexStride = (uint32_t)g->indices.stride; d.vertexStride = (uint32_t)g->vertices.stride;
+      d.numTris = g->indices.count; d.numVerts = g->vertices.count; d.geomID = (uint32_t)i;
+      descs.push_back(d);
+    }
+  }
+  RQDeviceImage img{nullptr, {}};
+  RQBuildStats st;
+  cudaCheck(rqBuildBVH(descs.data(), (int)descs.size(), (uint32_t)sc->flags, &dev->build, (rqStream)s, &img, &st), "BVH build");
+  if (sc->image.base) rqFreeImage(&sc->image);
+  sc->image = img; sc->stats = st;
+  sc->modified = false; sc->everCommitted = true;
+  if (sc->progress) sc->progress(sc->progressPtr, 1.0);
+  if (dev->benchmark || dev->verbose >= 2) {
+    // same fields as the reference's line (bvh.cpp:173-178): seconds, prims/s, SAH, bytes
+    printf("BENCHMARK_BUILD %g %g %g %llu BVH8q<triangle>.b200\n", st.msTotal * 1e-3, st.numPrimsValid / (st.msTotal * 1e-3 + 1e-12),
+           st.sah, (unsigned long long)st.bytes);
+    fflush(stdout);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// ray-stream dispatch
+// --------------------------------------------------------------------------------------------
+void checkQuery(Scene* sc, RTCIntersectContext* ctx) {
+  if (!sc->everCommitted || sc->modified) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");   // scene.cpp:13,30
+  if (ctx && ctx->filter) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the GPU");
+}
+
+void fillArgs(Scene* sc, RTCIntersectContext* ctx, RQTraceArgs& a, bool stream) {
+  memset(&a, 0, sizeof(a));
+  a.image = sc->image.base; a.nodesOffset = sc->image.header.nodesOffset; a.trisOffset = sc->image.header.trisOffset;
+  a.depth = sc->image.header.depth;
+  a.robust = (sc->flags & RTC_SCENE_FLAG_ROBUST) ? 1u : 0u;
+  a.instID0 = ctx ? ctx->instID[0] : RTC_INVALID_GEOMETRY_ID;
+  a.streamSemantics = stream ? 1u : 0u;
+}
+
+// Trace M records of `stride` bytes at `rays`; occluded selects the any-hit kernel; recBytes is
+// 80 (RTCRayHit) or 48 (RTCRay).  Device-resident memory is traced in place; host memory is staged
+// through a ring of device buffers so copies of one chunk overlap the kernel of another.
+void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, size_t stride, bool occluded,
+                 size_t recBytes, RQTraceCounters* countersOut) {
+  if (M == 0) return;
+  Device* dev = sc->dev;
+  if (!dev->hasGpu) fail(RTC_ERROR_UNKNOWN, "no CUDA device");
+  dev->bind();
+  RQTraceArgs a; fillArgs(sc, ctx, a, M > 1);
+  RQTraceCounters* dC = nullptr;
+  if (countersOut) {
+    std::lock_guard<std::mutex> l(dev->stageMutex);
+    if (!dev->dCounters) cudaCheck(cudaMalloc((void**)&dev->dCounters, sizeof(RQTraceCounters)), "counters");
+    dC = dev->dCounters;
+    cudaCheck(cudaMemsetAsync(dC, 0, sizeof(RQTraceCounters), dev->stream()), "counters");
+    cudaCheck(cudaStreamSynchronize(dev->stream()), "counters");
+  }
+  a.counters = dC;
+  if (isDevicePointer(rays)) {
+    cudaStream_t s = dev->stream();
+    a.rays = rays; a.numRays = M; a.stride = stride;
+    cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
+    if (!dev->async || countersOut) cudaCheck(cudaStreamSynchronize(s), "trace");
+  } else {
+    std::lock_guard<std::mutex> l(dev->stageMutex);     // host-staged calls of one device are serialised
+    const size_t chunk = dev->chunkRays;
+    unsigned done = 0; int slot = 0;
+    while (done < M) {
+      const unsigned n = (unsigned)std::min<size_t>(chunk, M - done);
+      const size_t span = (size_t)(n - 1) * stride + recBytes;
+      const int r = slot % Device::kRing; slot++;
+      if (!dev->ringStream[r]) cudaCheck(cudaStreamCreateWithFlags(&dev->ringStream[r], cudaStreamNonBlocking), "stream");
+      if (dev->ringCap[r] < span) {
+        cudaCheck(cudaStreamSynchronize(dev->ringStream[r]), "staging");
+        if (dev->ringBuf[r]) cudaFree(dev->ringBuf[r]);
+        dev->ringBuf[r] = nullptr; dev->ringCap[r] = 0;
+        cudaCheck(cudaMalloc(&dev->ringBuf[r], span + 256), "staging alloc");
+        dev->ringCap[r] = span;
+      }
+      char* h = (char*)rays + (size_t)done * stride;
+      cudaStream_t s = dev->ringStream[r];
+      cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], h, span, cudaMemcpyHostToDevice, s), "ray upload");
+      a.rays = dev->ringBuf[r]; a.numRays = n; a.stride = stride;
+      cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
+      cudaCheck(cudaMemcpyAsync(h, dev->ringBuf[r], span, cudaMemcpyDeviceToHost, s), "hit download");
+      done += n;
+    }
+    for (int r = 0; r < Device::kRing; r++) if (dev->ringStream[r]) cudaCheck(cudaStreamSynchronize(dev->ringStream[r]), "trace");
+  }
+  if (countersOut) {
+    cudaCheck(cudaDeviceSynchronize(), "counters");
+    cudaCheck(cudaMemcpy(countersOut, dC, sizeof(RQTraceCounters), cudaMemcpyDeviceToHost), "counters");
+  }
+}
+
+// host-side packing for the packet / pointer layouts (rtcore_ray.h:52-251): N lanes -> AoS records
+struct Lane { float *org_x, *org_y, *org_z, *tnear, *dir_x, *dir_y, *dir_z, *time, *tfar; unsigned *mask, *id, *flags;
+              float *Ng_x, *Ng_y, *Ng_z, *u, *v; unsigned *primID, *geomID, *instID; };
+
+void tracePacked(Scene* sc, RTCIntersectContext* ctx, const Lane& L, const int* valid, unsigned N, bool occluded) {
+  std::vector<RTCRayHit> tmp(N);
+  for (unsigned i = 0; i < N; i++) {
+    RTCRayHit& r = tmp[i];
+    const bool ok = valid ? valid[i] != 0 : true;
+    r.ray.org_x = L.org_x[i]; r.ray.org_y = L.org_y[i]; r.ray.org_z = L.org_z[i];
+    r.ray.dir_x = L.dir_x[i]; r.ray.dir_y = L.dir_y[i]; r.ray.dir_z = L.dir_z[i];
+    r.ray.tnear = ok ? L.tnear[i] : INFINITY; r.ray.tfar = ok ? L.tfar[i] : -INFINITY;   // inactive lane
+    r.ray.time = 0.f; r.ray.mask = r.ray.id = r.ray.flags = 0;
+    r.hit.geomID = RTC_INVALID_GEOMETRY_ID;
+  }
+  // packets follow the single-ray entry rules of their lanes
+  Device* dev = sc->dev; (void)dev;
+  traceStream(sc, ctx, tmp.data(), N, sizeof(RTCRayHit), occluded, occluded ? sizeof(RTCRay) : sizeof(RTCRayHit), nullptr);
+  for (unsigned i = 0; i < N; i++) {
+    const RTCRayHit& r = tmp[i];
+    const bool ok = valid ? valid[i] != 0 : true;
+    if (!ok) continue;
+    if (occluded) { if (r.ray.tfar == -INFINITY) L.tfar[i] = -INFINITY; continue; }
+    if (r.hit.geomID == RTC_INVALID_GEOMETRY_ID) continue;
+    L.tfar[i] = r.ray.tfar; L.Ng_x[i] = r.hit.Ng_x; L.Ng_y[i] = r.hit.Ng_y; L.Ng_z[i] = r.hit.Ng_z;
+    L.u[i] = r.hit.u; L.v[i] = r.hit.v; L.primID[i] = r.hit.primID; L.geomID[i] = r.hit.geomID; L.instID[i] = r.hit.instID[0];
+  }
+}
+
+template <typename RayT, typename HitT>
+Lane laneOf(RayT* r, HitT* h) {
+  Lane L;
+  L.org_x = r->org_x; L.org_y = r->org_y; L.org_z = r->org_z; L.tnear = r->tnear; L.dir_x = r->dir_x; L.dir_y = r->dir_y;
+  L.dir_z = r->dir_z; L.time = r->time; L.tfar = r->tfar; L.mask = r->mask; L.id = r->id; L.flags = r->flags;
+  if (h) { L.Ng_x = h->Ng_x; L.Ng_y = h->Ng_y; L.Ng_z = h->Ng_z; L.u = h->u; L.v = h->v; L.primID = h->primID; L.geomID = h->geomID; L.instID = h->instID[0]; }
+  else { L.Ng_x = L.Ng_y = L.Ng_z = L.u = L.v = nullptr; L.primID = L.geomID = L.instID = nullptr; }
+  return L;
+}
+Lane laneOfN(float* base, unsigned N, bool withHit) {     // runtime-N SoA block: field k at word k*N
+  Lane L; unsigned* ub = (unsigned*)base;
+  L.org_x = base; L.org_y = base + N; L.org_z = base + 2 * N; L.tnear = base + 3 * N; L.dir_x = base + 4 * N; L.dir_y = base + 5 * N;
+  L.dir_z = base + 6 * N; L.time = base + 7 * N; L.tfar = base + 8 * N; L.mask = ub + 9 * N; L.id = ub + 10 * N; L.flags = ub + 11 * N;
+  if (withHit) { float* h = base + 12 * N; unsigned* uh = (unsigned*)h;
+    L.Ng_x = h; L.Ng_y = h + N; L.Ng_z = h + 2 * N; L.u = h + 3 * N; L.v = h + 4 * N; L.primID = uh + 5 * N; L.geomID = uh + 6 * N; L.instID = uh + 7 * N; }
+  else { L.Ng_x = L.Ng_y = L.Ng_z = L.u = L.v = nullptr; L.primID = L.geomID = L.instID = nullptr; }
+  return L;
+}
+
+inline Device* devOf(Scene* s) { return s ? s->dev : nullptr; }
+inline Device* devOf(Geometry* g) { return g ? g->dev : nullptr; }
+inline Device* devOf(Buffer* b) { return b ? b->dev : nullptr; }
+
+void unsupported(Device* dev, const char* what) {
+  processError(dev, RTC_ERROR_INVALID_OPERATION, (std::string(what) + " is not supported by the B200 ray-query device").c_str());
+}
+
+}  // namespace
+
+// ================================================================================================
+// device
+// ================================================================================================
+RTC_API RTCDevice rtcNewDevice(const char* config) {
+  std::lock_guard<std::mutex> l(g_apiMutex);
+  Device* d = nullptr;
+  RTC_TRY
+    d = new Device();
+    bool allowNoGpu = false;
+    parseConfig(d, config, &allowNoGpu);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      if (!allowNoGpu) { delete d; d = nullptr; fail(RTC_ERROR_UNKNOWN, "no CUDA device available (this engine has no CPU fallback)"); }
+    } else {
+      if (d->ordinal < 0 || d->ordinal >= n) { delete d; d = nullptr; fail(RTC_ERROR_INVALID_ARGUMENT, "gpu ordinal out of range"); }
+      cudaDeviceProp p;
+      cudaCheck(cudaGetDeviceProperties(&p, d->ordinal), "device query");
+      if (p.major < 10) { delete d; d = nullptr; fail(RTC_ERROR_UNSUPPORTED_CPU, "kernels are built for sm_100a only"); }
+      d->hasGpu = true;
+      d->bind();
+      cudaCheck(cudaStreamCreateWithFlags(&d->ownStream, cudaStreamNonBlocking), "stream");
+      if (d->verbose >= 1)
+        printf("b200-rayquery %s on GPU %d: %s, %d SMs, %.1f GB\n", RTC_VERSION_STRING, d->ordinal, p.name, p.multiProcessorCount, p.totalGlobalMem / 1e9);
+    }
+    return (RTCDevice)d;
+  RTC_CATCH(nullptr)
+  return nullptr;
+}
+
+RTC_API void rtcRetainDevice(RTCDevice h) {
+  std::lock_guard<std::mutex> l(g_apiMutex);
+  RTC_TRY VERIFY_HANDLE(h); ((Device*)h)->retain(); RTC_CATCH((Device*)h)
+}
+RTC_API void rtcReleaseDevice(RTCDevice h) {
+  std::lock_guard<std::mutex> l(g_apiMutex);
+  RTC_TRY VERIFY_HANDLE(h); ((Device*)h)->release(); RTC_CATCH(nullptr)
+}
+
+RTC_API ssize_t rtcGetDeviceProperty(RTCDevice h, enum RTCDeviceProperty prop) {
+  Device* d = (Device*)h;
+  RTC_TRY
+    VERIFY_HANDLE(h);
+    switch (prop) {
+      case RTC_DEVICE_PROPERTY_VERSION: return RTC_VERSION;
+      case RTC_DEVICE_PROPERTY_VERSION_MAJOR: return RTC_VERSION_MAJOR;
+      case RTC_DEVICE_PROPERTY_VERSION_MINOR: return RTC_VERSION_MINOR;
+      case RTC_DEVICE_PROPERTY_VERSION_PATCH: return RTC_VERSION_PATCH;
+      case RTC_DEVICE_PROPERTY_NATIVE_RAY4_SUPPORTED: case RTC_DEVICE_PROPERTY_NATIVE_RAY8_SUPPORTED:
+      case RTC_DEVICE_PROPERTY_NATIVE_RAY16_SUPPORTED: return 0;        // packets are repacked, streams are native
+      case RTC_DEVICE_PROPERTY_RAY_STREAM_SUPPORTED: return 1;
+      case RTC_DEVICE_PROPERTY_BACKFACE_CULLING_CURVES_ENABLED: return 0;
+      case RTC_DEVICE_PROPERTY_RAY_MASK_SUPPORTED: return 0;
+      case RTC_DEVICE_PROPERTY_BACKFACE_CULLING_ENABLED: return 0;
+      case RTC_DEVICE_PROPERTY_FILTER_FUNCTION_SUPPORTED: return 0;
+      case RTC_DEVICE_PROPERTY_IGNORE_INVALID_RAYS_ENABLED: return 0;
+      case RTC_DEVICE_PROPERTY_COMPACT_POLYS_ENABLED: return 0;
+      case RTC_DEVICE_PROPERTY_TRIANGLE_GEOMETRY_SUPPORTED: return 1;
+      case RTC_DEVICE_PROPERTY_QUAD_GEOMETRY_SUPPORTED: case RTC_DEVICE_PROPERTY_SUBDIVISION_GEOMETRY_SUPPORTED:
+      case RTC_DEVICE_PROPERTY_CURVE_GEOMETRY_SUPPORTED: case RTC_DEVICE_PROPERTY_USER_GEOMETRY_SUPPORTED:
+      case RTC_DEVICE_PROPERTY_POINT_GEOMETRY_SUPPORTED: return 0;
+      case RTC_DEVICE_PROPERTY_TASKING_SYSTEM: return 0;
+      case RTC_DEVICE_PROPERTY_JOIN_COMMIT_SUPPORTED: return 1;
+      case RTC_DEVICE_PROPERTY_PARALLEL_COMMIT_SUPPORTED: return 0;
+      default: fail(RTC_ERROR_INVALID_ARGUMENT, "unknown readable property");
+    }
+  RTC_CATCH(d)
+  return 0;
+}
+RTC_API void rtcSetDeviceProperty(RTCDevice h, const enum RTCDeviceProperty, ssize_t) {
+  Device* d = (Device*)h;
+  RTC_TRY VERIFY_HANDLE(h); fail(RTC_ERROR_INVALID_ARGUMENT, "unknown writable property"); RTC_CATCH(d)
+}
+RTC_API enum RTCError rtcGetDeviceError(RTCDevice h) {
+  Device* d = (Device*)h;
+  if (!d) { RTCError e = g_threadError; g_threadError = RTC_ERROR_NONE; return e; }
+  std::lock_guard<std::mutex> l(d->errMutex);
+  RTCError e = d->error; d->error = RTC_ERROR_NONE; return e;
+}
+RTC_API void rtcSetDeviceErrorFunction(RTCDevice h, RTCErrorFunction fn, void* p) {
+  Device* d = (Device*)h;
+  RTC_TRY VERIFY_HANDLE(h); { std::lock_guard<std::mutex> l(d->errMutex); d->errFn = fn; d->errPtr = p; } RTC_CATCH(d)
+}
+RTC_API void rtcSetDeviceMemoryMonitorFunction(RTCDevice h, RTCMemoryMonitorFunction fn, void* p) {
+  Device* d = (Device*)h;
+  RTC_TRY VERIFY_HANDLE(h); d->memFn = fn; d->memPtr = p; RTC_CATCH(d)
+}
+
+// ================================================================================================
+// buffers
+// ================================================================================================
+RTC_API RTCBuffer rtcNewBuffer(RTCDevice h, size_t bytes) {
+  Device* d = (Device*)h;
+  RTC_TRY VERIFY_HANDLE(h); return (RTCBuffer) new Buffer(d, bytes, nullptr); RTC_CATCH(d)
+  return nullptr;
+}
+RTC_API RTCBuffer rtcNewSharedBuffer(RTCDevice h, void* ptr, size_t bytes) {
+  Device* d = (Device*)h;
+  RTC_TRY VERIFY_HANDLE(h); VERIFY_HANDLE(ptr); return (RTCBuffer) new Buffer(d, bytes, ptr); RTC_CATCH(d)
+  return nullptr;
+}
+RTC_API void* rtcGetBufferData(RTCBuffer h) {
+  Buffer* b = (Buffer*)h;
+  RTC_TRY VERIFY_HANDLE(h); return b->ptr; RTC_CATCH(devOf(b))
+  return nullptr;
+}
+RTC_API void rtcRetainBuffer(RTCBuffer h) { Buffer* b = (Buffer*)h; RTC_TRY VERIFY_HANDLE(h); b->retain(); RTC_CATCH(devOf(b)) }
+RTC_API void rtcReleaseBuffer(RTCBuffer h) { Buffer* b = (Buffer*)h; Device* d = devOf(b); RTC_TRY VERIFY_HANDLE(h); b->release(); RTC_CATCH(d) }
+
+// ================================================================================================
+// geometry
+// ================================================================================================
+RTC_API RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
+  Device* d = (Device*)h;
+  RTC_TRY
+    VERIFY_HANDLE(h);
+    if (type != RTC_GEOMETRY_TYPE_TRIANGLE)
+      fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE is supported by the B200 ray-query device");
+    return (RTCGeometry) new Geometry(d, type);
+  RTC_CATCH(d)
+  return nullptr;
+}
+RTC_API void rtcRetainGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); g->retain(); RTC_CATCH(devOf(g)) }
+RTC_API void rtcReleaseGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; Device* d = devOf(g); RTC_TRY VERIFY_HANDLE(h); g->release(); RTC_CATCH(d) }
+RTC_API void rtcCommitGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); ++g->modCounter; g->committed = true; RTC_CATCH(devOf(g)) }
+RTC_API void rtcEnableGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); if (!g->enabled) { g->enabled = true; ++g->modCounter; } RTC_CATCH(devOf(g)) }
+RTC_API void rtcDisableGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); if (g->enabled) { g->enabled = false; ++g->modCounter; } RTC_CATCH(devOf(g)) }
+RTC_API void rtcSetGeometryTimeStepCount(RTCGeometry h, unsigned int n) {
+  Geometry* g = (Geometry*)h;
+  RTC_TRY VERIFY_HANDLE(h);
+    if (n == 0 || n > RTC_MAX_TIME_STEP_COUNT) fail(RTC_ERROR_INVALID_OPERATION, "number of time steps is out of range");
+    if (n != 1) fail(RTC_ERROR_INVALID_OPERATION, "motion blur is not supported by the B200 ray-query device");
+  RTC_CATCH(devOf(g))
+}
+RTC_API void rtcSetGeometryMask(RTCGeometry h, unsigned int mask) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); g->mask = mask; RTC_CATCH(devOf(g)) }
+RTC_API void rtcSetGeometryBuildQuality(RTCGeometry h, enum RTCBuildQuality q) {
+  Geometry* g = (Geometry*)h;
+  RTC_TRY VERIFY_HANDLE(h);
+    if (q != RTC_BUILD_QUALITY_LOW && q != RTC_BUILD_QUALITY_MEDIUM && q != RTC_BUILD_QUALITY_HIGH && q != RTC_BUILD_QUALITY_REFIT)
+      fail(RTC_ERROR_INVALID_OPERATION, "invalid build quality");
+    g->quality = q; g->update();
+  RTC_CATCH(devOf(g))
+}
+
+namespace {
+void setBuffer(Geometry* g, RTCBufferType type, unsigned slot, RTCFormat format, Buffer* buf, size_t offset, size_t stride, unsigned num) {
+  if ((((size_t)buf->ptr + offset) & 3) || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
+  if (type == RTC_BUFFER_TYPE_VERTEX) {
+    if (format != RTC_FORMAT_FLOAT3) fail(RTC_ERROR_INVALID_OPERATION, "invalid vertex buffer format");
+    if (stride * (size_t)num > 16ull * 1024 * 1024 * 1024) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer can be at most 16GB large");
+    if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid vertex buffer slot");
+    g->vertices.set(buf, offset, stride, num, format);
+  } else if (type == RTC_BUFFER_TYPE_INDEX) {
+    if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot");
+    if (format != RTC_FORMAT_UINT3) fail(RTC_ERROR_INVALID_OPERATION, "invalid index buffer format");
+    g->indices.set(buf, offset, stride, num, format);
+  } else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) {
+    fail(RTC_ERROR_INVALID_OPERATION, "vertex attributes are not supported by the B200 ray-query device");
+  } else {
+    fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
+  }
+  g->update();
+}
+}  // namespace
+
+RTC_API void rtcSetGeometryBuffer(RTCGeometry h, enum RTCBufferType type, unsigned int slot, enum RTCFormat format, RTCBuffer hb,
+                                  size_t byteOffset, size_t byteStride, size_t itemCount) {
+  Geometry* g = (Geometry*)h; Buffer* b = (Buffer*)hb;
+  RTC_TRY
+    VERIFY_HANDLE(h); VERIFY_HANDLE(hb);
+    if (g->dev != b->dev) fail(RTC_ERROR_INVALID_ARGUMENT, "inputs are from different devices");
+    if (itemCount > 0xFFFFFFFFu) fail(RTC_ERROR_INVALID_ARGUMENT, "buffer too large");
+    setBuffer(g, type, slot, format, b, byteOffset, byteStride, (unsigned)itemCount);
+  RTC_CATCH(devOf(g))
+}
+RTC_API void rtcSetSharedGeometryBuffer(RTCGeometry h, enum RTCBufferType type, unsigned int slot, enum RTCFormat format, const void* ptr,
+                                        size_t byteOffset, size_t byteStride, size_t itemCount) {
+  Geometry* g = (Geometry*)h;
+  RTC_TRY
+    VERIFY_HANDLE(h);
+    if (itemCount > 0xFFFFFFFFu) fail(RTC_ERROR_INVALID_ARGUMENT, "buffer too large");
+    Buffer* b = new Buffer(g->dev, itemCount * byteStride, (char*)ptr + byteOffset);
+    try { setBuffer(g, type, slot, format, b, 0, byteStride, (unsigned)itemCount); } catch (...) { b->release(); throw; }
+    b->release();
+  RTC_CATCH(devOf(g))
+}
+RTC_API void* rtcSetNewGeometryBuffer(RTCGeometry h, enum RTCBufferType type, unsigned int slot, enum RTCFormat format,
+                                      size_t byteStride, size_t itemCount) {
+  Geometry* g = (Geometry*)h;
+  RTC_TRY
+    VERIFY_HANDLE(h);
+    if (itemCount > 0xFFFFFFFFu) fail(RTC_ERROR_INVALID_ARGUMENT, "buffer too large");
+    size_t bytes = itemCount * byteStride;
+    if (type == RTC_BUFFER_TYPE_VERTEX || type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) bytes += (16 - (byteStride % 16)) % 16;
+    Buffer* b = new Buffer(g->dev, bytes, nullptr);
+    try { setBuffer(g, type, slot, format, b, 0, byteStride, (unsigned)itemCount); } catch (...) { b->release(); throw; }
+    void* p = b->ptr;
+    b->release();
+    return p;
+  RTC_CATCH(devOf(g))
+  return nullptr;
+}
+RTC_API void* rtcGetGeometryBufferData(RTCGeometry h, enum RTCBufferType type, unsigned int slot) {
+  Geometry* g = (Geometry*)h;
+  RTC_TRY
+    VERIFY_HANDLE(h);
+    if (type == RTC_BUFFER_TYPE_INDEX && slot == 0) return (void*)g->indices.data();
+    if (type == RTC_BUFFER_TYPE_VERTEX && slot == 0) return (void*)g->vertices.data();
+    fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
+  RTC_CATCH(devOf(g))
+  return nullptr;
+}
+RTC_API void rtcUpdateGeometryBuffer(RTCGeometry h, enum RTCBufferType, unsigned int) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); g->update(); RTC_CATCH(devOf(g)) }
+RTC_API void rtcSetGeometryUserData(RTCGeometry h, void* p) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); g->userPtr = p; RTC_CATCH(devOf(g)) }
+RTC_API void* rtcGetGeometryUserData(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); return g->userPtr; RTC_CATCH(devOf(g)) return nullptr; }
+RTC_API void rtcSetGeometryIntersectFilterFunction(RTCGeometry h, RTCFilterFunctionN f) {
+  Geometry* g = (Geometry*)h;
+  RTC_TRY VERIFY_HANDLE(h); if (f) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the GPU"); RTC_CATCH(devOf(g))
+}
+RTC_API void rtcSetGeometryOccludedFilterFunction(RTCGeometry h, RTCFilterFunctionN f) {
+  Geometry* g = (Geometry*)h;
+  RTC_TRY VERIFY_HANDLE(h); if (f) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the GPU"); RTC_CATCH(devOf(g))
+}
+
+// ================================================================================================
+// scene
+// ================================================================================================
+RTC_API RTCScene rtcNewScene(RTCDevice h) {
+  Device* d = (Device*)h;
+  RTC_TRY VERIFY_HANDLE(h); return (RTCScene) new Scene(d); RTC_CATCH(d)
+  return nullptr;
+}
+RTC_API RTCDevice rtcGetSceneDevice(RTCScene h) {
+  Scene* s = (Scene*)h;
+  RTC_TRY VERIFY_HANDLE(h); s->dev->retain(); return (RTCDevice)s->dev; RTC_CATCH(devOf(s))   // extra reference (rtcore.cpp:204)
+  return nullptr;
+}
+RTC_API void rtcRetainScene(RTCScene h) { Scene* s = (Scene*)h; RTC_TRY VERIFY_HANDLE(h); s->retain(); RTC_CATCH(devOf(s)) }
+RTC_API void rtcReleaseScene(RTCScene h) { Scene* s = (Scene*)h; Device* d = devOf(s); RTC_TRY VERIFY_HANDLE(h); s->release(); RTC_CATCH(d) }
+
+namespace {
+unsigned bindGeometry(Scene* s, unsigned geomID, Geometry* g) {
+  std::lock_guard<std::mutex> l(s->geomMutex);
+  if (geomID == RTC_INVALID_GEOMETRY_ID) {
+    if (!s->freeIDs.empty()) { geomID = *s->freeIDs.begin(); s->freeIDs.erase(s->freeIDs.begin()); }
+    else geomID = s->nextID++;
+  } else {
+    if (geomID < s->geoms.size() && s->geoms[geomID]) fail(RTC_ERROR_INVALID_OPERATION, "invalid geometry ID provided");
+    if (geomID >= s->nextID) { for (unsigned i = s->nextID; i < geomID; i++) s->freeIDs.insert(i); s->nextID = geomID + 1; }
+    else s->freeIDs.erase(geomID);
+  }
+  if (geomID >= s->geoms.size()) s->geoms.resize(geomID + 1, nullptr);
+  g->retain();
+  s->geoms[geomID] = g;
+  if (geomID < s->seenMod.size()) s->seenMod[geomID] = 0xFFFFFFFFu;
+  if (g->enabled) s->modified = true;
+  return geomID;
+}
+}  // namespace
+
+RTC_API unsigned int rtcAttachGeometry(RTCScene hs, RTCGeometry hg) {
+  Scene* s = (Scene*)hs; Geometry* g = (Geometry*)hg;
+  RTC_TRY
+    VERIFY_HANDLE(hs); VERIFY_HANDLE(hg);
+    if (s->dev != g->dev) fail(RTC_ERROR_INVALID_ARGUMENT, "inputs are from different devices");
+    return bindGeometry(s, RTC_INVALID_GEOMETRY_ID, g);
+  RTC_CATCH(devOf(s))
+  return (unsigned)-1;
+}
+RTC_API void rtcAttachGeometryByID(RTCScene hs, RTCGeometry hg, unsigned int geomID) {
+  Scene* s = (Scene*)hs; Geometry* g = (Geometry*)hg;
+  RTC_TRY
+    VERIFY_HANDLE(hs); VERIFY_HANDLE(hg);
+    if (geomID == RTC_INVALID_GEOMETRY_ID) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid argument");
+    if (s->dev != g->dev) fail(RTC_ERROR_INVALID_ARGUMENT, "inputs are from different devices");
+    bindGeometry(s, geomID, g);
+  RTC_CATCH(devOf(s))
+}
+RTC_API void rtcDetachGeometry(RTCScene hs, unsigned int geomID) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    VERIFY_HANDLE(hs);
+    if (geomID == RTC_INVALID_GEOMETRY_ID) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid argument");
+    Geometry* g = nullptr;
+    {
+      std::lock_guard<std::mutex> l(s->geomMutex);
+      if (geomID >= s->geoms.size()) fail(RTC_ERROR_INVALID_OPERATION, "invalid geometry ID");
+      g = s->geoms[geomID];
+      if (!g) fail(RTC_ERROR_INVALID_OPERATION, "invalid geometry");
+      if (g->enabled) s->modified = true;
+      s->geoms[geomID] = nullptr;
+      s->freeIDs.insert(geomID);
+    }
+    g->release();
+  RTC_CATCH(devOf(s))
+}
+RTC_API RTCGeometry rtcGetGeometry(RTCScene hs, unsigned int geomID) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    VERIFY_HANDLE(hs);
+    std::lock_guard<std::mutex> l(s->geomMutex);
+    if (geomID >= s->geoms.size()) return nullptr;
+    return (RTCGeometry)s->geoms[geomID];
+  RTC_CATCH(devOf(s))
+  return nullptr;
+}
+RTC_API void rtcCommitScene(RTCScene hs) { Scene* s = (Scene*)hs; RTC_TRY VERIFY_HANDLE(hs); commitScene(s); RTC_CATCH(devOf(s)) }
+RTC_API void rtcJoinCommitScene(RTCScene hs) { Scene* s = (Scene*)hs; RTC_TRY VERIFY_HANDLE(hs); commitScene(s); RTC_CATCH(devOf(s)) }
+RTC_API void rtcSetSceneProgressMonitorFunction(RTCScene hs, RTCProgressMonitorFunction f, void* p) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY VERIFY_HANDLE(hs); s->progress = f; s->progressPtr = p; RTC_CATCH(devOf(s))
+}
+RTC_API void rtcSetSceneBuildQuality(RTCScene hs, enum RTCBuildQuality q) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY VERIFY_HANDLE(hs);
+    if (q != RTC_BUILD_QUALITY_LOW && q != RTC_BUILD_QUALITY_MEDIUM && q != RTC_BUILD_QUALITY_HIGH)
+      fail(RTC_ERROR_INVALID_OPERATION, "invalid build quality");
+    if (q != s->quality) { s->quality = q; s->modified = true; }
+  RTC_CATCH(devOf(s))
+}
+RTC_API void rtcSetSceneFlags(RTCScene hs, enum RTCSceneFlags f) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY VERIFY_HANDLE(hs); if (f != s->flags) { s->flags = f; s->modified = true; } RTC_CATCH(devOf(s))
+}
+RTC_API enum RTCSceneFlags rtcGetSceneFlags(RTCScene hs) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY VERIFY_HANDLE(hs); return s->flags; RTC_CATCH(devOf(s))
+  return RTC_SCENE_FLAG_NONE;
+}
+RTC_API void rtcGetSceneBounds(RTCScene hs, struct RTCBounds* b) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    VERIFY_HANDLE(hs); VERIFY_HANDLE(b);
+    if (!s->everCommitted || s->modified) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");
+    const RQImageHeader& H = s->image.header;
+    b->lower_x = H.lo[0]; b->lower_y = H.lo[1]; b->lower_z = H.lo[2]; b->align0 = 0;
+    b->upper_x = H.hi[0]; b->upper_y = H.hi[1]; b->upper_z = H.hi[2]; b->align1 = 0;
+  RTC_CATCH(devOf(s))
+}
+RTC_API void rtcGetSceneLinearBounds(RTCScene hs, struct RTCLinearBounds* b) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    VERIFY_HANDLE(hs); VERIFY_HANDLE(b);
+    rtcGetSceneBounds(hs, &b->bounds0); b->bounds1 = b->bounds0;
+  RTC_CATCH(devOf(s))
+}
+
+// ================================================================================================
+// queries
+// ================================================================================================
+RTC_API void rtcIntersect1M(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHit* rayhit, unsigned int M, size_t byteStride) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY checkQuery(s, ctx); traceStream(s, ctx, rayhit, M, byteStride, false, sizeof(RTCRayHit), nullptr); RTC_CATCH(devOf(s))
+}
+RTC_API void rtcOccluded1M(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRay* ray, unsigned int M, size_t byteStride) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY checkQuery(s, ctx); traceStream(s, ctx, ray, M, byteStride, true, sizeof(RTCRay), nullptr); RTC_CATCH(devOf(s))
+}
+RTC_API void rtcIntersect1(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHit* rayhit) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY checkQuery(s, ctx); traceStream(s, ctx, rayhit, 1, sizeof(RTCRayHit), false, sizeof(RTCRayHit), nullptr); RTC_CATCH(devOf(s))
+}
+RTC_API void rtcOccluded1(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRay* ray) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY checkQuery(s, ctx); traceStream(s, ctx, ray, 1, sizeof(RTCRay), true, sizeof(RTCRay), nullptr); RTC_CATCH(devOf(s))
+}
+#define B200RQ_PACKET_ENTRY(W)                                                                                              \
+  RTC_API void rtcIntersect##W(const int* valid, RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHit##W* rh) {    \
+    Scene* s = (Scene*)hs;                                                                                                  \
+    RTC_TRY checkQuery(s, ctx); tracePacked(s, ctx, laneOf(&rh->ray, &rh->hit), valid, W, false); RTC_CATCH(devOf(s))        \
+  }                                                                                                                         \
+  RTC_API void rtcOccluded##W(const int* valid, RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRay##W* r) {         \
+    Scene* s = (Scene*)hs;                                                                                                  \
+    RTC_TRY checkQuery(s, ctx); tracePacked(s, ctx, laneOf(r, (RTCHit##W*)nullptr), valid, W, true); RTC_CATCH(devOf(s))     \
+  }
+B200RQ_PACKET_ENTRY(4)
+B200RQ_PACKET_ENTRY(8)
+B200RQ_PACKET_ENTRY(16)
+
+RTC_API void rtcIntersect1Mp(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHit** rh, unsigned int M) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    checkQuery(s, ctx);
+    std::vector<RTCRayHit> tmp(M);
+    for (unsigned i = 0; i < M; i++) tmp[i] = *rh[i];
+    for (unsigned i = 0; i < M; i++) tmp[i].hit.geomID = RTC_INVALID_GEOMETRY_ID;
+    traceStream(s, ctx, tmp.data(), M, sizeof(RTCRayHit), false, sizeof(RTCRayHit), nullptr);
+    for (unsigned i = 0; i < M; i++)
+      if (tmp[i].hit.geomID != RTC_INVALID_GEOMETRY_ID) { rh[i]->ray.tfar = tmp[i].ray.tfar; rh[i]->hit = tmp[i].hit; }
+  RTC_CATCH(devOf(s))
+}
+RTC_API void rtcOccluded1Mp(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRay** r, unsigned int M) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    checkQuery(s, ctx);
+    std::vector<RTCRay> tmp(M);
+    for (unsigned i = 0; i < M; i++) tmp[i] = *r[i];
+    traceStream(s, ctx, tmp.data(), M, sizeof(RTCRay), true, sizeof(RTCRay), nullptr);
+    for (unsigned i = 0; i < M; i++) if (tmp[i].tfar == -INFINITY) r[i]->tfar = -INFINITY;
+  RTC_CATCH(devOf(s))
+}
+RTC_API void rtcIntersectNM(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHitN* rh, unsigned int N, unsigned int M, size_t byteStride) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    checkQuery(s, ctx);
+    for (unsigned m = 0; m < M; m++) tracePacked(s, ctx, laneOfN((float*)((char*)rh + m * byteStride), N, true), nullptr, N, false);
+  RTC_CATCH(devOf(s))
+}
+RTC_API void rtcOccludedNM(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayN* r, unsigned int N, unsigned int M, size_t byteStride) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    checkQuery(s, ctx);
+    for (unsigned m = 0; m < M; m++) tracePacked(s, ctx, laneOfN((float*)((char*)r + m * byteStride), N, false), nullptr, N, true);
+  RTC_CATCH(devOf(s))
+}
+RTC_API void rtcIntersectNp(RTCScene hs, struct RTCIntersectContext* ctx, const struct RTCRayHitNp* rh, unsigned int N) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    checkQuery(s, ctx);
+    Lane L;
+    L.org_x = rh->ray.org_x; L.org_y = rh->ray.org_y; L.org_z = rh->ray.org_z; L.tnear = rh->ray.tnear; L.dir_x = rh->ray.dir_x;
+    L.dir_y = rh->ray.dir_y; L.dir_z = rh->ray.dir_z; L.time = rh->ray.time; L.tfar = rh->ray.tfar; L.mask = rh->ray.mask; L.id = rh->ray.id;
+    L.flags = rh->ray.flags; L.Ng_x = rh->hit.Ng_x; L.Ng_y = rh->hit.Ng_y; L.Ng_z = rh->hit.Ng_z; L.u = rh->hit.u; L.v = rh->hit.v;
+    L.primID = rh->hit.primID; L.geomID = rh->hit.geomID; L.instID = rh->hit.instID[0];
+    tracePacked(s, ctx, L, nullptr, N, false);
+  RTC_CATCH(devOf(s))
+}
+RTC_API void rtcOccludedNp(RTCScene hs, struct RTCIntersectContext* ctx, const struct RTCRayNp* r, unsigned int N) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    checkQuery(s, ctx);
+    Lane L; memset(&L, 0, sizeof(L));
+    L.org_x = r->org_x; L.org_y = r->org_y; L.org_z = r->org_z; L.tnear = r->tnear; L.dir_x = r->dir_x; L.dir_y = r->dir_y;
+    L.dir_z = r->dir_z; L.time = r->time; L.tfar = r->tfar; L.mask = r->mask; L.id = r->id; L.flags = r->flags;
+    tracePacked(s, ctx, L, nullptr, N, true);
+  RTC_CATCH(devOf(s))
+}
+
+// ================================================================================================
+// B200 extensions (include/rq_b200.h)
+// ================================================================================================
+RTC_API void rtcxSetDeviceStream(RTCDevice h, void* stream) { Device* d = (Device*)h; RTC_TRY VERIFY_HANDLE(h); d->userStream = (cudaStream_t)stream; RTC_CATCH(d) }
+RTC_API void rtcxSynchronizeDevice(RTCDevice h) {
+  Device* d = (Device*)h;
+  RTC_TRY VERIFY_HANDLE(h); if (d->hasGpu) { d->bind(); cudaCheck(cudaStreamSynchronize(d->stream()), "synchronize"); } RTC_CATCH(d)
+}
+RTC_API int rtcxGetDeviceOrdinal(RTCDevice h) { Device* d = (Device*)h; return d && d->hasGpu ? d->ordinal : -1; }
+RTC_API int rtcxGetSceneBuildStats(RTCScene hs, struct RTCXBuildStats* o) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    VERIFY_HANDLE(hs); VERIFY_HANDLE(o);
+    if (!s->everCommitted) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");
+    static_assert(sizeof(RTCXBuildStats) == sizeof(RQBuildStats), "stats layouts must agree");
+    memcpy(o, &s->stats, sizeof(*o));
+    return 0;
+  RTC_CATCH(devOf(s))
+  return -1;
+}
+RTC_API const void* rtcxGetSceneImage(RTCScene hs, size_t* bytes) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    VERIFY_HANDLE(hs);
+    if (!s->everCommitted || s->modified) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");
+    if (bytes) *bytes = (size_t)s->image.header.totalBytes;
+    return s->image.base;
+  RTC_CATCH(devOf(s))
+  return nullptr;
+}
+RTC_API void rtcxSetSceneImage(RTCScene hs, const void* src, size_t bytes) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    VERIFY_HANDLE(hs); VERIFY_HANDLE(src);
+    Device* dev = s->dev;
+    if (!dev->hasGpu) fail(RTC_ERROR_UNKNOWN, "no CUDA device");
+    if (bytes < sizeof(RQImageHeader)) fail(RTC_ERROR_INVALID_ARGUMENT, "image too small");
+    dev->bind();
+    std::unique_lock<std::mutex> lock(s->buildMutex);
+    RQImageHeader H;
+    cudaCheck(cudaMemcpy(&H, src, sizeof(H), cudaMemcpyDefault), "image header");
+    if (H.magic != RQ_IMAGE_MAGIC || H.totalBytes != bytes || H.nodesOffset != 128 ||
+        H.trisOffset != H.nodesOffset + (uint64_t)H.numNodes * sizeof(RQNode) ||
+        H.trisOffset + (uint64_t)H.numTris * sizeof(RQTri) > H.totalBytes)
+      fail(RTC_ERROR_INVALID_ARGUMENT, "not a BVH image");
+    void* p = nullptr;
+    cudaCheck(cudaMalloc(&p, bytes), "image alloc");
+    int e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyDefault, dev->stream());
+    if (!e) e = cudaStreamSynchronize(dev->stream());
+    if (e) { cudaFree(p); cudaCheck(e, "image copy"); }
+    if (s->image.base) rqFreeImage(&s->image);
+    s->image.base = p; s->image.header = H;
+    s->flags = (RTCSceneFlags)H.flags;
+    memset(&s->stats, 0, sizeof(s->stats));
+    s->stats.numNodes = H.numNodes; s->stats.numTris = H.numTris; s->stats.depth = H.depth; s->stats.sah = H.sah; s->stats.bytes = H.totalBytes;
+    s->stats.numPrimsValid = H.numTris;
+    s->modified = false; s->everCommitted = true;
+    { std::lock_guard<std::mutex> gl(s->geomMutex); s->seenMod.assign(s->geoms.size(), 0); for (size_t i = 0; i < s->geoms.size(); i++) if (s->geoms[i]) s->seenMod[i] = s->geoms[i]->modCounter; }
+  RTC_CATCH(devOf(s))
+}
+RTC_API void rtcxIntersect1MCounted(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHit* rh, unsigned int M, size_t stride,
+                                    struct RTCXTraceCounters* out) {
+  Scene* s = (Scene*)hs;
+  static_assert(sizeof(RTCXTraceCounters) == sizeof(RQTraceCounters), "counter layouts must agree");
+  RTC_TRY checkQuery(s, ctx); VERIFY_HANDLE(out); traceStream(s, ctx, rh, M, stride, false, sizeof(RTCRayHit), (RQTraceCounters*)out); RTC_CATCH(devOf(s))
+}
+RTC_API void rtcxOccluded1MCounted(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRay* r, unsigned int M, size_t stride,
+                                   struct RTCXTraceCounters* out) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY checkQuery(s, ctx); VERIFY_HANDLE(out); traceStream(s, ctx, r, M, stride, true, sizeof(RTCRay), (RQTraceCounters*)out); RTC_CATCH(devOf(s))
+}
+RTC_API unsigned long long rtcxGetLaunchCount(void) { return rqLaunchCount(); }
+
+// ================================================================================================
+// Entry points outside the hot path: exported so existing programs link, raise INVALID_OPERATION.
+// (reference: kernels/common/rtcore.cpp -- curves, subdivision, instancing, user geometry,
+//  point queries, collision, interpolation, BVH builder API)
+// ================================================================================================
+#define B200RQ_STUB(ret, name, args, devexpr, retval) \
+  RTC_API ret name args { unsupported((devexpr), #name); return retval; }
+#define B200RQ_NODEV ((Device*)nullptr)
+B200RQ_STUB(void, rtcSetGeometryTimeRange, (RTCGeometry g, float, float), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryVertexAttributeCount, (RTCGeometry g, unsigned int), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryMaxRadiusScale, (RTCGeometry g, float), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryPointQueryFunction, (RTCGeometry g, RTCPointQueryFunction), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryUserPrimitiveCount, (RTCGeometry g, unsigned int), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryBoundsFunction, (RTCGeometry g, void*, void*), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryIntersectFunction, (RTCGeometry g, void*), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryOccludedFunction, (RTCGeometry g, void*), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcFilterIntersection, (const void*, const void*), B200RQ_NODEV, )
+B200RQ_STUB(void, rtcFilterOcclusion, (const void*, const void*), B200RQ_NODEV, )
+B200RQ_STUB(void, rtcSetGeometryInstancedScene, (RTCGeometry g, RTCScene), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryTransform, (RTCGeometry g, unsigned int, enum RTCFormat, const void*), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryTransformQuaternion, (RTCGeometry g, unsigned int, const void*), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcGetGeometryTransform, (RTCGeometry g, float, enum RTCFormat, void*), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryTessellationRate, (RTCGeometry g, float), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryTopologyCount, (RTCGeometry g, unsigned int), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometrySubdivisionMode, (RTCGeometry g, unsigned int, enum RTCSubdivisionMode), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryVertexAttributeTopology, (RTCGeometry g, unsigned int, unsigned int), devOf((Geometry*)g), )
+B200RQ_STUB(void, rtcSetGeometryDisplacementFunction, (RTCGeometry g, void*), devOf((Geometry*)g), )
+B200RQ_STUB(unsigned int, rtcGetGeometryFirstHalfEdge, (RTCGeometry g, unsigned int), devOf((Geometry*)g), 0)
+B200RQ_STUB(unsigned int, rtcGetGeometryFace, (RTCGeometry g, unsigned int), devOf((Geometry*)g), 0)
+B200RQ_STUB(unsigned int, rtcGetGeometryNextHalfEdge, (RTCGeometry g, unsigned int), devOf((Geometry*)g), 0)
+B200RQ_STUB(unsigned int, rtcGetGeometryPreviousHalfEdge, (RTCGeometry g, unsigned int), devOf((Geometry*)g), 0)
+B200RQ_STUB(unsigned int, rtcGetGeometryOppositeHalfEdge, (RTCGeometry g, unsigned int, unsigned int), devOf((Geometry*)g), 0)
+B200RQ_STUB(void, rtcInterpolate, (const void*), B200RQ_NODEV, )
+B200RQ_STUB(void, rtcInterpolateN, (const void*), B200RQ_NODEV, )
+B200RQ_STUB(bool, rtcPointQuery, (RTCScene s, void*, void*, RTCPointQueryFunction, void*), devOf((Scene*)s), false)
+B200RQ_STUB(bool, rtcPointQuery4, (const int*, RTCScene s, void*, void*, RTCPointQueryFunction, void**), devOf((Scene*)s), false)
+B200RQ_STUB(bool, rtcPointQuery8, (const int*, RTCScene s, void*, void*, RTCPointQueryFunction, void**), devOf((Scene*)s), false)
+B200RQ_STUB(bool, rtcPointQuery16, (const int*, RTCScene s, void*, void*, RTCPointQueryFunction, void**), devOf((Scene*)s), false)
+B200RQ_STUB(void, rtcCollide, (RTCScene s, RTCScene, void*, void*), devOf((Scene*)s), )
+B200RQ_STUB(void*, rtcNewBVH, (RTCDevice d), (Device*)d, nullptr)
+B200RQ_STUB(void*, rtcBuildBVH, (const void*), B200RQ_NODEV, nullptr)
+B200RQ_STUB(void*, rtcThreadLocalAlloc, (void*, size_t, size_t), B200RQ_NODEV, nullptr)
+B200RQ_STUB(void, rtcRetainBVH, (void*), B200RQ_NODEV, )
+B200RQ_STUB(void, rtcReleaseBVH, (void*), B200RQ_NODEV, )
