@@ -865,6 +865,17 @@ RTC_API const void* rtcxGetSceneImage(RTCScene hs, size_t* bytes) {
   RTC_CATCH(devOf(s))
   return nullptr;
 }
+RTC_API void rtcxCopySceneImage(RTCScene hs, void* dst, size_t bytes) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    VERIFY_HANDLE(hs); VERIFY_HANDLE(dst);
+    if (!s->everCommitted || s->modified) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");
+    if (bytes != s->image.header.totalBytes) fail(RTC_ERROR_INVALID_ARGUMENT, "size does not match the image");
+    s->dev->bind();
+    cudaCheck(cudaMemcpyAsync(dst, s->image.base, bytes, cudaMemcpyDefault, s->dev->stream()), "image copy");
+    cudaCheck(cudaStreamSynchronize(s->dev->stream()), "image copy");
+  RTC_CATCH(devOf(s))
+}
 RTC_API void rtcxSetSceneImage(RTCScene hs, const void* src, size_t bytes) {
   Scene* s = (Scene*)hs;
   RTC_TRY

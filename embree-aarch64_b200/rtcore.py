@@ -1,8 +1,8 @@
 """ctypes binding of the rtcore C ABI (include/embree3/rtcore.h, include/rq_b200.h).
 
 The same binding drives any library that exports the `rtc*` symbols: the product
-(`embree-aarch64_b200/lib/libembree3.so`) and, in tests and the CPU baseline only, the reference
-library compiled by `oracle/build_ref.py`.  That is the point of the drop-in boundary: one harness,
+(`embree-aarch64_b200/lib/libembree3.so`) and, in tests and the CPU baseline only, a build of the
+reference library (path supplied by the caller; this package never looks for it).  That is the point of the drop-in boundary: one harness,
 two libraries, identical calls (the shape of the reference's own `IntersectWithMode`,
 tutorials/verify/rtcore_helpers.h:751-879).
 
@@ -145,6 +145,7 @@ class RTCore:
             _sig(L, "rtcxGetSceneBuildStats", C.c_int, [vp, C.POINTER(BuildStats)])
             _sig(L, "rtcxGetSceneImage", vp, [vp, C.POINTER(sz)])
             _sig(L, "rtcxSetSceneImage", None, [vp, vp, sz])
+            _sig(L, "rtcxCopySceneImage", None, [vp, vp, sz])
             _sig(L, "rtcxIntersect1MCounted", None, [vp, ctxp, vp, u, sz, C.POINTER(TraceCounters)])
             _sig(L, "rtcxOccluded1MCounted", None, [vp, ctxp, vp, u, sz, C.POINTER(TraceCounters)])
             _sig(L, "rtcxGetLaunchCount", C.c_ulonglong, [])

@@ -51,6 +51,9 @@ RTC_API int rtcxGetSceneBuildStats(RTCScene scene, struct RTCXBuildStats* stats_
  * broadcast.  */
 RTC_API const void* rtcxGetSceneImage(RTCScene scene, size_t* bytes_o);
 RTC_API void rtcxSetSceneImage(RTCScene scene, const void* deviceImage, size_t bytes);
+/* Copies the image into caller memory (device or host, `bytes` must equal the image size): the
+ * send buffer of the broadcast. */
+RTC_API void rtcxCopySceneImage(RTCScene scene, void* dst, size_t bytes);
 
 /* Same as rtcIntersect1M / rtcOccluded1M, run with the instrumented kernel variant; the counters
  * are the measured numerator of the traversal roofline. */

@@ -1,0 +1,212 @@
+"""CPU-only checks of the drop-in boundary: the library loads, exports every symbol the headers
+declare, the struct layouts are the reference's, and the host-side object model follows the
+reference's error conventions and state machine (no compute without a GPU).
+Reference behaviour being mirrored: kernels/common/rtcore.cpp, scene.cpp:595-653, geometry.cpp:80-107,
+scene_triangle_mesh.cpp:35-80, device.cpp:258-316."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+
+rt = cases.rt
+ROOT = cases.ROOT
+
+
+def declared_symbols():
+    names = set()
+    for h in ("include/embree3/rtcore.h", "include/rq_b200.h"):
+        src = open(os.path.join(ROOT, h)).read()
+        names |= set(re.findall(r"RTC_API[^;(]*?\b(rtcx?[A-Z]\w*)\s*\(", src))
+    for w in (4, 8, 16):
+        names |= {f"rtcIntersect{w}", f"rtcOccluded{w}"}
+    return names
+
+
+def test_library_exports_every_declared_symbol(product):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", product.path]).decode()
+    exported = set(re.findall(r" T (\w+)", out))
+    decl = declared_symbols()
+    assert len(decl) > 70
+    assert not (decl - exported), sorted(decl - exported)
+    assert all(s.startswith("rtc") for s in exported), [s for s in exported if not s.startswith("rtc")]
+    # out-of-scope entry points still link
+    for s in ("rtcSetGeometryTransform", "rtcPointQuery", "rtcCollide", "rtcInterpolate", "rtcNewBVH", "rtcSetGeometryInstancedScene"):
+        assert s in exported, s
+
+
+def test_struct_layouts_match_reference_headers(tmp_path):
+    """sizeof/offsetof of the wire structs (rtcore_ray.h:11-49: 48 + 32 bytes, 16-byte aligned)."""
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "embree3/rtcore.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(struct RTCRay), sizeof(struct RTCHit), sizeof(struct RTCRayHit),
+         offsetof(struct RTCRay, tfar), offsetof(struct RTCRayHit, hit), offsetof(struct RTCHit, primID),
+         sizeof(struct RTCRayHit4), sizeof(struct RTCRayHit8), sizeof(struct RTCRayHit16), sizeof(struct RTCBounds),
+         sizeof(struct RTCIntersectContext), _Alignof(struct RTCRay8), _Alignof(struct RTCRay16));
+  return 0;
+}''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    vals = list(map(int, subprocess.check_output([str(exe)]).split()))
+    assert vals == [48, 32, 80, 32, 48, 20, 320, 640, 1280, 32, 24, 32, 64], vals
+    assert rt.RAY_DTYPE.itemsize == 48 and rt.RAYHIT_DTYPE.itemsize == 80
+
+
+def test_header_compiles_as_cpp_and_forwarders(tmp_path):
+    src = tmp_path / "h.cpp"
+    src.write_text('#include "embree3/rtcore_ray.h"\n#include "embree3/rtcore_scene.h"\n#include "embree3/rtcore_geometry.h"\n'
+                   '#include "rq_b200.h"\nint main(){ RTCIntersectContext c; rtcInitIntersectContext(&c); RTCRayHit r; (void)r; return c.instID[0]==RTC_INVALID_GEOMETRY_ID?0:1; }\n')
+    subprocess.check_call(["g++", "-std=c++11", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+def test_no_gpu_means_no_device(product):
+    """Without CUDA rtcNewDevice fails loudly (no CPU fallback); with CUDA it succeeds."""
+    import torch
+    d = product.lib.rtcNewDevice(b"")
+    if torch.cuda.is_available():
+        assert d
+        product.lib.rtcReleaseDevice(d)
+    else:
+        assert not d
+        assert product.lib.rtcGetDeviceError(None) == rt.RTC_ERROR_UNKNOWN
+        assert product.lib.rtcGetDeviceError(None) == rt.RTC_ERROR_NONE      # reading clears (device.cpp:273-286)
+
+
+@pytest.fixture()
+def hostdev(product):
+    """A device object without GPU requirements: host-side API logic only (commit/query would fail)."""
+    d = product.lib.rtcNewDevice(b"allow_no_gpu=1")
+    assert d
+    yield d
+    product.lib.rtcReleaseDevice(d)
+
+
+def err(product, d):
+    return product.lib.rtcGetDeviceError(d)
+
+
+def test_error_slot_first_error_wins_and_callback(product, hostdev):
+    L = product.lib
+    seen = []
+    CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p)
+    cb = CB(lambda p, code, msg: seen.append((code, msg.decode())))
+    L.rtcSetDeviceErrorFunction.argtypes = [C.c_void_p, CB, C.c_void_p]
+    L.rtcSetDeviceErrorFunction(hostdev, cb, None)
+    assert not L.rtcNewGeometry(hostdev, rt.RTC_GEOMETRY_TYPE_QUAD)           # unsupported type -> INVALID_OPERATION
+    L.rtcCommitGeometry(None)                                                 # NULL handle -> INVALID_ARGUMENT, thread slot
+    g = L.rtcNewGeometry(hostdev, rt.RTC_GEOMETRY_TYPE_TRIANGLE)
+    L.rtcSetGeometryTimeStepCount(g, 2)                                       # second error on the device: not recorded
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    assert err(product, hostdev) == rt.RTC_ERROR_NONE
+    assert err(product, None) == rt.RTC_ERROR_INVALID_ARGUMENT
+    assert [c for c, _ in seen] == [rt.RTC_ERROR_INVALID_OPERATION, rt.RTC_ERROR_INVALID_OPERATION]
+    L.rtcSetDeviceErrorFunction(hostdev, CB(0), None)
+    L.rtcReleaseGeometry(g)
+
+
+def test_buffer_rules(product, hostdev):
+    """scene_triangle_mesh.cpp:35-80: alignment, formats, slots."""
+    L = product.lib
+    g = L.rtcNewGeometry(hostdev, rt.RTC_GEOMETRY_TYPE_TRIANGLE)
+    v = np.zeros(16, np.float32)
+    L.rtcSetSharedGeometryBuffer(g, rt.RTC_BUFFER_TYPE_VERTEX, 0, rt.RTC_FORMAT_FLOAT3, v.ctypes.data + 2, 0, 12, 3)
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION           # not 4-byte aligned
+    L.rtcSetSharedGeometryBuffer(g, rt.RTC_BUFFER_TYPE_VERTEX, 0, rt.RTC_FORMAT_FLOAT3, v.ctypes.data, 0, 10, 3)
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION           # stride not a multiple of 4
+    L.rtcSetSharedGeometryBuffer(g, rt.RTC_BUFFER_TYPE_VERTEX, 0, rt.RTC_FORMAT_UINT3, v.ctypes.data, 0, 12, 3)
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION           # wrong vertex format
+    L.rtcSetSharedGeometryBuffer(g, rt.RTC_BUFFER_TYPE_INDEX, 1, rt.RTC_FORMAT_UINT3, v.ctypes.data, 0, 12, 1)
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_ARGUMENT            # index slot != 0
+    L.rtcSetSharedGeometryBuffer(g, rt.RTC_BUFFER_TYPE_INDEX, 0, rt.RTC_FORMAT_FLOAT3, v.ctypes.data, 0, 12, 1)
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION           # wrong index format
+    L.rtcSetSharedGeometryBuffer(g, 99, 0, rt.RTC_FORMAT_FLOAT3, v.ctypes.data, 0, 12, 1)
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_ARGUMENT            # unknown buffer type
+    p = L.rtcSetNewGeometryBuffer(g, rt.RTC_BUFFER_TYPE_VERTEX, 0, rt.RTC_FORMAT_FLOAT3, 12, 5)
+    assert p and p % 16 == 0 and L.rtcGetGeometryBufferData(g, rt.RTC_BUFFER_TYPE_VERTEX, 0) == p
+    assert err(product, hostdev) == rt.RTC_ERROR_NONE
+    b = L.rtcNewBuffer(hostdev, 256)
+    assert L.rtcGetBufferData(b)
+    L.rtcSetGeometryBuffer(g, rt.RTC_BUFFER_TYPE_INDEX, 0, rt.RTC_FORMAT_UINT3, b, 4, 12, 8)
+    assert L.rtcGetGeometryBufferData(g, rt.RTC_BUFFER_TYPE_INDEX, 0) == L.rtcGetBufferData(b) + 4
+    L.rtcReleaseBuffer(b)
+    L.rtcReleaseGeometry(g)
+    assert err(product, hostdev) == rt.RTC_ERROR_NONE
+
+
+def test_geometry_ids_lowest_free_first(product, hostdev):
+    """scene.cpp:595-623 + common/sys/alloc.h:100-125: smallest previously freed ID first."""
+    L = product.lib
+    sc = L.rtcNewScene(hostdev)
+    gs = [L.rtcNewGeometry(hostdev, rt.RTC_GEOMETRY_TYPE_TRIANGLE) for _ in range(6)]
+    ids = [L.rtcAttachGeometry(sc, g) for g in gs[:4]]
+    assert ids == [0, 1, 2, 3]
+    L.rtcDetachGeometry(sc, 2)
+    L.rtcDetachGeometry(sc, 0)
+    assert L.rtcAttachGeometry(sc, gs[4]) == 0
+    assert L.rtcAttachGeometry(sc, gs[5]) == 2
+    assert L.rtcGetGeometry(sc, 2) == gs[5] and L.rtcGetGeometry(sc, 1) == gs[1]
+    L.rtcAttachGeometryByID(sc, gs[0], 10)
+    assert L.rtcGetGeometry(sc, 10) == gs[0]
+    assert L.rtcAttachGeometry(sc, gs[2]) == 4                               # ids 4..9 are free now, lowest first
+    L.rtcAttachGeometryByID(sc, gs[3], 1)                                    # occupied
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    L.rtcDetachGeometry(sc, 77)
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    for g in gs:
+        L.rtcReleaseGeometry(g)
+    L.rtcReleaseScene(sc)
+    assert err(product, hostdev) == rt.RTC_ERROR_NONE
+
+
+def test_commit_state_machine_without_gpu(product, hostdev):
+    L = product.lib
+    sc = L.rtcNewScene(hostdev)
+    ctx = product.context()
+    r = rt.new_rays(4)
+    L.rtcIntersect1M(sc, C.byref(ctx), r.ctypes.data, 4, 80)                 # scene.cpp:13,30 missing_rtcCommit
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    b = rt.Bounds()
+    L.rtcGetSceneBounds(sc, C.byref(b))
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    g = L.rtcNewGeometry(hostdev, rt.RTC_GEOMETRY_TYPE_TRIANGLE)
+    L.rtcAttachGeometry(sc, g)
+    L.rtcCommitScene(sc)                                                     # geometry.cpp:103-107
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    L.rtcCommitGeometry(g)
+    import torch
+    if not torch.cuda.is_available():
+        L.rtcCommitScene(sc)                                                 # no device: loud failure, not a CPU build
+        assert err(product, hostdev) == rt.RTC_ERROR_UNKNOWN
+    L.rtcSetSceneFlags(sc, rt.RTC_SCENE_FLAG_ROBUST)
+    assert L.rtcGetSceneFlags(sc) == rt.RTC_SCENE_FLAG_ROBUST
+    L.rtcSetSceneBuildQuality(sc, 7)
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    L.rtcSetGeometryTransform.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_void_p]
+    L.rtcSetGeometryTransform(g, 0, 0, None)                                 # out-of-scope entry point
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    assert L.rtcGetDeviceProperty(hostdev, 0) == 31201 and L.rtcGetDeviceProperty(hostdev, 96) == 1
+    assert L.rtcGetDeviceProperty(hostdev, 66) == 0 and L.rtcGetDeviceProperty(hostdev, 35) == 1
+    L.rtcReleaseGeometry(g)
+    L.rtcReleaseScene(sc)
+
+
+def test_oracle_is_not_on_the_product_path():
+    """Nothing under the package may reference oracle/ (the checker is never the thing shipped)."""
+    pk = os.path.join(ROOT, "embree-aarch64_b200")
+    for dp, _, fs in os.walk(pk):
+        if os.path.basename(dp) in ("build", "lib", "__pycache__"):
+            continue
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "rq_oracle" not in txt and "oracle/" not in txt and "libembree3_ref" not in txt, os.path.join(dp, f)
+    out = subprocess.check_output(["ldd", os.path.join(pk, "lib", "libembree3.so")]).decode()
+    assert "oracle" not in out and "torch" not in out

@@ -1,0 +1,135 @@
+"""Pins the oracle (oracle/rq_oracle.c): against the reference's known-answer expectations, against
+the golden vectors produced by the real reference library, and against the live reference library
+when it exists in this checkout.  CPU only."""
+import numpy as np
+import pytest
+
+import cases
+
+parity = cases.importlib.import_module("embree-aarch64_b200.parity")
+rt, fx = cases.rt, cases.fx
+ULP = np.float32(1.1920928955078125e-07)
+ALL = list(cases.CASES)
+
+
+def _oracle_closest(oracle, g):
+    h = oracle.build(g["meshes"], robust=bool(g["flags"] & rt.RTC_SCENE_FLAG_ROBUST))
+    r = g["rays"].copy()
+    oracle.intersect(h, r)
+    return h, r
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_oracle_matches_golden_closest(oracle, name):
+    g = cases.load_golden(name)
+    h, r = _oracle_closest(oracle, g)
+    res = parity.compare_closest(r, g["closest"])
+    oracle.free(h)
+    if name == "overlapping":      # coincident duplicates: geomID depends on the BVH's test order; t,u,v must agree
+        assert res["hitmiss_disagree"] == 0 and res["id_disagree_unexplained"] == 0, res
+    else:
+        assert res["pass"], res
+    # rays the reference left untouched must be bit-identical (InactiveRaysTest, verify.cpp:2869-2891)
+    miss = g["closest"]["geomID"] == 0xFFFFFFFF
+    assert np.array_equal(r[miss].view(np.uint8), g["closest"][miss].view(np.uint8))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_oracle_matches_golden_occluded(oracle, name):
+    g = cases.load_golden(name)
+    h = oracle.build(g["meshes"], robust=bool(g["flags"] & rt.RTC_SCENE_FLAG_ROBUST))
+    s = g["shadow_in"].copy()
+    oracle.occluded(h, s)
+    assert parity.compare_occluded(s, g["shadow_out"])["disagree"] == 0
+    s2 = cases.occluded_by_group(lambda part: oracle.occluded(h, part), fx.to_ray(g["rays"]), g.get("groups"))
+    res = parity.compare_occluded(s2, g["occl_self_out"])
+    oracle.free(h)
+    assert res["disagree"] == 0 and res["untouched_ok"], res
+    # occluded writes tfar only
+    for k in rt.RAY_DTYPE.names:
+        if k != "tfar":
+            assert np.array_equal(s2[k].view(np.uint32), fx.to_ray(g["rays"])[k].view(np.uint32)), k
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_oracle_builder_reproduces_reference_sah(oracle, name):
+    """The restated binned-SAH builder yields the reference's own SAH figure (BENCHMARK_BUILD) and bounds."""
+    g = cases.load_golden(name)
+    h = oracle.build(g["meshes"])
+    sah, b = oracle.sah(h), oracle.bounds(h)
+    oracle.free(h)
+    # where no median-split fallback / tie is involved the figure is reproduced to print precision;
+    # fallback splits depend on the primitive order inside a partition, which is not specified
+    exact = name not in ("edge_rays", "overlapping")
+    assert abs(sah - g["sah_ref"]) <= (2e-5 if exact else 1e-2) * max(1.0, g["sah_ref"]), (sah, g["sah_ref"])
+    assert np.array_equal(b, g["bounds_ref"])
+
+
+def test_triangle_hit_known_answers(oracle):
+    """TriangleHitTest (verify.cpp:2339-2426): analytic expectations, 16 ulp."""
+    g = cases.load_golden("triangle_hit")
+    h, r = _oracle_closest(oracle, g)
+    oracle.free(h)
+    assert (r["geomID"] == 0).all() and (r["primID"] == 0).all()
+    assert np.abs(r["u"] - g["expect_u"]).max() <= 16 * ULP
+    assert np.abs(r["v"] - g["expect_v"]).max() <= 16 * ULP
+    assert np.abs(r["tfar"] - 1.0).max() <= 16 * ULP
+    ng = np.stack([r["Ng_x"], r["Ng_y"], r["Ng_z"]], 1)
+    assert np.abs(ng - np.array([0, 0, 1], np.float32)).max() <= 16 * ULP
+    p_t = np.stack([r["org_x"] + r["tfar"] * r["dir_x"], r["org_y"] + r["tfar"] * r["dir_y"], r["org_z"] + r["tfar"] * r["dir_z"]], 1)
+    p_uv = np.stack([r["u"], r["v"], np.zeros_like(r["u"])], 1)
+    assert np.abs(p_t - p_uv).max() <= 16 * ULP
+
+
+def test_small_triangles_known_prims(oracle):
+    """SmallTriangleHitTest (verify.cpp:2981-3048): the aimed-at primID, failure rate <= 2e-5."""
+    g = cases.load_golden("small_triangles")
+    h, r = _oracle_closest(oracle, g)
+    oracle.free(h)
+    assert (r["primID"] != g["expect_prim"]).mean() <= 2e-5
+
+
+def test_watertight_all_hit(oracle):
+    """WatertightTest (verify.cpp:2898-2979): from inside a closed far-away sphere every ray hits (ROBUST)."""
+    g = cases.load_golden("robust_far_sphere")
+    h, r = _oracle_closest(oracle, g)
+    oracle.free(h)
+    assert (r["geomID"] == 0xFFFFFFFF).mean() <= 2e-5
+
+
+def test_single_triangle_intersectors(oracle):
+    ok, o = oracle.tri_test((0.25, 0.25, -1), (0, 0, 1), 0.0, np.inf, (0, 0, 0), (1, 0, 0), (0, 1, 0))
+    assert ok and abs(o[0] - 1) < 1e-6 and abs(o[1] - 0.25) < 1e-6 and abs(o[2] - 0.25) < 1e-6 and tuple(o[3:]) == (0, 0, 1)
+    ok, o = oracle.tri_test((0.25, 0.25, -1), (0, 0, 1), 0.0, np.inf, (0, 0, 0), (1, 0, 0), (0, 1, 0), robust=True)
+    assert ok and abs(o[0] - 1) < 1e-6 and abs(o[1] - 0.25) < 1e-6
+    assert not oracle.tri_test((2, 2, -1), (0, 0, 1), 0.0, np.inf, (0, 0, 0), (1, 0, 0), (0, 1, 0))[0]
+    assert not oracle.tri_test((0.25, 0.25, -1), (0, 0, 1), 0.0, 0.5, (0, 0, 0), (1, 0, 0), (0, 1, 0))[0]        # tfar too short
+    assert not oracle.tri_test((0.25, 0.25, -1), (1, 0, 0), 0.0, np.inf, (0, 0, 0), (1, 0, 0), (0, 1, 0))[0]     # parallel: den == 0
+
+
+@pytest.mark.parametrize("scale,seed", [(0.12, 3), (0.2, 4)])
+def test_oracle_matches_live_reference(oracle, reflib, scale, seed):
+    """Larger randomised check against the real library when it is available in this checkout."""
+    meshes = fx.scene_c2(scale)
+    dev = reflib.new_device("")
+    sc, keep = reflib.build_scene(dev, meshes)
+    h = oracle.build(meshes)
+    prim = fx.primary_rays(128, 128, **fx.C2_CAMERA)
+    a, b = prim.copy(), prim.copy()
+    oracle.intersect(h, a)
+    reflib.intersect(sc, b)
+    assert parity.compare_closest(a, b)["pass"]
+    d = fx.diffuse_rays(b, sample_id=seed)
+    a, b = d.copy(), d.copy()
+    oracle.intersect(h, a)
+    reflib.intersect(sc, b)
+    res = parity.compare_closest(a, b)
+    assert res["pass"], res
+    s = fx.shadow_rays(b)
+    s1, s2 = s.copy(), s.copy()
+    oracle.occluded(h, s1)
+    reflib.occluded(sc, s2)
+    assert parity.compare_occluded(s1, s2)["pass"]
+    oracle.free(h)
+    reflib.lib.rtcReleaseScene(sc)
+    reflib.lib.rtcReleaseDevice(dev)

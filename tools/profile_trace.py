@@ -1,0 +1,43 @@
+"""Profiling harness: prepares the configs[1] (or c3) streams on the device, then brackets exactly one
+closest-hit launch and one occlusion launch with cudaProfilerStart/Stop (use ncu --profile-from-start off)."""
+import argparse, importlib, sys, time
+import numpy as np
+sys.path.insert(0, ".")
+pkg = importlib.import_module("embree-aarch64_b200")
+fx, rt = pkg.fixtures, pkg.rtcore
+import torch
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="c2")
+ap.add_argument("--bands", type=int, default=8)
+ap.add_argument("--reps", type=int, default=1)
+args = ap.parse_args()
+lib = rt.RTCore()
+dev = lib.new_device("async=1")
+st = torch.cuda.Stream(); torch.cuda.set_stream(st)
+lib.lib.rtcxSetDeviceStream(dev, st.cuda_stream)
+meshes = fx.scene_c3(1.0) if args.workload == "c3" else fx.scene_c2(1.0)
+sc, keep = lib.build_scene(dev, meshes)
+print("build", lib.build_stats(sc), flush=True)
+d_parts, s_parts = [], []
+for b in range(args.bands):
+    prim = fx.primary_rays(4096, 4096, rows=(b * 512, b * 512 + 512), **fx.C2_CAMERA)
+    lib.intersect(sc, prim, coherent=True)
+    d_parts.append(fx.diffuse_rays(prim)); s_parts.append(fx.shadow_rays(prim))
+diffuse, shadow = np.concatenate(d_parts), np.concatenate(s_parts)
+nd, ns = len(diffuse), len(shadow)
+p_d = torch.from_numpy(diffuse.view(np.uint8).reshape(nd, 80)).cuda()
+p_s = torch.from_numpy(shadow.view(np.uint8).reshape(ns, 48)).cuda()
+w_d, w_s = p_d.clone(), p_s.clone()
+lib.intersect_ptr(sc, w_d.data_ptr(), nd, 80); lib.occluded_ptr(sc, w_s.data_ptr(), ns, 48)
+torch.cuda.synchronize()
+for rep in range(args.reps):
+    w_d.copy_(p_d); w_s.copy_(p_s); torch.cuda.synchronize()
+    e = [torch.cuda.Event(True) for _ in range(3)]
+    torch.cuda.profiler.start()
+    e[0].record(); lib.intersect_ptr(sc, w_d.data_ptr(), nd, 80)
+    e[1].record(); lib.occluded_ptr(sc, w_s.data_ptr(), ns, 48)
+    e[2].record(); torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    print("closest %.3f ms %.1f Mrays/s | occluded %.3f ms %.1f Mrays/s" % (e[0].elapsed_time(e[1]), nd / e[0].elapsed_time(e[1]) / 1e3,
+          e[1].elapsed_time(e[2]), ns / e[1].elapsed_time(e[2]) / 1e3), flush=True)
