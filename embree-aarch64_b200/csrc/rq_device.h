@@ -40,7 +40,8 @@ struct RQTraceArgs {
   uint32_t    instID0;
   uint32_t    streamSemantics;  // occluded only: 1 = stream entry rules (M>1), 0 = single-ray rules
   RQTraceCounters* counters;    // device pointer or NULL (NULL = fast kernel)
-  unsigned int* workCounter;    // device scratch word (zeroed by the launcher)
+  unsigned int* workCounter;    // device scratch word, exclusive to this launch until it completes (zeroed by the launcher)
+  uint32_t    refillBelow;      // persistent-kernel refill threshold in lanes, 0 = default
 };
 int rqLaunchIntersect(const RQTraceArgs* a, rqStream stream);
 int rqLaunchOccluded(const RQTraceArgs* a, rqStream stream);

@@ -71,6 +71,9 @@ struct Device : RefCounted {
   void* ringBuf[kRing] = {nullptr, nullptr, nullptr, nullptr};
   size_t ringCap[kRing] = {0, 0, 0, 0};
   RQTraceCounters* dCounters = nullptr;
+  unsigned int* dWork = nullptr;          // ray cursors of the persistent kernels: one per ring stream + one for the device stream
+  std::mutex launchMutex;                 // (cursor reset + launch) pairs on the device stream are enqueued atomically
+  unsigned refillBelow = 0;
 
   cudaStream_t stream() const { return userStream ? userStream : ownStream; }
   void bind() const { if (hasGpu) cudaSetDevice(ordinal); }
@@ -80,6 +83,7 @@ struct Device : RefCounted {
       cudaSetDevice(ordinal);
       for (int i = 0; i < kRing; i++) { if (ringBuf[i]) cudaFree(ringBuf[i]); if (ringStream[i]) cudaStreamDestroy(ringStream[i]); }
       if (dCounters) cudaFree(dCounters);
+      if (dWork) cudaFree(dWork);
       if (ownStream) cudaStreamDestroy(ownStream);
     }
   }
@@ -130,6 +134,7 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "cost_node") d->build.costNode = (float)atof(v.c_str());
     else if (k == "cost_tri") d->build.costTri = (float)atof(v.c_str());
     else if (k == "leaf_tris") d->build.maxLeafTris = atoi(v.c_str());
+    else if (k == "refill") d->refillBelow = (unsigned)std::max(0, std::min(32, atoi(v.c_str())));
     else if (k == "allow_no_gpu") *allowNoGpu = atoi(v.c_str()) != 0;
   }
   d->build.verbose = d->verbose;
@@ -301,10 +306,15 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
     cudaCheck(cudaStreamSynchronize(dev->stream()), "counters");
   }
   a.counters = dC;
+  a.refillBelow = dev->refillBelow;
   if (isDevicePointer(rays)) {
     cudaStream_t s = dev->stream();
     a.rays = rays; a.numRays = M; a.stride = stride;
-    cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
+    a.workCounter = dev->dWork + 8 * Device::kRing;
+    {
+      std::lock_guard<std::mutex> ll(dev->launchMutex);
+      cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
+    }
     if (!dev->async || countersOut) cudaCheck(cudaStreamSynchronize(s), "trace");
   } else {
     std::lock_guard<std::mutex> l(dev->stageMutex);     // host-staged calls of one device are serialised
@@ -326,6 +336,7 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
       cudaStream_t s = dev->ringStream[r];
       cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], h, span, cudaMemcpyHostToDevice, s), "ray upload");
       a.rays = dev->ringBuf[r]; a.numRays = n; a.stride = stride;
+      a.workCounter = dev->dWork + 8 * r;
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
       cudaCheck(cudaMemcpyAsync(h, dev->ringBuf[r], span, cudaMemcpyDeviceToHost, s), "hit download");
       done += n;
@@ -419,6 +430,7 @@ RTC_API RTCDevice rtcNewDevice(const char* config) {
       d->hasGpu = true;
       d->bind();
       cudaCheck(cudaStreamCreateWithFlags(&d->ownStream, cudaStreamNonBlocking), "stream");
+      cudaCheck(cudaMalloc((void**)&d->dWork, 32 * (Device::kRing + 1)), "work counters");
       if (d->verbose >= 1)
         printf("b200-rayquery %s on GPU %d: %s, %d SMs, %.1f GB\n", RTC_VERSION_STRING, d->ordinal, p.name, p.multiProcessorCount, p.totalGlobalMem / 1e9);
     }

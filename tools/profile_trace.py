@@ -11,9 +11,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c2")
 ap.add_argument("--bands", type=int, default=8)
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--cfg", default="")
 args = ap.parse_args()
 lib = rt.RTCore()
-dev = lib.new_device("async=1")
+dev = lib.new_device("async=1," + args.cfg)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 lib.lib.rtcxSetDeviceStream(dev, st.cuda_stream)
 meshes = fx.scene_c3(1.0) if args.workload == "c3" else fx.scene_c2(1.0)
