@@ -42,6 +42,7 @@ struct RQTraceArgs {
   RQTraceCounters* counters;    // device pointer or NULL (NULL = fast kernel)
   unsigned int* workCounter;    // device scratch word, exclusive to this launch until it completes (zeroed by the launcher)
   uint32_t    refillBelow;      // persistent-kernel refill threshold in lanes, 0 = default
+  uint32_t    split;            // traversal loop shape: 1 = one triangle per iteration, 0 = whole leaf list per node
 };
 int rqLaunchIntersect(const RQTraceArgs* a, rqStream stream);
 int rqLaunchOccluded(const RQTraceArgs* a, rqStream stream);

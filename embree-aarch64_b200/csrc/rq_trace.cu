@@ -33,6 +33,7 @@ struct TraceParams {
   uint32_t numRays;
   uint32_t instID0;
   uint32_t streamSemantics;
+  uint32_t split;            // 1 = one triangle per loop iteration (T/N split), 0 = whole leaf list at once
   uint32_t refillBelow;      // idle lanes fetch new rays when fewer than this many lanes are traversing
   unsigned int* workCounter; // global ray cursor, zero at launch
   RQTraceCounters* counters;
@@ -62,7 +63,7 @@ __device__ __forceinline__ float byteToUnit(uint32_t w, uint32_t j) {
 // ray goes idle; when fewer than P.refillBelow lanes of the warp are still traversing, the idle
 // lanes fetch new rays (one atomicAdd per warp per refill), so SIMD lanes stay busy although ray
 // lifetimes differ by an order of magnitude (miss after 4 nodes vs hit after 40).
-template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, int STACK>
+template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int STACK>
 __global__ void __launch_bounds__(128)
 k_trace(const TraceParams P) {
   const unsigned lane = threadIdx.x & 31u;
@@ -80,7 +81,7 @@ k_trace(const TraceParams P) {
   uint32_t tmask = 0u, triBase = 0u;                            // pending leaf triangles of the current node
   bool found = false;
   float hu = 0.f, hv = 0.f; RQVec3 hNg = rq_v3(0.f, 0.f, 0.f); uint32_t hPrim = 0, hGeom = 0;
-  unsigned long long cntRays = 0, cntNodes = 0, cntTris = 0, cntHits = 0; unsigned cntStack = 0;
+  unsigned long long cntRays = 0, cntNodes = 0, cntTris = 0, cntHits = 0, cntEmpty = 0, cntHitNodes = 0; unsigned cntStack = 0, rayNodes = 0;
   bool exhausted = false;                                       // warp-uniform: the global counter ran past numRays
 
   for (;;) {
@@ -117,7 +118,7 @@ k_trace(const TraceParams P) {
               tnearBox = fmaxf(tnear, 0.0f);
               octinv = 7u - ((dx < 0.f ? 1u : 0u) | (dy < 0.f ? 2u : 0u) | (dz < 0.f ? 4u : 0u));
               ng = make_uint2(0u, 0x80000000u);                 // virtual parent: one inner hit -> node 0
-              if (COUNT) cntRays++;
+              if (COUNT) { cntRays++; rayNodes = 0; }
             }
           }
         }
@@ -139,7 +140,9 @@ k_trace(const TraceParams P) {
       // ---------------- T phase ----------------
       const bool hasTri = active && (tmask != 0u);
       if (__any_sync(FULL, hasTri)) {
-        if (hasTri) {
+        // SPLIT: one triangle per iteration (incoherent streams); otherwise the whole list now
+        // (coherent streams: neighbouring lanes have lists of similar length)
+        while (SPLIT ? hasTri : (active && tmask != 0u)) {
           const uint32_t b = 31u - (uint32_t)__clz((int)tmask);
           tmask &= ~(1u << b);
           const float4* tp = P.tris + (size_t)(triBase + b) * 3;
@@ -157,6 +160,7 @@ k_trace(const TraceParams P) {
               hPrim = __float_as_uint(t2.y); hGeom = __float_as_uint(t2.z);
             }
           }
+          if (SPLIT) break;
         }
       }
       // ---------------- N phase ----------------
@@ -167,7 +171,7 @@ k_trace(const TraceParams P) {
             active = false;
             if (found) {
               char* rp = P.rays + (size_t)rid * P.stride;
-              if (COUNT) cntHits++;
+              if (COUNT) { cntHits++; cntHitNodes += rayNodes; }
               if (OCCLUDED) {
                 *(float*)(rp + 32) = -INFINITY;
               } else {
@@ -199,7 +203,7 @@ k_trace(const TraceParams P) {
           const uint32_t rel = __popc(ng.y & 0xFFu & ((1u << slot) - 1u));
           const uint4* np = P.nodes + (size_t)(ng.x + rel) * 8;
           const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-          if (COUNT) cntNodes++;
+          if (COUNT) { cntNodes++; rayNodes++; }
 
           // Slab test of the 8 quantised child boxes.  Plane q of an axis lies at t = q*a + b with
           // a = 2^e * idir (t per grid step) and b = (p - org) * idir.  The byte q is turned into the
@@ -255,6 +259,7 @@ k_trace(const TraceParams P) {
               hitmask |= ((tmin <= tmax) | overflow) ? contrib : 0u;
             }
           }
+          if (COUNT && hitmask == 0u) cntEmpty++;
           ng = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
           tmask = hitmask & 0x00FFFFFFu;
           triBase = n1.y;
@@ -271,6 +276,8 @@ k_trace(const TraceParams P) {
     atomicAdd(&P.counters->nodes, cntNodes);
     atomicAdd(&P.counters->tris, cntTris);
     atomicAdd(&P.counters->hits, cntHits);
+    atomicAdd(&P.counters->emptyNodes, cntEmpty);
+    atomicAdd(&P.counters->hitNodes, cntHitNodes);
     atomicMax(&P.counters->stackMax, (unsigned long long)cntStack);
   }
 }
@@ -293,9 +300,12 @@ cudaError_t launchOne(void (*kern)(const TraceParams), const TraceParams& P, cud
 
 template <bool OCC, bool ROBUST, bool COUNT, bool ALIGNED>
 cudaError_t launchStack(const TraceParams& P, uint32_t depth, cudaStream_t s) {
-  if (depth <= 32) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, 32>, P, s);
-  if (depth <= 96) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, 96>, P, s);
-  return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, 208>, P, s);
+  if (depth <= 32) {
+    if (P.split) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, true, 32>, P, s);
+    return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 32>, P, s);
+  }
+  if (depth <= 96) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 96>, P, s);
+  return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 208>, P, s);
 }
 
 }  // namespace
@@ -310,7 +320,8 @@ static int launchTrace(bool occ, const RQTraceArgs* a, cudaStream_t s) {
   P.rays = (char*)a->rays; P.stride = a->stride; P.numRays = a->numRays; P.instID0 = a->instID0;
   P.streamSemantics = a->streamSemantics; P.counters = a->counters;
   P.workCounter = a->workCounter;
-  P.refillBelow = a->refillBelow ? a->refillBelow : 20u;
+  P.refillBelow = a->refillBelow ? a->refillBelow : 26u;
+  P.split = a->split;
   if (!P.workCounter) return (int)cudaErrorInvalidValue;
   {
     cudaError_t ez = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), s);   // stream ordered with the launch

@@ -105,4 +105,6 @@ struct RQTraceCounters {
   unsigned long long tris;        // triangle records fetched
   unsigned long long hits;        // rays that report a hit / are occluded
   unsigned long long stackMax;    // deepest traversal stack seen
+  unsigned long long emptyNodes;  // node records fetched whose children were all missed / culled
+  unsigned long long hitNodes;    // node records fetched by rays that end up reporting a hit
 };

@@ -73,7 +73,11 @@ struct Device : RefCounted {
   RQTraceCounters* dCounters = nullptr;
   unsigned int* dWork = nullptr;          // ray cursors of the persistent kernels: one per ring stream + one for the device stream
   std::mutex launchMutex;                 // (cursor reset + launch) pairs on the device stream are enqueued atomically
-  unsigned refillBelow = 0;
+  // traversal schedule per query kind, tuned on B200 (DESIGN.md "traversal schedule"): incoherent
+  // closest-hit streams refill idle lanes early and take one triangle per iteration; coherent
+  // streams and occlusion streams keep a warp's rays together (late refill, whole leaf lists)
+  int refillClosest = 26, refillCoherent = 4, refillOccluded = 4;
+  int splitClosest = 1, splitCoherent = 0, splitOccluded = 0;
 
   cudaStream_t stream() const { return userStream ? userStream : ownStream; }
   void bind() const { if (hasGpu) cudaSetDevice(ordinal); }
@@ -134,7 +138,12 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "cost_node") d->build.costNode = (float)atof(v.c_str());
     else if (k == "cost_tri") d->build.costTri = (float)atof(v.c_str());
     else if (k == "leaf_tris") d->build.maxLeafTris = atoi(v.c_str());
-    else if (k == "refill") d->refillBelow = (unsigned)std::max(0, std::min(32, atoi(v.c_str())));
+    else if (k == "split_closest") d->splitClosest = atoi(v.c_str());
+    else if (k == "split_occluded") d->splitOccluded = atoi(v.c_str());
+    else if (k == "refill") d->refillClosest = std::max(1, std::min(32, atoi(v.c_str())));
+    else if (k == "refill_coherent") d->refillCoherent = std::max(1, std::min(32, atoi(v.c_str())));
+    else if (k == "refill_occluded") d->refillOccluded = std::max(1, std::min(32, atoi(v.c_str())));
+    else if (k == "split_coherent") d->splitCoherent = atoi(v.c_str());
     else if (k == "allow_no_gpu") *allowNoGpu = atoi(v.c_str()) != 0;
   }
   d->build.verbose = d->verbose;
@@ -306,7 +315,9 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
     cudaCheck(cudaStreamSynchronize(dev->stream()), "counters");
   }
   a.counters = dC;
-  a.refillBelow = dev->refillBelow;
+  const bool coherent = ctx && (ctx->flags & RTC_INTERSECT_CONTEXT_FLAG_COHERENT);   // a hint only, as in the reference
+  a.refillBelow = (unsigned)(occluded ? dev->refillOccluded : coherent ? dev->refillCoherent : dev->refillClosest);
+  a.split = (occluded ? dev->splitOccluded : coherent ? dev->splitCoherent : dev->splitClosest) ? 1u : 0u;
   if (isDevicePointer(rays)) {
     cudaStream_t s = dev->stream();
     a.rays = rays; a.numRays = M; a.stride = stride;

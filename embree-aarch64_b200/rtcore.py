@@ -63,7 +63,8 @@ class BuildStats(C.Structure):
 
 class TraceCounters(C.Structure):
     _fields_ = [("rays", C.c_ulonglong), ("nodes", C.c_ulonglong), ("tris", C.c_ulonglong),
-                ("hits", C.c_ulonglong), ("stackMax", C.c_ulonglong)]
+                ("hits", C.c_ulonglong), ("stackMax", C.c_ulonglong), ("emptyNodes", C.c_ulonglong),
+                ("hitNodes", C.c_ulonglong)]
 
 
 def new_rays(n, hit=True):

@@ -32,6 +32,8 @@ struct RTCXTraceCounters {
   unsigned long long tris;      /* triangle records fetched (x48 B)                               */
   unsigned long long hits;      /* rays that found a hit / are occluded                           */
   unsigned long long stackMax;  /* deepest traversal stack                                        */
+  unsigned long long emptyNodes;/* node records fetched whose children were all missed or culled  */
+  unsigned long long hitNodes;  /* node records fetched by rays that report a hit                 */
 };
 
 /* Stream (a cudaStream_t passed as void*) on which builds and device-resident queries are
