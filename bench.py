@@ -216,22 +216,8 @@ def run_ours(args):
         build = lib.build_stats(sc)
         build["commit_wall_ms"] = float(np.median(build_times) * 1e3)
     if world > 1:
-        nbytes = C.c_size_t(0)
-        if rank == 0:
-            lib.lib.rtcxGetSceneImage(sc, C.byref(nbytes))
-        size = torch.tensor([nbytes.value], dtype=torch.int64, device="cuda")
-        dist.broadcast(size, 0)
-        img = torch.empty(int(size.item()), dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            lib.lib.rtcxCopySceneImage(sc, img.data_ptr(), nbytes.value)
-        torch.cuda.synchronize(); dist.barrier()
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record(); dist.broadcast(img, 0); e1.record(); torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
-        if rank != 0:
-            sc = lib.lib.rtcNewScene(dev)
-            lib.lib.rtcxSetSceneImage(sc, img.data_ptr(), img.numel())
-        del img
+        mg = importlib.import_module("embree-aarch64_b200.multigpu")
+        sc, bcast_ms = mg.replicate_scene(lib, dev, sc if rank == 0 else None, 0)
     assert lib.lib.rtcGetDeviceError(dev) == 0
 
     # ---- this rank's shard: full 4096x4096 frame, sampler seed = rank (weak scaling) ----
