@@ -213,11 +213,12 @@ bool isDevicePointer(const void* p) {
 }
 
 struct TempDev {                                         // device copies of host geometry buffers, freed after the build
-  std::vector<void*> ptrs;
-  ~TempDev() { for (void* p : ptrs) cudaFree(p); }
+  std::vector<void*> ptrs; cudaStream_t stream = nullptr;   // stream-ordered pool: no cudaMalloc/cudaFree stalls on re-commit
+  ~TempDev() { for (void* p : ptrs) cudaFreeAsync(p, stream); }
   const uint8_t* upload(const char* src, size_t bytes, cudaStream_t s) {
     void* d = nullptr;
-    cudaCheck(cudaMalloc(&d, bytes ? bytes : 16), "geometry upload (alloc)");
+    stream = s;
+    cudaCheck(cudaMallocAsync(&d, bytes ? bytes : 16, s), "geometry upload (alloc)");
     ptrs.push_back(d);
     if (bytes) cudaCheck(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s), "geometry upload (copy)");
     return (const uint8_t*)d;
