@@ -512,9 +512,8 @@ emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2*
     step[a] = __uint_as_float((uint32_t)eb << 23);             // 2^(eb-127)
     inv[a] = __uint_as_float((uint32_t)(254 - eb) << 23);       // 2^(127-eb)
   }
-  N.imask = 0; N.childBase = childBase; N.triBase = triBase;
+  N.pad0 = 0; N.pad1 = 0; N.masks = 0; N.childBase = childBase; N.triBase = triBase;
   for (int s = 0; s < 8; s++) {
-    N.meta[s] = 0;
     for (int a = 0; a < 3; a++) { N.qlo[a][s] = 255; N.qhi[a][s] = 0; }
   }
   uint32_t innerRank = 0, triOff = 0;
@@ -534,20 +533,20 @@ emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2*
     const double Aq = (double)halfArea(dq[0], dq[1], dq[2]);
     const double Ax = (double)halfArea(chi[c][0] - clo[c][0], chi[c][1] - clo[c][1], chi[c][2] - clo[c][2]);
     if (inner[c]) {
-      N.imask |= (uint8_t)(1u << s);
-      N.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
+      N.masks |= 1u << (24 + s);
       nextQueue[qBase + innerRank] = make_uint2(child[c], childBase + innerRank);
       nextParentOf[qBase + innerRank] = w;
       innerRank++;
       sahInnerQ += Aq; sahInnerX += Ax;
     } else {
       const uint32_t nt = ctris[c];                           // 1..3
-      N.meta[s] = (uint8_t)((((1u << nt) - 1u) << 5) | triOff);
+      N.masks |= ((1u << nt) - 1u) << (3 * s);                // triangles are stored in slot order
       const uint32_t first = child[c] >= firstLeaf ? child[c] - firstLeaf : t.rangeFirst[child[c]];
       for (uint32_t j = 0; j < nt; j++) {
         const float4* src = (const float4*)(trisIn + vals[first + j]);
         float4* dst = (float4*)(trisOut + triBase + triOff + j);
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        if ((triBase + triOff + j) & 1u) { dst[0] = src[2]; dst[1] = src[0]; dst[2] = src[1]; }   // odd records: last 16 bytes first (rq_types.h)
+        else { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
       }
       triOff += nt;
       sahLeafQ += Aq * (double)((nt + 3) / 4); sahLeafX += Ax * (double)((nt + 3) / 4);

@@ -43,6 +43,7 @@ struct RQTraceArgs {
   unsigned int* workCounter;    // device scratch word, exclusive to this launch until it completes (zeroed by the launcher)
   uint32_t    refillBelow;      // persistent-kernel refill threshold in lanes, 0 = default
   uint32_t    split;            // traversal loop shape: 1 = one triangle per iteration, 0 = whole leaf list per node
+  uint32_t    tVote;            // split only: 0 = both phases every iteration, K = triangle phase when >= K lanes wait for it
 };
 int rqLaunchIntersect(const RQTraceArgs* a, rqStream stream);
 int rqLaunchOccluded(const RQTraceArgs* a, rqStream stream);

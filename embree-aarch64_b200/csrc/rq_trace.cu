@@ -26,14 +26,16 @@
 namespace {
 
 struct TraceParams {
-  const uint4* nodes;        // RQNode array viewed as 8 x uint4 per node
-  const float4* tris;        // RQTri array viewed as 3 x float4 per triangle
+  const char* nodes;         // RQNode array, 128 bytes per node (traversal reads bytes 0..95 as 3 x 32 B)
+  const char* tris;          // RQTri array, 48 bytes per triangle (32 + 16 B, order by index parity: rq_types.h)
   char* rays;
   size_t stride;
   uint32_t numRays;
   uint32_t instID0;
   uint32_t streamSemantics;
   uint32_t split;            // 1 = one triangle per loop iteration (T/N split), 0 = whole leaf list at once
+  uint32_t tVote;            // split only: 0 = T then N every iteration; K >= 1 = one phase per iteration, T when >= K lanes wait for it
+  uint32_t sdepth;           // stack entries per thread kept in shared memory (the rest spills to local memory)
   uint32_t refillBelow;      // idle lanes fetch new rays when fewer than this many lanes are traversing
   unsigned int* workCounter; // global ray cursor, zero at launch
   RQTraceCounters* counters;
@@ -44,15 +46,28 @@ __device__ __forceinline__ float rcpSafe(float d) {           // common/math/vec
   return 1.0f / a;
 }
 
-// byte j of w as float WITHOUT the int->float converter: I2F.U8 issues on the quarter-rate XU pipe and
-// 48 of them per node made that pipe the limiter (ncu: xu 54-71 % busy).  PRMT drops the byte into
-// the mantissa of 2^23 (0x4B000000 | q == 8388608 + q exactly), one FADD removes the bias.
-__device__ __forceinline__ float byteToFloat(uint32_t w, uint32_t j) {
-  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | j)) - 8388608.0f;
-}
-// byte j of w as the float 1 + q*2^-15 (bits 0x3F80qq00): a single PRMT, the bias is folded into the FMA
+// Byte j of w as the float 1 + q*2^-16 (bits 0x3F800000 + q*128) with ONE integer dot product:
+// IDP.4A issues on the FMA-heavy pipe.  History (ncu, profiles/): I2F.U8 kept the quarter-rate XU
+// pipe 54-71 % busy; PRMT (bits 0x3F80qq00) moved the work to the half-rate ALU pipe, which then
+// became the limiter (alu 65-74 % of peak, fma 30 %, stall math_pipe_throttle); the dot product
+// moves it to the pipe that has room.  The bias is folded into the FMA of the slab test.
 __device__ __forceinline__ float byteToUnit(uint32_t w, uint32_t j) {
-  return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (j << 4)));
+  return __uint_as_float(__dp4a(w, 0x80u << (8u * j), 0x3F800000u));
+}
+
+// 256-bit read-only global load (LDG.E.256.CONSTANT, new on sm_100).  The L1 data pipe spends one
+// wavefront per 128-byte line a load instruction touches, whatever its width; with divergent rays
+// every lane touches its own line, so an 80-byte node read as 5 x 16 B cost 5 wavefronts per lane
+// and made l1tex__data_pipe_lsu_wavefronts the limiter (82 % of peak, profiles/r01b_ncu_trace.txt).
+// Three 32-byte loads per node and 32 + 16 bytes per triangle cut that by 40 %.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+#ifdef RQ_LD128                                                  // A/B switch: two 16-byte loads instead
+  const uint4 a = __ldg((const uint4*)p), b = __ldg((const uint4*)p + 1);
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+  return;
+#endif
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
 }
 
 // far-plane inflation (1 + 2^-22): absorbs the rounding of the slab arithmetic so a box is never
@@ -63,11 +78,35 @@ __device__ __forceinline__ float byteToUnit(uint32_t w, uint32_t j) {
 // ray goes idle; when fewer than P.refillBelow lanes of the warp are still traversing, the idle
 // lanes fetch new rays (one atomicAdd per warp per refill), so SIMD lanes stay busy although ray
 // lifetimes differ by an order of magnitude (miss after 4 nodes vs hit after 40).
-template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int STACK>
+template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int SPILL>
 __global__ void __launch_bounds__(128)
 k_trace(const TraceParams P) {
+  // Traversal stack: one 8-byte node-group entry per tree level.  The first P.sdepth levels live
+  // in shared memory, entry-major ([level][thread]) so that lanes with different stack depths still
+  // hit 32 different banks: a push/pop is 2 wavefronts per warp.  In local memory the same access
+  // touched one line per lane and the stack made up 27 % of all L1 sectors
+  // (profiles/r01c: 192 M local of 717 M sectors).  Levels beyond P.sdepth spill to local memory.
+  extern __shared__ uint2 s_stack[];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned FULL = 0xffffffffu;
+
+  // Per-node bookkeeping by table instead of per-child shifts (LDS runs on the idle LSU pipe):
+  //   s_perm[o][m]: slot mask m -> priority mask, slot k moves to bit k ^ o (o = 7 - ray octant)
+  //   s_exp3[m]   : slot mask m -> triangle mask, slot k covers bits 3k..3k+2
+  __shared__ uint8_t s_perm[8 * 256];
+  __shared__ uint32_t s_exp3[256];
+  for (unsigned i = threadIdx.x; i < 8u * 256u; i += blockDim.x) {
+    const unsigned o = i >> 8, m = i & 255u;
+    unsigned r = 0;
+    for (unsigned k = 0; k < 8; k++) if (m & (1u << k)) r |= 1u << (k ^ o);
+    s_perm[i] = (uint8_t)r;
+  }
+  for (unsigned m = threadIdx.x; m < 256u; m += blockDim.x) {
+    unsigned r = 0;
+    for (unsigned k = 0; k < 8; k++) if (m & (1u << k)) r |= 7u << (3u * k);
+    s_exp3[m] = r;
+  }
+  __syncthreads();
 
   // ---- per-lane ray state ----
   bool active = false;
@@ -75,10 +114,11 @@ k_trace(const TraceParams P) {
   float ox = 0.f, oy = 0.f, oz = 0.f, tnear = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, tfar = 0.f;
   float idx_ = 0.f, idy_ = 0.f, idz_ = 0.f, tnearBox = 0.f;
   uint32_t octinv = 0;
-  uint2 stack[STACK];
+  uint2 spill[SPILL ? SPILL : 1];
+  const uint32_t sdepth = P.sdepth;
   int sp = 0;
   uint2 ng = make_uint2(0u, 0u);
-  uint32_t tmask = 0u, triBase = 0u;                            // pending leaf triangles of the current node
+  uint32_t tmask = 0u, triBase = 0u, tvalid = 0u;               // pending leaf triangles of the current node
   bool found = false;
   float hu = 0.f, hv = 0.f; RQVec3 hNg = rq_v3(0.f, 0.f, 0.f); uint32_t hPrim = 0, hGeom = 0;
   unsigned long long cntRays = 0, cntNodes = 0, cntTris = 0, cntHits = 0, cntEmpty = 0, cntHitNodes = 0; unsigned cntStack = 0, rayNodes = 0;
@@ -139,16 +179,32 @@ k_trace(const TraceParams P) {
       const RQVec3 O = rq_v3(ox, oy, oz), D = rq_v3(dx, dy, dz);
       // ---------------- T phase ----------------
       const bool hasTri = active && (tmask != 0u);
-      if (__any_sync(FULL, hasTri)) {
+      const unsigned tb = __ballot_sync(FULL, hasTri);
+      // Phase vote (SPLIT with P.tVote = K >= 1): an iteration runs ONE phase.  Lanes that reach
+      // triangles wait until K lanes do (or nobody has a node to visit), so the expensive N phase
+      // (~230 instructions) no longer runs with the T lanes switched off and the T phase
+      // (~120 instructions) runs at least K lanes wide.
+      bool runN = true;
+      if (SPLIT && P.tVote) {
+        const unsigned nb = __ballot_sync(FULL, active && tmask == 0u);
+        runN = !(tb != 0u && ((unsigned)__popc(tb) >= P.tVote || nb == 0u));
+      }
+      if (tb != 0u && !(SPLIT && P.tVote && runN)) {
         // SPLIT: one triangle per iteration (incoherent streams); otherwise the whole list now
         // (coherent streams: neighbouring lanes have lists of similar length)
         while (SPLIT ? hasTri : (active && tmask != 0u)) {
           const uint32_t b = 31u - (uint32_t)__clz((int)tmask);
           tmask &= ~(1u << b);
-          const float4* tp = P.tris + (size_t)(triBase + b) * 3;
-          const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+          const uint32_t ti = triBase + __popc(tvalid & ((1u << b) - 1u));
+          const char* tp = P.tris + (size_t)ti * 48;
+          const uint32_t odd = ti & 1u;                         // odd records store their last 16 bytes first (32-byte alignment of the wide load)
+          uint32_t tw[8];
+          ldg256(tp + (odd ? 16 : 0), tw);
+          const float4 t2 = __ldg((const float4*)(tp + (odd ? 0 : 32)));
           if (COUNT) cntTris++;
-          const RQVec3 v0 = rq_v3(t0.x, t0.y, t0.z), v1 = rq_v3(t0.w, t1.x, t1.y), v2 = rq_v3(t1.z, t1.w, t2.x);
+          const RQVec3 v0 = rq_v3(__uint_as_float(tw[0]), __uint_as_float(tw[1]), __uint_as_float(tw[2]));
+          const RQVec3 v1 = rq_v3(__uint_as_float(tw[3]), __uint_as_float(tw[4]), __uint_as_float(tw[5]));
+          const RQVec3 v2 = rq_v3(__uint_as_float(tw[6]), __uint_as_float(tw[7]), t2.x);
           RQTriHit h;
           const bool ok = ROBUST ? rq_pluecker(O, D, tnear, tfar, v0, v1, v2, h)
                                  : rq_moeller(O, D, tnear, tfar, v0, v1, v2, h);
@@ -164,9 +220,9 @@ k_trace(const TraceParams P) {
         }
       }
       // ---------------- N phase ----------------
-      if (active && tmask == 0u) {
+      if (runN && active && tmask == 0u) {
         if (!(ng.y & 0xFF000000u)) {                            // node group exhausted: pop, or the ray is finished
-          if (sp > STACK) sp = STACK;                           // entries beyond the stack were dropped (cannot happen: STACK >= depth)
+          if (sp > (int)sdepth + SPILL) sp = (int)sdepth + SPILL;  // entries beyond the stack were dropped (cannot happen: capacity >= depth)
           if (sp == 0) {
             active = false;
             if (found) {
@@ -187,7 +243,9 @@ k_trace(const TraceParams P) {
               }
             }
           } else {
-            ng = stack[--sp];
+            --sp;
+            if ((uint32_t)sp < sdepth) ng = s_stack[(uint32_t)sp * 128u + threadIdx.x];
+            else if (SPILL) ng = spill[(uint32_t)sp - sdepth];
           }
         }
         if (active) {
@@ -195,26 +253,31 @@ k_trace(const TraceParams P) {
           const uint32_t bit = 31u - (uint32_t)__clz((int)ng.y);
           ng.y &= ~(1u << bit);
           if (ng.y & 0xFF000000u) {
-            if (sp < STACK) stack[sp] = ng;
+            if ((uint32_t)sp < sdepth) s_stack[(uint32_t)sp * 128u + threadIdx.x] = ng;
+            else if (SPILL && sp < (int)sdepth + SPILL) spill[(uint32_t)sp - sdepth] = ng;
             sp++;
             if (COUNT) cntStack = max(cntStack, (unsigned)sp);
           }
           const uint32_t slot = (bit - 24u) ^ octinv;
           const uint32_t rel = __popc(ng.y & 0xFFu & ((1u << slot) - 1u));
-          const uint4* np = P.nodes + (size_t)(ng.x + rel) * 8;
-          const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+          const char* np = P.nodes + (size_t)(ng.x + rel) * 128;
+          uint32_t na[8], nb[8], nc[8];
+          ldg256(np, na); ldg256(np + 32, nb); ldg256(np + 64, nc);
+          const uint4 n0 = make_uint4(na[0], na[1], na[2], na[3]), n1 = make_uint4(na[4], na[5], na[6], na[7]);
+          const uint4 n2 = make_uint4(nb[0], nb[1], nb[2], nb[3]), n3 = make_uint4(nb[4], nb[5], nb[6], nb[7]);
+          const uint4 n4 = make_uint4(nc[0], nc[1], nc[2], nc[3]);
           if (COUNT) { cntNodes++; rayNodes++; }
 
           // Slab test of the 8 quantised child boxes.  Plane q of an axis lies at t = q*a + b with
-          // a = 2^e * idir (t per grid step) and b = (p - org) * idir.  The byte q is turned into the
-          // float v = 1 + q*2^-15 by ONE PRMT (bits 0x3F80qq00), so t = fma(v, A, B) with A = a*2^15,
-          // B = b - A: two instructions per plane and no int->float converter.  B is rounded once
-          // per node; the margin eps >= that rounding keeps the test conservative (near planes
-          // earlier, far planes later), and far planes are additionally inflated by 1 + 2^-22.
+          // a = 2^e * idir (t per grid step) and b = (p - org) * idir.  The byte q becomes the float
+          // v = 1 + q*2^-16 with one IDP.4A, so t = fma(v, A, B) with A = a*2^16, B = b - A: two
+          // FMA-pipe instructions per plane.  B is rounded once per node; the margin eps >= that
+          // rounding keeps the test conservative (near planes earlier, far planes later), and far
+          // planes are additionally inflated by 1 + 2^-22.
           const float tfarBox = fmaxf(tfar, 0.0f);
-          const float Ax = __uint_as_float((n0.w & 0xFFu) << 23) * idx_ * 32768.0f;
-          const float Ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idy_ * 32768.0f;
-          const float Az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idz_ * 32768.0f;
+          const float Ax = __uint_as_float((n0.w & 0xFFu) << 23) * idx_ * 65536.0f;
+          const float Ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idy_ * 65536.0f;
+          const float Az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idz_ * 65536.0f;
           const float bx = (__uint_as_float(n0.x) - ox) * idx_;
           const float by = (__uint_as_float(n0.y) - oy) * idy_;
           const float bz = (__uint_as_float(n0.z) - oz) * idz_;
@@ -224,7 +287,7 @@ k_trace(const TraceParams P) {
           const float Bx = (bx - Ax) - ex, By = (by - Ay) - ey, Bz = (bz - Az) - ez;
           const float Axf = Ax * RQ_FAR_INFLATE, Ayf = Ay * RQ_FAR_INFLATE, Azf = Az * RQ_FAR_INFLATE;
           const float Bxf = (bx - Ax) * RQ_FAR_INFLATE + ex, Byf = (by - Ay) * RQ_FAR_INFLATE + ey, Bzf = (bz - Az) * RQ_FAR_INFLATE + ez;
-          // a grid step too large for the 2^15 pre-scale (absurd extents x axis-parallel ray): enter every child
+          // a grid step too large for the 2^16 pre-scale (absurd extents x axis-parallel ray): enter every child
           const bool overflow = !(fabsf(Ax) < 1e37f && fabsf(Ay) < 1e37f && fabsf(Az) < 1e37f);
           // near/far quantised planes per axis by ray direction sign (two words = 8 slots each)
           const uint32_t qlx0 = n2.x, qlx1 = n2.y, qly0 = n2.z, qly1 = n2.w, qlz0 = n3.x, qlz1 = n3.y;
@@ -233,35 +296,34 @@ k_trace(const TraceParams P) {
           const uint32_t nearX[2] = {nx ? qhx0 : qlx0, nx ? qhx1 : qlx1}, farX[2] = {nx ? qlx0 : qhx0, nx ? qlx1 : qhx1};
           const uint32_t nearY[2] = {ny ? qhy0 : qly0, ny ? qhy1 : qly1}, farY[2] = {ny ? qly0 : qhy0, ny ? qly1 : qhy1};
           const uint32_t nearZ[2] = {nz ? qhz0 : qlz0, nz ? qhz1 : qlz1}, farZ[2] = {nz ? qlz0 : qhz0, nz ? qlz1 : qhz1};
-          const uint32_t metaW[2] = {n1.z, n1.w};
-          const uint32_t octinv4 = octinv * 0x01010101u;
 
-          uint32_t hitmask = 0;
+          // Child k is hit iff  m <= M, m <= tfar, M >= tnear  with m = max of its three near
+          // distances, M = min of its three far distances.  The three differences are formed on
+          // the FMA pipe; the OR of their sign bits is the miss flag, shifted into `miss` by one
+          // funnel shift: 2 FMNMX3 + LOP3 + SHF on the ALU pipe per child (was 15).
+          uint32_t miss = 0;
           #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            // per-byte bookkeeping for 4 children at once: inner children get their bit at
-            // 24 + (slot ^ octinv), leaf children at their triangle offset
-            const uint32_t meta4 = metaW[h];
-            const uint32_t inner4 = ((meta4 & (meta4 << 1)) & 0x10101010u) >> 4;          // 0x01 in bytes with index >= 24
-            const uint32_t index4 = (meta4 ^ (octinv4 & (inner4 * 0xFFu))) & 0x1F1F1F1Fu;
-            const uint32_t bits4 = (meta4 >> 5) & 0x07070707u;
-            #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const float tminx = fmaf(byteToUnit(nearX[h], j), Ax, Bx);
-              const float tminy = fmaf(byteToUnit(nearY[h], j), Ay, By);
-              const float tminz = fmaf(byteToUnit(nearZ[h], j), Az, Bz);
-              const float tmaxx = fmaf(byteToUnit(farX[h], j), Axf, Bxf);
-              const float tmaxy = fmaf(byteToUnit(farY[h], j), Ayf, Byf);
-              const float tmaxz = fmaf(byteToUnit(farZ[h], j), Azf, Bzf);
-              const float tmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, tnearBox));
-              const float tmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tfarBox));
-              const uint32_t contrib = ((bits4 >> (8 * j)) & 0xFFu) << ((index4 >> (8 * j)) & 0xFFu);
-              hitmask |= ((tmin <= tmax) | overflow) ? contrib : 0u;
-            }
+          for (int k = 7; k >= 0; k--) {
+            const int h = k >> 2, j = k & 3;
+            const float tminx = fmaf(byteToUnit(nearX[h], j), Ax, Bx);
+            const float tminy = fmaf(byteToUnit(nearY[h], j), Ay, By);
+            const float tminz = fmaf(byteToUnit(nearZ[h], j), Az, Bz);
+            const float tmaxx = fmaf(byteToUnit(farX[h], j), Axf, Bxf);
+            const float tmaxy = fmaf(byteToUnit(farY[h], j), Ayf, Byf);
+            const float tmaxz = fmaf(byteToUnit(farZ[h], j), Azf, Bzf);
+            const float m = fmaxf(fmaxf(tminx, tminy), tminz);
+            const float M = fminf(fminf(tmaxx, tmaxy), tmaxz);
+            const uint32_t sgn = __float_as_uint(M - m) | __float_as_uint(tfarBox - m) | __float_as_uint(M - tnearBox);
+            miss = __funnelshift_l(sgn, miss, 1);
           }
-          if (COUNT && hitmask == 0u) cntEmpty++;
-          ng = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
-          tmask = hitmask & 0x00FFFFFFu;
+          const uint32_t masks = n1.z;
+          const uint32_t hit8 = overflow ? 0xFFu : (~miss & 0xFFu);
+          const uint32_t imask = masks >> 24;
+          const uint32_t prio = s_perm[octinv * 256u + (hit8 & imask)];
+          if (COUNT && (hit8 & imask) == 0u && (s_exp3[hit8] & masks & 0x00FFFFFFu) == 0u) cntEmpty++;
+          ng = make_uint2(n1.x, (prio << 24) | imask);
+          tvalid = masks & 0x00FFFFFFu;
+          tmask = s_exp3[hit8] & tvalid;
           triBase = n1.y;
         }
       }
@@ -287,25 +349,29 @@ cudaError_t launchOne(void (*kern)(const TraceParams), const TraceParams& P, cud
   // more than the stream needs
   static int numSMs = 0;
   if (!numSMs) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev); }
+  const size_t smem = (size_t)P.sdepth * 128u * sizeof(uint2);
   int perSM = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, 128, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, 128, smem);
   if (e != cudaSuccess) return e;
   if (perSM < 1) perSM = 1;
   const unsigned need = (P.numRays + 127u) / 128u;
   const unsigned grid = need < (unsigned)(numSMs * perSM) ? need : (unsigned)(numSMs * perSM);
-  kern<<<grid, 128, 0, s>>>(P);
+  kern<<<grid, 128, smem, s>>>(P);
   rqCountLaunch(1);
   return cudaGetLastError();
 }
 
+constexpr uint32_t kSharedStackLevels = 16;   // 16 KB per CTA; deeper trees spill the remaining levels to local memory
+
 template <bool OCC, bool ROBUST, bool COUNT, bool ALIGNED>
-cudaError_t launchStack(const TraceParams& P, uint32_t depth, cudaStream_t s) {
-  if (depth <= 32) {
-    if (P.split) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, true, 32>, P, s);
-    return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 32>, P, s);
+cudaError_t launchStack(TraceParams& P, uint32_t depth, cudaStream_t s) {
+  P.sdepth = depth < kSharedStackLevels ? (depth ? depth : 1u) : kSharedStackLevels;
+  if (depth <= kSharedStackLevels) {
+    if (P.split) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, true, 0>, P, s);
+    return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 0>, P, s);
   }
-  if (depth <= 96) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 96>, P, s);
-  return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 208>, P, s);
+  if (depth <= kSharedStackLevels + 80) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 80>, P, s);
+  return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 192>, P, s);
 }
 
 }  // namespace
@@ -315,13 +381,13 @@ cudaError_t launchStack(const TraceParams& P, uint32_t depth, cudaStream_t s) {
 static int launchTrace(bool occ, const RQTraceArgs* a, cudaStream_t s) {
   if (a->numRays == 0) return 0;
   TraceParams P;
-  P.nodes = (const uint4*)((const char*)a->image + a->nodesOffset);
-  P.tris = (const float4*)((const char*)a->image + a->trisOffset);
+  P.nodes = (const char*)a->image + a->nodesOffset;
+  P.tris = (const char*)a->image + a->trisOffset;
   P.rays = (char*)a->rays; P.stride = a->stride; P.numRays = a->numRays; P.instID0 = a->instID0;
   P.streamSemantics = a->streamSemantics; P.counters = a->counters;
   P.workCounter = a->workCounter;
   P.refillBelow = a->refillBelow ? a->refillBelow : 26u;
-  P.split = a->split;
+  P.split = a->split; P.tVote = a->tVote; P.sdepth = 0;
   if (!P.workCounter) return (int)cudaErrorInvalidValue;
   {
     cudaError_t ez = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), s);   // stream ordered with the launch

@@ -12,22 +12,23 @@
 #define RQ_INVALID 0xFFFFFFFFu
 
 // One 8-wide node = one 128-byte, 128-byte-aligned line.
-// Traversal reads only the first 80 bytes (five 16-byte loads, three 32-byte sectors):
+// Traversal reads bytes 0..95 as three 32-byte loads (LDG.E.256); bytes 0..79 are the hot fields:
 //   child box k, axis a:  lo = p[a] + qlo[a][k] * 2^(e[a]-127),  hi = p[a] + qhi[a][k] * 2^(e[a]-127)
 //   (floor/ceil quantised: the decoded box always contains the exact child box)
-// meta[k]: 0 = empty slot
-//          inner child: 0b001sssss with sssss = 24 + k
-//          leaf child : high 3 bits = unary triangle count (001,011,111 = 1,2,3),
-//                       low 5 bits = offset of its first triangle relative to triBase (0..23)
-// inner child k lives at node index childBase + popcount(imask & ((1<<k)-1)).
+// masks: bits 24..31 = imask, bit 24+k set <=> slot k holds an inner node;
+//        bits 0..23  = tvalid, slot k owns bits 3k..3k+2, one bit per triangle of a leaf slot
+//        (1..3 triangles, low bits first); an empty slot has neither.
+// inner child k lives at node index childBase + popcount(imask & ((1<<k)-1));
+// the triangle of tvalid bit b lives at triangle index triBase + popcount(tvalid & ((1<<b)-1)).
 // The remaining 48 bytes are "cold": exact bounds and bookkeeping for statistics / refit.
 struct alignas(128) RQNode {
   float    p[3];            //  0  origin of the quantisation grid (= exact lower corner)
   uint8_t  e[3];            // 12  biased exponents of the grid step per axis
-  uint8_t  imask;           // 15  bit k set <=> slot k holds an inner node
+  uint8_t  pad0;            // 15
   uint32_t childBase;       // 16
   uint32_t triBase;         // 20
-  uint8_t  meta[8];         // 24
+  uint32_t masks;           // 24  imask << 24 | tvalid
+  uint32_t pad1;            // 28
   uint8_t  qlo[3][8];       // 32  qlo[axis][slot]
   uint8_t  qhi[3][8];       // 56
   // ---- cold part (never touched by traversal) ----
@@ -40,7 +41,10 @@ struct alignas(128) RQNode {
 };
 static_assert(sizeof(RQNode) == 128, "RQNode must be one 128-byte line");
 
-// One triangle = 48 bytes = three 16-byte loads.  Vertices are stored verbatim (fp32 bits of the
+// One triangle = 48 bytes, read as one 32-byte and one 16-byte load.  In the device image the
+// records of ODD index are stored rotated -- bytes 32..47 (v2.z, primID, geomID, pad) first, then
+// bytes 0..31 -- so that the 32-byte part of every record is 32-byte aligned (48*i + 16 for odd i).
+// The struct below is the canonical (even / builder-input) order.  Vertices are stored verbatim (fp32 bits of the
 // user's vertex buffer) so that e1 = v0-v1, e2 = v2-v0, Ng = cross(e2,e1) reproduce the reference's
 // precomputed TriangleM<4>::e1/e2 bit for bit (triangle.h:45-51) and the watertight test can use
 // v0,v1,v2 directly (trianglev.h).
@@ -69,7 +73,7 @@ struct RQGeomDesc {
 // Flat image of a committed BVH: header + nodes + triangles, all offset based, so a byte copy
 // (cudaMemcpyPeer / NCCL broadcast) yields a usable replica on another GPU.
 struct RQImageHeader {
-  uint64_t magic;            // 'RQB200v1'
+  uint64_t magic;            // 'RQB200v2'
   uint32_t numNodes;
   uint32_t numTris;
   uint32_t depth;            // levels of 8-wide nodes (stack bound)
@@ -83,7 +87,7 @@ struct RQImageHeader {
   uint64_t pad[5];
 };
 static_assert(sizeof(RQImageHeader) == 128, "header is one line");
-#define RQ_IMAGE_MAGIC 0x3176303032425152ull
+#define RQ_IMAGE_MAGIC 0x3276303032425152ull   /* 'RQB200v2' */
 
 struct RQBuildStats {
   uint32_t numPrimsIn;       // triangles submitted

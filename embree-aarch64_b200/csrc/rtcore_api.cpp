@@ -78,6 +78,7 @@ struct Device : RefCounted {
   // streams and occlusion streams keep a warp's rays together (late refill, whole leaf lists)
   int refillClosest = 26, refillCoherent = 4, refillOccluded = 4;
   int splitClosest = 1, splitCoherent = 0, splitOccluded = 0;
+  int tVote = 0;
 
   cudaStream_t stream() const { return userStream ? userStream : ownStream; }
   void bind() const { if (hasGpu) cudaSetDevice(ordinal); }
@@ -139,6 +140,7 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "cost_tri") d->build.costTri = (float)atof(v.c_str());
     else if (k == "leaf_tris") d->build.maxLeafTris = atoi(v.c_str());
     else if (k == "split_closest") d->splitClosest = atoi(v.c_str());
+    else if (k == "tvote") d->tVote = std::max(0, std::min(32, atoi(v.c_str())));
     else if (k == "split_occluded") d->splitOccluded = atoi(v.c_str());
     else if (k == "refill") d->refillClosest = std::max(1, std::min(32, atoi(v.c_str())));
     else if (k == "refill_coherent") d->refillCoherent = std::max(1, std::min(32, atoi(v.c_str())));
@@ -319,6 +321,7 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
   const bool coherent = ctx && (ctx->flags & RTC_INTERSECT_CONTEXT_FLAG_COHERENT);   // a hint only, as in the reference
   a.refillBelow = (unsigned)(occluded ? dev->refillOccluded : coherent ? dev->refillCoherent : dev->refillClosest);
   a.split = (occluded ? dev->splitOccluded : coherent ? dev->splitCoherent : dev->splitClosest) ? 1u : 0u;
+  a.tVote = (unsigned)dev->tVote;
   if (isDevicePointer(rays)) {
     cudaStream_t s = dev->stream();
     a.rays = rays; a.numRays = M; a.stride = stride;

@@ -12,8 +12,9 @@ ap.add_argument("--workload", default="c2")
 ap.add_argument("--bands", type=int, default=8)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--cfg", default="")
+ap.add_argument("--lib", default=None, help="path of an experiment build (csrc/Makefile variant)")
 args = ap.parse_args()
-lib = rt.RTCore()
+lib = rt.RTCore(args.lib) if args.lib else rt.RTCore()
 dev = lib.new_device("async=1," + args.cfg)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 lib.lib.rtcxSetDeviceStream(dev, st.cuda_stream)
