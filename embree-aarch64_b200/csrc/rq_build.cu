@@ -629,7 +629,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   ScratchScope scratch(stream);
   t_scratchStream = stream;
   int err = 0;
-  RQBuildParams P = {1.0f, 0.3f, 3, 0};
+  RQBuildParams P = {1.0f, 1.0f, 3, 0};
   if (params) P = *params;
   if (P.maxLeafTris < 1) P.maxLeafTris = 1;
   if (P.maxLeafTris > 3) P.maxLeafTris = 3;

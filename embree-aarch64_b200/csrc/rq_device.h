@@ -35,6 +35,7 @@ struct RQTraceArgs {
   uint32_t    depth;       // header.depth
   uint32_t    robust;      // 1 = Pluecker (RTC_SCENE_FLAG_ROBUST), 0 = Moeller-Trumbore
   void*       rays;
+  void*       out;         // where hit fields are written (same record layout); NULL = in place
   uint32_t    numRays;
   size_t      stride;
   uint32_t    instID0;
@@ -43,6 +44,7 @@ struct RQTraceArgs {
   unsigned int* workCounter;    // device scratch word, exclusive to this launch until it completes (zeroed by the launcher)
   uint32_t    refillBelow;      // persistent-kernel refill threshold in lanes, 0 = default
   uint32_t    split;            // traversal loop shape: 1 = one triangle per iteration, 0 = whole leaf list per node
+  uint32_t    stackSmem;        // traversal stack levels kept in shared memory (0 = all in local memory), the rest spills to local
   uint32_t    tVote;            // split only: 0 = both phases every iteration, K = triangle phase when >= K lanes wait for it
 };
 int rqLaunchIntersect(const RQTraceArgs* a, rqStream stream);

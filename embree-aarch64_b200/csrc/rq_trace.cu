@@ -28,7 +28,8 @@ namespace {
 struct TraceParams {
   const char* nodes;         // RQNode array, 128 bytes per node (traversal reads bytes 0..95 as 3 x 32 B)
   const char* tris;          // RQTri array, 48 bytes per triangle (32 + 16 B, order by index parity: rq_types.h)
-  char* rays;
+  char* rays;                // records are read here ...
+  char* out;                 // ... and hit fields written here (same layout; == rays unless the stream is staged, see rtcore_api.cpp)
   size_t stride;
   uint32_t numRays;
   uint32_t instID0;
@@ -226,7 +227,7 @@ k_trace(const TraceParams P) {
           if (sp == 0) {
             active = false;
             if (found) {
-              char* rp = P.rays + (size_t)rid * P.stride;
+              char* rp = P.out + (size_t)rid * P.stride;
               if (COUNT) { cntHits++; cntHitNodes += rayNodes; }
               if (OCCLUDED) {
                 *(float*)(rp + 32) = -INFINITY;
@@ -361,17 +362,22 @@ cudaError_t launchOne(void (*kern)(const TraceParams), const TraceParams& P, cud
   return cudaGetLastError();
 }
 
-constexpr uint32_t kSharedStackLevels = 16;   // 16 KB per CTA; deeper trees spill the remaining levels to local memory
-
+// Stack capacity = tree depth (one node-group entry per level).  P.sdepth levels live in shared
+// memory (device option stack_smem, 0..16), the rest in a local-memory array of SPILL entries.
 template <bool OCC, bool ROBUST, bool COUNT, bool ALIGNED>
 cudaError_t launchStack(TraceParams& P, uint32_t depth, cudaStream_t s) {
-  P.sdepth = depth < kSharedStackLevels ? (depth ? depth : 1u) : kSharedStackLevels;
-  if (depth <= kSharedStackLevels) {
+  if (P.sdepth > depth) P.sdepth = depth;
+  const uint32_t spill = depth - P.sdepth;
+  if (spill == 0) {
     if (P.split) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, true, 0>, P, s);
     return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 0>, P, s);
   }
-  if (depth <= kSharedStackLevels + 80) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 80>, P, s);
-  return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 192>, P, s);
+  if (spill <= 32) {
+    if (P.split) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, true, 32>, P, s);
+    return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 32>, P, s);
+  }
+  if (spill <= 96) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 96>, P, s);
+  return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 208>, P, s);
 }
 
 }  // namespace
@@ -383,17 +389,17 @@ static int launchTrace(bool occ, const RQTraceArgs* a, cudaStream_t s) {
   TraceParams P;
   P.nodes = (const char*)a->image + a->nodesOffset;
   P.tris = (const char*)a->image + a->trisOffset;
-  P.rays = (char*)a->rays; P.stride = a->stride; P.numRays = a->numRays; P.instID0 = a->instID0;
+  P.rays = (char*)a->rays; P.out = a->out ? (char*)a->out : (char*)a->rays; P.stride = a->stride; P.numRays = a->numRays; P.instID0 = a->instID0;
   P.streamSemantics = a->streamSemantics; P.counters = a->counters;
   P.workCounter = a->workCounter;
   P.refillBelow = a->refillBelow ? a->refillBelow : 26u;
-  P.split = a->split; P.tVote = a->tVote; P.sdepth = 0;
+  P.split = a->split; P.tVote = a->tVote; P.sdepth = a->stackSmem;
   if (!P.workCounter) return (int)cudaErrorInvalidValue;
   {
     cudaError_t ez = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), s);   // stream ordered with the launch
     if (ez != cudaSuccess) return (int)ez;
   }
-  const bool aligned = (((uintptr_t)a->rays | (uintptr_t)a->stride) & 15u) == 0;
+  const bool aligned = (((uintptr_t)a->rays | (uintptr_t)P.out | (uintptr_t)a->stride) & 15u) == 0;
   const bool count = a->counters != nullptr;
   const bool robust = a->robust != 0;
   cudaError_t e;

@@ -58,7 +58,7 @@ struct Device : RefCounted {
   bool hasGpu = false;
   int verbose = 0, benchmark = 0, async = 0;
   size_t chunkRays = 1u << 20;
-  RQBuildParams build{1.0f, 0.3f, 3, 0};
+  RQBuildParams build{1.0f, 1.0f, 3, 0};
   cudaStream_t ownStream = nullptr, userStream = nullptr;
   std::mutex errMutex;
   RTCError error = RTC_ERROR_NONE;
@@ -79,6 +79,12 @@ struct Device : RefCounted {
   int refillClosest = 26, refillCoherent = 4, refillOccluded = 4;
   int splitClosest = 1, splitCoherent = 0, splitOccluded = 0;
   int tVote = 0;
+  int stackSmem = 16;                     // stack levels kept in shared memory, deeper levels spill to local memory (same-box A/B: +4.4 % closest, +1 % occluded vs local only)
+  // page-locked host streams: 0 = staged both ways (H2D, kernel, D2H); 1 = rays staged by DMA, hit fields written by
+  // the kernel straight into the caller's buffer over PCIe (no D2H copy); 2 = traced in place over PCIe (no copies at all).
+  // Same-box A/B on B200 / PCIe Gen5 (profiles/r01g_ab.log): 0 -> 664 Mrays/s, 1 -> 606, 2 -> 603: SM-issued PCIe
+  // transactions are 32-64 bytes and lose to the copy engines' large TLPs, so staging stays the default.
+  int zeroCopy = 0;
 
   cudaStream_t stream() const { return userStream ? userStream : ownStream; }
   void bind() const { if (hasGpu) cudaSetDevice(ordinal); }
@@ -140,6 +146,8 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "cost_tri") d->build.costTri = (float)atof(v.c_str());
     else if (k == "leaf_tris") d->build.maxLeafTris = atoi(v.c_str());
     else if (k == "split_closest") d->splitClosest = atoi(v.c_str());
+    else if (k == "stack_smem") d->stackSmem = std::max(0, std::min(16, atoi(v.c_str())));
+    else if (k == "zerocopy") d->zeroCopy = atoi(v.c_str());
     else if (k == "tvote") d->tVote = std::max(0, std::min(32, atoi(v.c_str())));
     else if (k == "split_occluded") d->splitOccluded = atoi(v.c_str());
     else if (k == "refill") d->refillClosest = std::max(1, std::min(32, atoi(v.c_str())));
@@ -212,6 +220,12 @@ bool isDevicePointer(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+// page-locked host memory (cudaHostAlloc / cudaHostRegister): returns the address the GPU can use for it, else NULL
+void* mappedHostPointer(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
 struct TempDev {                                         // device copies of host geometry buffers, freed after the build
@@ -322,15 +336,23 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
   a.refillBelow = (unsigned)(occluded ? dev->refillOccluded : coherent ? dev->refillCoherent : dev->refillClosest);
   a.split = (occluded ? dev->splitOccluded : coherent ? dev->splitCoherent : dev->splitClosest) ? 1u : 0u;
   a.tVote = (unsigned)dev->tVote;
-  if (isDevicePointer(rays)) {
+  a.stackSmem = (unsigned)dev->stackSmem;
+  void* mapped = nullptr;
+  const bool onDevice = isDevicePointer(rays);
+  if (!onDevice && dev->zeroCopy && M >= 4096) mapped = mappedHostPointer(rays);
+  if (onDevice || (mapped && dev->zeroCopy == 2)) {
+    // Device-resident stream: traced in place.  Page-locked host stream: also traced in place -- the
+    // persistent kernel reads each ray once and writes only the hit fields of rays that hit, so the
+    // PCIe link carries ~64 of 80 bytes per ray inbound and ~10 bytes per ray outbound instead of
+    // two full copies of the stream; the call still returns only when the results are in the buffer.
     cudaStream_t s = dev->stream();
-    a.rays = rays; a.numRays = M; a.stride = stride;
+    a.rays = mapped ? mapped : rays; a.numRays = M; a.stride = stride;
     a.workCounter = dev->dWork + 8 * Device::kRing;
     {
       std::lock_guard<std::mutex> ll(dev->launchMutex);
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
     }
-    if (!dev->async || countersOut) cudaCheck(cudaStreamSynchronize(s), "trace");
+    if (!dev->async || countersOut || mapped) cudaCheck(cudaStreamSynchronize(s), "trace");
   } else {
     std::lock_guard<std::mutex> l(dev->stageMutex);     // host-staged calls of one device are serialised
     const size_t chunk = dev->chunkRays;
@@ -351,9 +373,12 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
       cudaStream_t s = dev->ringStream[r];
       cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], h, span, cudaMemcpyHostToDevice, s), "ray upload");
       a.rays = dev->ringBuf[r]; a.numRays = n; a.stride = stride;
+      // page-locked caller memory: the kernel writes tfar / the hit of rays that hit straight into it
+      // (posted PCIe writes, ~10 bytes per ray on average) instead of copying the whole span back
+      a.out = mapped ? (char*)mapped + (size_t)done * stride : nullptr;
       a.workCounter = dev->dWork + 8 * r;
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
-      cudaCheck(cudaMemcpyAsync(h, dev->ringBuf[r], span, cudaMemcpyDeviceToHost, s), "hit download");
+      if (!mapped) cudaCheck(cudaMemcpyAsync(h, dev->ringBuf[r], span, cudaMemcpyDeviceToHost, s), "hit download");
       done += n;
     }
     for (int r = 0; r < Device::kRing; r++) if (dev->ringStream[r]) cudaCheck(cudaStreamSynchronize(dev->ringStream[r]), "trace");

@@ -210,6 +210,36 @@ def test_device_resident_strided_and_unaligned_streams(product, gpu_device):
     product.lib.rtcReleaseScene(sc)
 
 
+def test_pinned_host_streams_traced_in_place(product, gpu_device):
+    """Page-locked host streams take the zero-copy path (the kernel reads rays / writes hits over PCIe);
+    results must be bit-identical to the staged path used for pageable memory, padding untouched."""
+    import torch
+    g = cases.load_golden("two_geoms")
+    sc, keep = build(product, gpu_device, g)
+    reps = 4096 // len(g["rays"]) + 2                                    # the zero-copy path starts at 4096 rays
+    rays = np.tile(g["rays"], reps)
+    n = len(rays)
+    ref = rays.copy()
+    product.intersect(sc, ref)                                           # pageable -> staged copies
+    for stride in (80, 96):
+        host = np.full((n, stride), 0xCD, dtype=np.uint8)
+        host[:, :80] = rays.view(np.uint8).reshape(n, 80)
+        pinned = torch.from_numpy(host.copy()).pin_memory()
+        ctx = product.context()
+        product.lib.rtcIntersect1M(sc, C.byref(ctx), pinned.data_ptr(), n, stride)
+        out = pinned.numpy()
+        assert np.array_equal(out[:, :80].copy().reshape(-1).view(rt.RAYHIT_DTYPE), ref), stride
+        assert np.array_equal(out[:, 80:], host[:, 80:])
+    o = fx.to_ray(rays)
+    oref = o.copy()
+    product.occluded(sc, oref)
+    pinned = torch.from_numpy(o.view(np.uint8).reshape(n, 48).copy()).pin_memory()
+    product.occluded_ptr(sc, pinned.data_ptr(), n)
+    assert np.array_equal(pinned.numpy().reshape(-1).view(rt.RAY_DTYPE), oref)
+    assert product.lib.rtcGetDeviceError(gpu_device) == 0
+    product.lib.rtcReleaseScene(sc)
+
+
 def test_empty_scenes_updates_and_disable(product, gpu_device):
     """EmptySceneTest :1061, EmptyGeometryTest :1093, UpdateTest :1710, enable/disable, detach."""
     L = product.lib
