@@ -193,7 +193,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = rt.RTCore()                                                      # fails loudly when the CUDA library is missing
+    lib = rt.RTCore(os.environ["RQ_B200_LIB"]) if os.environ.get("RQ_B200_LIB") else rt.RTCore()   # fails loudly when the CUDA library is missing (RQ_B200_LIB: experiment build)
     dev = lib.new_device(f"gpu={local},async=1" + ("," + os.environ["RQ_B200_CFG"] if os.environ.get("RQ_B200_CFG") else ""))   # RQ_B200_CFG: extra device options for experiments
     # a real (non-default) stream shared by torch and the library: the CUDA events below are recorded on
     # the stream the kernels are launched on (handle 0 would mean "the library's own stream")

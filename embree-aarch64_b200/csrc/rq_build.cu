@@ -340,32 +340,25 @@ struct B2 {                    // binary-tree arrays (2n-1 nodes unless noted)
   uint32_t* flag;              // n-1 arrival counters
 };
 
-__global__ void __launch_bounds__(256)
-k_refit_dp(B2 t, int n, const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals,
-           float costNode, float costTri, int maxLeafTris) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  uint32_t node = (uint32_t)(n - 1 + k);
-  {
-    const float4* src = (const float4*)(trisIn + vals[k]);
-    const float4 a = src[0], b = src[1], c = src[2];
-    const float lx = fminf(fminf(a.x, a.w), b.z), ly = fminf(fminf(a.y, b.x), b.w), lz = fminf(fminf(a.z, b.y), c.x);
-    const float hx = fmaxf(fmaxf(a.x, a.w), b.z), hy = fmaxf(fmaxf(a.y, b.x), b.w), hz = fmaxf(fmaxf(a.z, b.y), c.x);
-    const float A = halfArea(hx - lx, hy - ly, hz - lz);
-    t.lo[node] = make_float4(lx, ly, lz, A);
-    t.hi[node] = make_float4(hx, hy, hz, __uint_as_float(1u));
-    const float cl = A * costTri;
-    float4* cp = (float4*)(t.cost + (size_t)node * 8);
-    cp[0] = make_float4(cl, cl, cl, cl);
-    cp[1] = make_float4(cl, cl, cl, 0.f);
-    t.dec[node] = 0;
-  }
-  __threadfence();
-  uint32_t cur = t.parent[node];
-  while (cur != RQ_INVALID) {
-    if (atomicAdd(&t.flag[cur], 1u) == 0u) return;             // first arrival: sibling not ready yet
-    __threadfence();
-    const uint32_t L = t.left[cur], R = t.right[cur];
+// Leaf k of the binary tree (node id n-1+k): bounds of its triangle and the trivial collapse programme.
+__device__ __forceinline__ void initLeaf(const B2& t, uint32_t node, const RQTri* __restrict__ trisIn, uint32_t tri, float costTri) {
+  const float4* src = (const float4*)(trisIn + tri);
+  const float4 a = src[0], b = src[1], c = src[2];
+  const float lx = fminf(fminf(a.x, a.w), b.z), ly = fminf(fminf(a.y, b.x), b.w), lz = fminf(fminf(a.z, b.y), c.x);
+  const float hx = fmaxf(fmaxf(a.x, a.w), b.z), hy = fmaxf(fmaxf(a.y, b.x), b.w), hz = fmaxf(fmaxf(a.z, b.y), c.x);
+  const float A = halfArea(hx - lx, hy - ly, hz - lz);
+  t.lo[node] = make_float4(lx, ly, lz, A);
+  t.hi[node] = make_float4(hx, hy, hz, __uint_as_float(1u));
+  const float cl = A * costTri;
+  float4* cp = (float4*)(t.cost + (size_t)node * 8);
+  cp[0] = make_float4(cl, cl, cl, cl);
+  cp[1] = make_float4(cl, cl, cl, 0.f);
+  t.dec[node] = 0;
+}
+
+// Bounds, triangle count and the collapse programme of binary node `cur` from its finished children L, R.
+__device__ __forceinline__ void combineNode(const B2& t, uint32_t cur, uint32_t L, uint32_t R,
+                                            float costNode, float costTri, int maxLeafTris) {
     // data produced by other SMs in this launch: read through L2 (ld.cg), never L1
     const float4 llo = __ldcg(t.lo + L), lhi = __ldcg(t.hi + L), rlo = __ldcg(t.lo + R), rhi = __ldcg(t.hi + R);
     const float4 l0 = __ldcg((const float4*)(t.cost + (size_t)L * 8)), l1 = __ldcg((const float4*)(t.cost + (size_t)L * 8) + 1);
@@ -405,9 +398,140 @@ k_refit_dp(B2 t, int n, const RQTri* __restrict__ trisIn, const uint32_t* __rest
     cp[0] = make_float4(c[1], c[2], c[3], c[4]);
     cp[1] = make_float4(c[5], c[6], c[7], 0.f);
     t.dec[cur] = dec;
+}
+
+__global__ void __launch_bounds__(256)
+k_refit_dp(B2 t, int n, const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals,
+           float costNode, float costTri, int maxLeafTris) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  uint32_t node = (uint32_t)(n - 1 + k);
+  initLeaf(t, node, trisIn, vals[k], costTri);
+  __threadfence();
+  uint32_t cur = t.parent[node];
+  while (cur != RQ_INVALID) {
+    if (atomicAdd(&t.flag[cur], 1u) == 0u) return;             // first arrival: sibling not ready yet
+    __threadfence();
+    combineNode(t, cur, t.left[cur], t.right[cur], costNode, costTri, maxLeafTris);
     __threadfence();
     cur = t.parent[cur];
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// 5b. PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) as the alternative to the
+//     radix tree: clusters sit in Morton order; every iteration each cluster looks R positions to
+//     either side for the neighbour with the smallest merged surface area, mutual nearest
+//     neighbours merge, the array is compacted (order preserved).  Because a merge only ever joins
+//     finished clusters, the bounds and the collapse programme of the new node are computed right
+//     there -- no separate refit pass.  Inner node ids are handed out downwards from n-2, so the
+//     last merge (the root) is node 0 as in the radix tree.
+// ----------------------------------------------------------------------------------------------
+constexpr int PLOC_THREADS = 256;
+constexpr int PLOC_MAX_RADIUS = 32;
+
+__global__ void __launch_bounds__(256)
+k_ploc_init(B2 t, int n, const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals, float costTri,
+            uint32_t* __restrict__ cid) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t node = (uint32_t)(n - 1 + k);
+  initLeaf(t, node, trisIn, vals[k], costTri);
+  cid[k] = node;
+}
+
+__global__ void __launch_bounds__(PLOC_THREADS)
+k_ploc_nn(B2 t, const uint32_t* __restrict__ cid, uint32_t m, int radius, uint32_t* __restrict__ nn) {
+  __shared__ float sb[PLOC_THREADS + 2 * PLOC_MAX_RADIUS][6];
+  const int b0 = (int)(blockIdx.x * PLOC_THREADS) - radius;
+  const int span = PLOC_THREADS + 2 * radius;
+  for (int s = threadIdx.x; s < span; s += PLOC_THREADS) {
+    const int g = b0 + s;
+    if (g >= 0 && g < (int)m) {
+      const uint32_t c = cid[g];
+      const float4 lo = t.lo[c], hi = t.hi[c];
+      sb[s][0] = lo.x; sb[s][1] = lo.y; sb[s][2] = lo.z; sb[s][3] = hi.x; sb[s][4] = hi.y; sb[s][5] = hi.z;
+    }
+  }
+  __syncthreads();
+  const int i = (int)(blockIdx.x * PLOC_THREADS + threadIdx.x);
+  if (i >= (int)m) return;
+  const int si = (int)threadIdx.x + radius;
+  const float lx = sb[si][0], ly = sb[si][1], lz = sb[si][2], hx = sb[si][3], hy = sb[si][4], hz = sb[si][5];
+  float best = FLT_MAX; int bj = -1;
+  const int j0 = max(i - radius, 0), j1 = min(i + radius, (int)m - 1);
+  for (int j = j0; j <= j1; j++) {
+    if (j == i) continue;
+    const int sj = j - b0;
+    const float d = halfArea(fmaxf(hx, sb[sj][3]) - fminf(lx, sb[sj][0]), fmaxf(hy, sb[sj][4]) - fminf(ly, sb[sj][1]),
+                             fmaxf(hz, sb[sj][5]) - fminf(lz, sb[sj][2]));
+    if (d < best) { best = d; bj = j; }                        // ties: the lower position wins on both sides => still mutual
+  }
+  nn[i] = (uint32_t)bj;
+}
+
+// merge mutual pairs (the lower position keeps the new cluster), flag survivors, count them per block
+__global__ void __launch_bounds__(PLOC_THREADS)
+k_ploc_merge(B2 t, uint32_t* __restrict__ cid, uint32_t m, const uint32_t* __restrict__ nn, uint32_t* __restrict__ keep,
+             uint32_t* __restrict__ blockCount, uint32_t* nextInner, float costNode, float costTri, int maxLeafTris) {
+  const uint32_t i = blockIdx.x * PLOC_THREADS + threadIdx.x;
+  bool alive = false;
+  if (i < m) {
+    const uint32_t j = nn[i];
+    const bool mutual = j < m && nn[j] == i;
+    alive = !(mutual && j < i);
+    if (mutual && i < j) {
+      const uint32_t id = atomicSub(nextInner, 1u);            // n-2, n-3, ... 0
+      const uint32_t L = cid[i], R = cid[j];
+      t.left[id] = L; t.right[id] = R; t.parent[L] = id; t.parent[R] = id;
+      combineNode(t, id, L, R, costNode, costTri, maxLeafTris);
+      cid[i] = id;
+    }
+    keep[i] = alive ? 1u : 0u;
+  }
+  const unsigned cnt = __syncthreads_count(alive);
+  if (threadIdx.x == 0) blockCount[blockIdx.x] = cnt;
+}
+
+// exclusive scan of the per-block survivor counts (one block), total to *total
+__global__ void __launch_bounds__(1024)
+k_ploc_scan(uint32_t* __restrict__ blockCount, uint32_t numBlocks, uint32_t* total) {
+  __shared__ uint32_t part[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < numBlocks; base += 1024) {
+    const uint32_t idx = base + threadIdx.x;
+    const uint32_t v = idx < numBlocks ? blockCount[idx] : 0u;
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const uint32_t a = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+      __syncthreads();
+      part[threadIdx.x] += a;
+      __syncthreads();
+    }
+    if (idx < numBlocks) blockCount[idx] = carry + part[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += part[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(PLOC_THREADS)
+k_ploc_compact(const uint32_t* __restrict__ cidIn, uint32_t m, const uint32_t* __restrict__ keep,
+               const uint32_t* __restrict__ blockOffset, uint32_t* __restrict__ cidOut) {
+  __shared__ uint32_t warpSum[PLOC_THREADS / 32];
+  const uint32_t i = blockIdx.x * PLOC_THREADS + threadIdx.x;
+  const bool alive = i < m && keep[i] != 0u;
+  const unsigned bal = __ballot_sync(0xffffffffu, alive);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warpSum[warp] = __popc(bal);
+  __syncthreads();
+  uint32_t off = blockOffset[blockIdx.x];
+  for (int w = 0; w < warp; w++) off += warpSum[w];
+  if (alive) cidOut[off + __popc(bal & ((1u << lane) - 1u))] = cidIn[i];
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -541,12 +665,19 @@ emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2*
     } else {
       const uint32_t nt = ctris[c];                           // 1..3
       N.masks |= ((1u << nt) - 1u) << (3 * s);                // triangles are stored in slot order
-      const uint32_t first = child[c] >= firstLeaf ? child[c] - firstLeaf : t.rangeFirst[child[c]];
-      for (uint32_t j = 0; j < nt; j++) {
-        const float4* src = (const float4*)(trisIn + vals[first + j]);
-        float4* dst = (float4*)(trisOut + triBase + triOff + j);
-        if ((triBase + triOff + j) & 1u) { dst[0] = src[2]; dst[1] = src[0]; dst[2] = src[1]; }   // odd records: last 16 bytes first (rq_types.h)
-        else { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
+      // the <= 3 triangles of this leaf slot: the leaves below binary node child[c] (tiny depth-first walk;
+      // works for the radix tree and for PLOC, whose subtrees are not contiguous in Morton order)
+      uint32_t walk[4]; int wsp = 0; uint32_t j = 0;
+      walk[wsp++] = child[c];
+      while (wsp > 0 && j < nt) {
+        const uint32_t x = walk[--wsp];
+        if (x >= firstLeaf) {
+          const float4* src = (const float4*)(trisIn + vals[x - firstLeaf]);
+          float4* dst = (float4*)(trisOut + triBase + triOff + j);
+          if ((triBase + triOff + j) & 1u) { dst[0] = src[2]; dst[1] = src[0]; dst[2] = src[1]; }   // odd records: last 16 bytes first (rq_types.h)
+          else { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
+          j++;
+        } else if (wsp < 3) { walk[wsp++] = t.right[x]; walk[wsp++] = t.left[x]; }
       }
       triOff += nt;
       sahLeafQ += Aq * (double)((nt + 3) / 4); sahLeafX += Ax * (double)((nt + 3) / 4);
@@ -629,7 +760,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   ScratchScope scratch(stream);
   t_scratchStream = stream;
   int err = 0;
-  RQBuildParams P = {1.0f, 1.0f, 3, 0};
+  RQBuildParams P = {1.0f, 1.0f, 3, 0, 1, 8};
   if (params) P = *params;
   if (P.maxLeafTris < 1) P.maxLeafTris = 1;
   if (P.maxLeafTris > 3) P.maxLeafTris = 3;
@@ -643,6 +774,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   cudaEvent_t ev[7]; for (auto& e : ev) e = nullptr;
   DevBuf<RQGeomDesc> dGeoms; DevBuf<RQTri> trisIn, trisOut; DevBuf<uint64_t> keys0, keys1;
   DevBuf<uint32_t> vals0, vals1, hist, digitTotal, left, right, parent, rangeFirst, flag, dec, qParent0, qParent1;
+  DevBuf<uint32_t> cid0, cid1, nnBuf, blockCount, plocCtr; uint32_t plocIters = 0;
   DevBuf<float4> blo, bhi; DevBuf<float> cost; DevBuf<uint2> queue0, queue1; DevBuf<RQNode> nodes;
   DevBuf<Bounds12> dBounds; DevBuf<uint32_t> dInvalid; DevBuf<EmitCounters> dCtr;
   Bounds12 hb; uint32_t hInvalid = 0; EmitCounters hc;
@@ -704,11 +836,38 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       t.parent = parent.p; t.rangeFirst = rangeFirst.p; t.flag = flag.p;
       CK(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t) * n, stream));
       CK(cudaMemsetAsync(parent.p, 0xFF, sizeof(uint32_t) * n2, stream));
-      if (n > 1) { k_hierarchy<<<blocksFor(n - 1, 256), 256, 0, stream>>>(keys0.p, (int)n, left.p, right.p, parent.p, rangeFirst.p); rqCountLaunch(1); }
-      CK(cudaEventRecord(ev[3], stream));
-      k_refit_dp<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costNode, P.costTri, P.maxLeafTris);
-      rqCountLaunch(1);
-      CK(cudaGetLastError());
+      if (P.builder == 1 && n > 1) {
+        // ---- PLOC: iterate nearest-neighbour search / merge / compaction until one cluster is left ----
+        const int radius = P.plocRadius < 1 ? 1 : (P.plocRadius > PLOC_MAX_RADIUS ? PLOC_MAX_RADIUS : P.plocRadius);
+        CK(cid0.alloc(n)); CK(cid1.alloc(n)); CK(nnBuf.alloc(n)); CK(blockCount.alloc(blocksFor(n, PLOC_THREADS) + 1)); CK(plocCtr.alloc(2));
+        const uint32_t initCtr[2] = {n - 2u, n};
+        CK(cudaMemcpyAsync(plocCtr.p, initCtr, sizeof(initCtr), cudaMemcpyHostToDevice, stream));
+        k_ploc_init<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costTri, cid0.p);
+        rqCountLaunch(1);
+        CK(cudaEventRecord(ev[3], stream));
+        uint32_t m = n; uint32_t *cin = cid0.p, *cout = cid1.p;
+        while (m > 1) {
+          const unsigned nb = blocksFor(m, PLOC_THREADS);
+          k_ploc_nn<<<nb, PLOC_THREADS, 0, stream>>>(t, cin, m, radius, nnBuf.p);
+          k_ploc_merge<<<nb, PLOC_THREADS, 0, stream>>>(t, cin, m, nnBuf.p, flag.p, blockCount.p, plocCtr.p, P.costNode, P.costTri, P.maxLeafTris);
+          k_ploc_scan<<<1, 1024, 0, stream>>>(blockCount.p, nb, plocCtr.p + 1);
+          k_ploc_compact<<<nb, PLOC_THREADS, 0, stream>>>(cin, m, flag.p, blockCount.p, cout);
+          rqCountLaunch(4);
+          uint32_t next = 0;
+          CK(cudaMemcpyAsync(&next, plocCtr.p + 1, 4, cudaMemcpyDeviceToHost, stream));
+          CK(cudaStreamSynchronize(stream));
+          if (next >= m || next == 0) { err = (int)cudaErrorUnknown; goto fail; }   // every iteration merges at least the globally closest pair
+          m = next; plocIters++;
+          std::swap(cin, cout);
+        }
+        CK(cudaGetLastError());
+      } else {
+        if (n > 1) { k_hierarchy<<<blocksFor(n - 1, 256), 256, 0, stream>>>(keys0.p, (int)n, left.p, right.p, parent.p, rangeFirst.p); rqCountLaunch(1); }
+        CK(cudaEventRecord(ev[3], stream));
+        k_refit_dp<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costNode, P.costTri, P.maxLeafTris);
+        rqCountLaunch(1);
+        CK(cudaGetLastError());
+      }
       CK(cudaEventRecord(ev[4], stream));
 
       // ---- emission, level by level ----
@@ -764,6 +923,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       stats->depth = depth; stats->numLeaves = hc.leafSlots; stats->sah = H.sah;
       stats->sahExact = rootA > 0 ? (hc.sahInnerX + hc.sahLeafX) / rootA : 0.0;
       stats->bytes = H.totalBytes;
+      stats->builderIterations = plocIters;
       cudaEventElapsedTime(&stats->msTotal, ev[0], ev[6]);
       cudaEventElapsedTime(&stats->msPrims, ev[0], ev[1]);
       cudaEventElapsedTime(&stats->msSort, ev[1], ev[2]);

@@ -12,6 +12,8 @@ struct RQBuildParams {
   float costTri;         // SAH cost of testing one triangle               (default 0.3)
   int   maxLeafTris;     // triangles per leaf slot, 1..3                  (default 3)
   int   verbose;
+  int   builder;         // binary-tree front end: 0 = radix tree over Morton codes (LBVH), 1 = PLOC
+  int   plocRadius;      // PLOC search radius in Morton-order positions, 1..32          (default 8)
 };
 
 // A committed BVH living in device memory: one allocation, header first.

@@ -80,7 +80,10 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
 // lanes fetch new rays (one atomicAdd per warp per refill), so SIMD lanes stay busy although ray
 // lifetimes differ by an order of magnitude (miss after 4 nodes vs hit after 40).
 template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int SPILL>
-__global__ void __launch_bounds__(128)
+#ifndef RQ_MIN_CTAS
+#define RQ_MIN_CTAS 8   /* 64 registers: 8 CTAs = 32 warps per SM; (128,1) let ptxas take 95 registers and cost 20 % (profiles/r01k_ab.log) */
+#endif
+__global__ void __launch_bounds__(128, RQ_MIN_CTAS)
 k_trace(const TraceParams P) {
   // Traversal stack: one 8-byte node-group entry per tree level.  The first P.sdepth levels live
   // in shared memory, entry-major ([level][thread]) so that lanes with different stack depths still
@@ -122,7 +125,7 @@ k_trace(const TraceParams P) {
   uint32_t tmask = 0u, triBase = 0u, tvalid = 0u;               // pending leaf triangles of the current node
   bool found = false;
   float hu = 0.f, hv = 0.f; RQVec3 hNg = rq_v3(0.f, 0.f, 0.f); uint32_t hPrim = 0, hGeom = 0;
-  unsigned long long cntRays = 0, cntNodes = 0, cntTris = 0, cntHits = 0, cntEmpty = 0, cntHitNodes = 0; unsigned cntStack = 0, rayNodes = 0;
+  unsigned long long cntRays = 0, cntNodes = 0, cntTris = 0, cntHits = 0, cntEmpty = 0, cntHitNodes = 0, cntLate = 0; unsigned cntStack = 0, rayNodes = 0;
   bool exhausted = false;                                       // warp-uniform: the global counter ran past numRays
 
   for (;;) {
@@ -267,7 +270,14 @@ k_trace(const TraceParams P) {
           const uint4 n0 = make_uint4(na[0], na[1], na[2], na[3]), n1 = make_uint4(na[4], na[5], na[6], na[7]);
           const uint4 n2 = make_uint4(nb[0], nb[1], nb[2], nb[3]), n3 = make_uint4(nb[4], nb[5], nb[6], nb[7]);
           const uint4 n4 = make_uint4(nc[0], nc[1], nc[2], nc[3]);
-          if (COUNT) { cntNodes++; rayNodes++; }
+          if (COUNT) {
+            cntNodes++; rayNodes++;
+            // how many fetches would a distance test at pop time have saved?  (exact bounds from the cold part)
+            const float* cb = (const float*)(np + 80);
+            const float t0x = ((dx < 0.f ? cb[3] : cb[0]) - ox) * idx_, t0y = ((dy < 0.f ? cb[4] : cb[1]) - oy) * idy_,
+                        t0z = ((dz < 0.f ? cb[5] : cb[2]) - oz) * idz_;
+            if (fmaxf(fmaxf(t0x, t0y), t0z) > tfar) cntLate++;
+          }
 
           // Slab test of the 8 quantised child boxes.  Plane q of an axis lies at t = q*a + b with
           // a = 2^e * idir (t per grid step) and b = (p - org) * idir.  The byte q becomes the float
@@ -341,6 +351,7 @@ k_trace(const TraceParams P) {
     atomicAdd(&P.counters->hits, cntHits);
     atomicAdd(&P.counters->emptyNodes, cntEmpty);
     atomicAdd(&P.counters->hitNodes, cntHitNodes);
+    atomicAdd(&P.counters->lateNodes, cntLate);
     atomicMax(&P.counters->stackMax, (unsigned long long)cntStack);
   }
 }

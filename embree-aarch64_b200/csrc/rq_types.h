@@ -100,6 +100,8 @@ struct RQBuildStats {
   double   sahExact;         // same with the exact fp32 child boxes
   float    msTotal, msPrims, msSort, msHierarchy, msRefit, msEmit;
   uint64_t bytes;
+  uint32_t builderIterations; // PLOC merge iterations (0 for the radix tree)
+  uint32_t pad;
 };
 
 // Per-call traversal counters (instrumented kernel variant only).
@@ -111,4 +113,5 @@ struct RQTraceCounters {
   unsigned long long stackMax;    // deepest traversal stack seen
   unsigned long long emptyNodes;  // node records fetched whose children were all missed / culled
   unsigned long long hitNodes;    // node records fetched by rays that end up reporting a hit
+  unsigned long long lateNodes;   // node records fetched although the node's own box already lies beyond the ray's current tfar
 };

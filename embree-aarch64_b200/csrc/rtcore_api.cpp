@@ -58,7 +58,7 @@ struct Device : RefCounted {
   bool hasGpu = false;
   int verbose = 0, benchmark = 0, async = 0;
   size_t chunkRays = 1u << 20;
-  RQBuildParams build{1.0f, 1.0f, 3, 0};
+  RQBuildParams build{1.0f, 1.0f, 3, 0, 1, 8};   // PLOC front end by default: same-box A/B +1 % closest, +8 % occluded Mrays/s vs the radix tree (profiles/r01l_ab.log)
   cudaStream_t ownStream = nullptr, userStream = nullptr;
   std::mutex errMutex;
   RTCError error = RTC_ERROR_NONE;
@@ -145,6 +145,8 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "cost_node") d->build.costNode = (float)atof(v.c_str());
     else if (k == "cost_tri") d->build.costTri = (float)atof(v.c_str());
     else if (k == "leaf_tris") d->build.maxLeafTris = atoi(v.c_str());
+    else if (k == "gpu_builder") d->build.builder = (v == "ploc") ? 1 : 0;
+    else if (k == "ploc_radius") d->build.plocRadius = atoi(v.c_str());
     else if (k == "split_closest") d->splitClosest = atoi(v.c_str());
     else if (k == "stack_smem") d->stackSmem = std::max(0, std::min(16, atoi(v.c_str())));
     else if (k == "zerocopy") d->zeroCopy = atoi(v.c_str());

@@ -58,13 +58,13 @@ class BuildStats(C.Structure):
                 ("sah", C.c_double), ("sahExact", C.c_double),
                 ("msTotal", C.c_float), ("msPrims", C.c_float), ("msSort", C.c_float),
                 ("msHierarchy", C.c_float), ("msRefit", C.c_float), ("msEmit", C.c_float),
-                ("bytes", C.c_ulonglong)]
+                ("bytes", C.c_ulonglong), ("builderIterations", C.c_uint), ("pad", C.c_uint)]
 
 
 class TraceCounters(C.Structure):
     _fields_ = [("rays", C.c_ulonglong), ("nodes", C.c_ulonglong), ("tris", C.c_ulonglong),
                 ("hits", C.c_ulonglong), ("stackMax", C.c_ulonglong), ("emptyNodes", C.c_ulonglong),
-                ("hitNodes", C.c_ulonglong)]
+                ("hitNodes", C.c_ulonglong), ("lateNodes", C.c_ulonglong)]
 
 
 def new_rays(n, hit=True):

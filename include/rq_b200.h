@@ -24,6 +24,8 @@ struct RTCXBuildStats {
   double sahExact;              /* same formula on the exact fp32 child boxes                     */
   float msTotal, msPrims, msSort, msHierarchy, msRefit, msEmit;   /* device time per build phase  */
   unsigned long long bytes;     /* size of the device image                                       */
+  unsigned int builderIterations; /* PLOC merge iterations (0 for the radix-tree front end)       */
+  unsigned int pad;
 };
 
 struct RTCXTraceCounters {
@@ -34,6 +36,7 @@ struct RTCXTraceCounters {
   unsigned long long stackMax;  /* deepest traversal stack                                        */
   unsigned long long emptyNodes;/* node records fetched whose children were all missed or culled  */
   unsigned long long hitNodes;  /* node records fetched by rays that report a hit                 */
+  unsigned long long lateNodes; /* node records fetched although their own box lies beyond the current tfar */
 };
 
 /* Stream (a cudaStream_t passed as void*) on which builds and device-resident queries are

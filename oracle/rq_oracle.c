@@ -330,8 +330,14 @@ static inline float rcp_safe(float d) { return 1.0f / (fabsf(d) < MIN_RCP_INPUT 
  * RTC_SCENE_FLAG_ROBUST selects intersectNodeRobust (:621-636): t = (plane - org) * rdir_{near,far} with
  * rdir_near = (1-3ulp)*rdir, rdir_far = (1+3ulp)*rdir (TravRayBase<N,Nx,true>, :121-135);
  * closest-hit child order: nearest first (bvh_traverser1.h:519-643); cull popped nodes with dist > tfar (:92-96) */
+/* work counters of the restated reference traversal (what EMBREE_STAT_COUNTERS counts per ray, kernels/common/stat.h:61-79):
+ * [0] rays traced, [1] inner nodes visited (8-wide slab tests), [2] leaves visited, [3] Triangle4 blocks tested, [4] triangles tested */
+static uint64_t g_cnt[5];
+RQO_API void rqo_trace_counters(uint64_t out[5], int reset) { for (int i = 0; i < 5; i++) { out[i] = g_cnt[i]; if (reset) g_cnt[i] = 0; } }
+
 static int trace_one(const scene_t* sc, ray_t* ray, rhit_t* hit, int occluded, uint32_t instID) {
   if (!sc->root) return 0;
+  g_cnt[0]++;
   const v3 O = V(ray->org_x, ray->org_y, ray->org_z), D = V(ray->dir_x, ray->dir_y, ray->dir_z);
   const float Of[3] = {O.x, O.y, O.z}, Df[3] = {D.x, D.y, D.z};
   const v3 rdir = V(rcp_safe(D.x), rcp_safe(D.y), rcp_safe(D.z));
@@ -345,6 +351,7 @@ static int trace_one(const scene_t* sc, ray_t* ray, rhit_t* hit, int occluded, u
     const node_t* nd = stack[sp].n;
     if (!occluded && stack[sp].d > ray->tfar) continue;
     if (nd->nchild == 0) {
+      g_cnt[2]++; g_cnt[3] += (nd->count + 3) / 4; g_cnt[4] += nd->count;
       for (uint32_t i = 0; i < nd->count; i++) {
         const tri_t* t = &sc->tris[nd->first + i];
         float o[6];
@@ -360,6 +367,7 @@ static int trace_one(const scene_t* sc, ray_t* ray, rhit_t* hit, int occluded, u
       continue;
     }
     const float tfarBox = fmaxf(ray->tfar, 0.0f);
+    g_cnt[1]++;
     int idx[8]; float dist[8]; int nh = 0;
     for (int i = 0; i < nd->nchild; i++) {
       const box3* b = &nd->cbox[i];

@@ -64,6 +64,12 @@ class Oracle:
         self.lib.rqo_stats(h, o)
         return dict(tris=o[0], nodes=o[1], leaves=o[2], blocks=o[3])
 
+    def trace_counters(self, reset=True):
+        """Work of the restated reference traversal since the last reset: rays, inner nodes, leaves, Triangle4 blocks, triangles."""
+        o = (C.c_uint64 * 5)()
+        self.lib.rqo_trace_counters(o, 1 if reset else 0)
+        return dict(rays=o[0], nodes=o[1], leaves=o[2], blocks=o[3], tris=o[4])
+
     def bounds(self, h):
         o = (C.c_float * 6)()
         self.lib.rqo_bounds(h, o)

@@ -26,9 +26,10 @@ def product():
     return cases.rt.RTCore()
 
 
-@pytest.fixture(scope="session")
-def gpu_device(product):
-    return product.new_device("")
+@pytest.fixture(scope="session", params=["gpu_builder=lbvh", "gpu_builder=ploc"])
+def gpu_device(product, request):
+    """Every GPU test runs against both binary-tree front ends of the builder (radix tree / PLOC)."""
+    return product.new_device(request.param)
 
 
 @pytest.fixture(scope="session")

@@ -210,13 +210,16 @@ def test_device_resident_strided_and_unaligned_streams(product, gpu_device):
     product.lib.rtcReleaseScene(sc)
 
 
-def test_pinned_host_streams_traced_in_place(product, gpu_device):
-    """Page-locked host streams take the zero-copy path (the kernel reads rays / writes hits over PCIe);
-    results must be bit-identical to the staged path used for pageable memory, padding untouched."""
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pinned_host_streams(product, mode):
+    """Page-locked host streams: staged both ways (zerocopy=0, default), staged in + hit fields written by the
+    kernel over PCIe (1), traced in place over PCIe (2).  All must be bit-identical to the pageable
+    path, with the padding between records untouched."""
     import torch
+    dev = product.new_device(f"zerocopy={mode}")
     g = cases.load_golden("two_geoms")
-    sc, keep = build(product, gpu_device, g)
-    reps = 4096 // len(g["rays"]) + 2                                    # the zero-copy path starts at 4096 rays
+    sc, keep = build(product, dev, g)
+    reps = 4096 // len(g["rays"]) + 2                                    # the zero-copy paths start at 4096 rays
     rays = np.tile(g["rays"], reps)
     n = len(rays)
     ref = rays.copy()
@@ -236,8 +239,9 @@ def test_pinned_host_streams_traced_in_place(product, gpu_device):
     pinned = torch.from_numpy(o.view(np.uint8).reshape(n, 48).copy()).pin_memory()
     product.occluded_ptr(sc, pinned.data_ptr(), n)
     assert np.array_equal(pinned.numpy().reshape(-1).view(rt.RAY_DTYPE), oref)
-    assert product.lib.rtcGetDeviceError(gpu_device) == 0
+    assert product.lib.rtcGetDeviceError(dev) == 0
     product.lib.rtcReleaseScene(sc)
+    product.lib.rtcReleaseDevice(dev)
 
 
 def test_empty_scenes_updates_and_disable(product, gpu_device):

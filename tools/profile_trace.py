@@ -12,6 +12,8 @@ ap.add_argument("--workload", default="c2")
 ap.add_argument("--bands", type=int, default=8)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--cfg", default="")
+ap.add_argument("--counters", action="store_true")
+ap.add_argument("--sort", default="none", help="host-side reordering experiment: none|octant|chunkdir:<chunk>:<bins>|global:<obits>:<bins>")
 ap.add_argument("--lib", default=None, help="path of an experiment build (csrc/Makefile variant)")
 args = ap.parse_args()
 lib = rt.RTCore(args.lib) if args.lib else rt.RTCore()
@@ -27,12 +29,56 @@ for b in range(args.bands):
     lib.intersect(sc, prim, coherent=True)
     d_parts.append(fx.diffuse_rays(prim)); s_parts.append(fx.shadow_rays(prim))
 diffuse, shadow = np.concatenate(d_parts), np.concatenate(s_parts)
+
+
+def dir_bin(r, nb):
+    """octahedral map of the direction to an nb x nb grid"""
+    d = np.stack([r["dir_x"], r["dir_y"], r["dir_z"]], 1).astype(np.float64)
+    d /= np.maximum(np.abs(d).sum(1, keepdims=True), 1e-30)
+    u, v = d[:, 0].copy(), d[:, 1].copy()
+    neg = d[:, 2] < 0
+    uu = (1 - np.abs(v)) * np.where(u >= 0, 1, -1); vv = (1 - np.abs(u)) * np.where(v >= 0, 1, -1)
+    u = np.where(neg, uu, u); v = np.where(neg, vv, v)
+    iu = np.clip(((u * 0.5 + 0.5) * nb).astype(np.int64), 0, nb - 1); iv = np.clip(((v * 0.5 + 0.5) * nb).astype(np.int64), 0, nb - 1)
+    return iu * nb + iv
+
+
+def reorder(r, mode):
+    if mode == "none":
+        return r
+    n = len(r)
+    if mode == "octant":
+        key = (r["dir_x"] < 0).astype(np.int64) | ((r["dir_y"] < 0).astype(np.int64) << 1) | ((r["dir_z"] < 0).astype(np.int64) << 2)
+    elif mode.startswith("chunkdir"):
+        _, chunk, nb = mode.split(":")
+        key = (np.arange(n) // int(chunk)) * 100000 + dir_bin(r, int(nb))
+    elif mode.startswith("global"):
+        _, ob, nb = mode.split(":")
+        ob = int(ob)
+        o = np.stack([r["org_x"], r["org_y"], r["org_z"]], 1).astype(np.float64)
+        lo, hi = o.min(0), o.max(0)
+        q = np.clip(((o - lo) / np.maximum(hi - lo, 1e-30) * (1 << ob)).astype(np.int64), 0, (1 << ob) - 1)
+        m = np.zeros(n, dtype=np.int64)
+        for b in range(ob):
+            for a in range(3):
+                m |= ((q[:, a] >> b) & 1) << (3 * b + a)
+        key = m * 100000 + dir_bin(r, int(nb))
+    return r[np.argsort(key, kind="stable")]
+
+
+diffuse, shadow = reorder(diffuse, args.sort), reorder(shadow, args.sort)
 nd, ns = len(diffuse), len(shadow)
 p_d = torch.from_numpy(diffuse.view(np.uint8).reshape(nd, 80)).cuda()
 p_s = torch.from_numpy(shadow.view(np.uint8).reshape(ns, 48)).cuda()
 w_d, w_s = p_d.clone(), p_s.clone()
 lib.intersect_ptr(sc, w_d.data_ptr(), nd, 80); lib.occluded_ptr(sc, w_s.data_ptr(), ns, 48)
 torch.cuda.synchronize()
+if args.counters:
+    w_d.copy_(p_d); w_s.copy_(p_s); torch.cuda.synchronize()
+    c = lib.intersect_counted(sc, w_d.data_ptr(), nd, 80)
+    print("closest per ray:", {k: round(v / max(c["rays"], 1), 3) for k, v in c.items() if k != "stackMax"}, "stackMax", c["stackMax"], flush=True)
+    c = lib.intersect_counted(sc, w_s.data_ptr(), ns, 48, occluded=True)
+    print("occluded per ray:", {k: round(v / max(c["rays"], 1), 3) for k, v in c.items() if k != "stackMax"}, "stackMax", c["stackMax"], flush=True)
 for rep in range(args.reps):
     w_d.copy_(p_d); w_s.copy_(p_s); torch.cuda.synchronize()
     e = [torch.cuda.Event(True) for _ in range(3)]
