@@ -779,6 +779,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   DevBuf<Bounds12> dBounds; DevBuf<uint32_t> dInvalid; DevBuf<EmitCounters> dCtr;
   Bounds12 hb; uint32_t hInvalid = 0; EmitCounters hc;
   uint32_t n = 0, depth = 0, numNodes = 1, numTris = 0;
+  std::vector<uint32_t> levelEnd(1, 1u);                        // level 0 = the root = node range [0,1)
   RQImageHeader H;
   void* image = nullptr;
   memset(&hc, 0, sizeof(hc));
@@ -886,6 +887,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
         CK(cudaGetLastError());
         count = hc.nextCount;
         depth++;
+        if (count) levelEnd.push_back(hc.nodeCount);              // children allocated by this launch = the next level
         if (count) CK(cudaMemsetAsync(&dCtr.p->nextCount, 0, 4, stream));
         std::swap(qin, qout); std::swap(pin, pout);
         if (depth > 200) { err = (int)cudaErrorUnknown; goto fail; }
@@ -932,6 +934,11 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       cudaEventElapsedTime(&stats->msEmit, ev[4], ev[6]);
     }
     out->base = image; out->header = H; image = nullptr;
+    out->numLevels = 0;
+    if (levelEnd.size() == depth && depth <= RQ_MAX_LEVELS && levelEnd.back() == numNodes) {
+      out->numLevels = depth;
+      for (uint32_t l = 0; l < depth; l++) out->levelEnd[l] = levelEnd[l];
+    }
   }
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   return 0;
@@ -939,6 +946,206 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
 fail:
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   if (image) cudaFree(image);
+  cudaGetLastError();
+  return err ? err : (int)cudaErrorUnknown;
+}
+
+// ================================================================================================
+// Refit: same topology, new vertex positions (RTC_BUILD_QUALITY_REFIT).
+//   k_refit_tris   one thread per triangle record of the image: (geomID, primID) -> index buffer ->
+//                  three vertices, validity rule of the build (invalid => NaN vertices: never hit)
+//   k_refit_nodes  one thread per node of one tree level (deepest level first): child boxes from
+//                  the leaf triangles / from the children's exact bounds written by the previous
+//                  launch, new quantisation grid, same directed rounding as k_emit
+// Traffic: 48 B read+written per triangle plus the vertex gathers, 128 B read+written per node.
+// ================================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256)
+k_refit_tris(const RQGeomDesc* __restrict__ geomsByID, uint32_t numSlots, RQTri* __restrict__ tris, uint32_t numTris) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numTris) return;
+  float4* rec = (float4*)(tris + i);
+  const uint32_t odd = i & 1u;                                  // odd records: last 16 bytes first (rq_types.h)
+  const float4 c = rec[odd ? 0 : 2];
+  const uint32_t primID = __float_as_uint(c.y), geomID = __float_as_uint(c.z);
+  if (geomID >= numSlots) return;
+  const RQGeomDesc G = geomsByID[geomID];
+  if (primID >= G.numTris || G.indices == nullptr || G.vertices == nullptr) return;
+  const uint32_t* ip = (const uint32_t*)(G.indices + (size_t)primID * G.indexStride);
+  const uint32_t i0 = ip[0], i1 = ip[1], i2 = ip[2];
+  const float qnan = __uint_as_float(0x7FC00000u);
+  float v[9] = {qnan, qnan, qnan, qnan, qnan, qnan, qnan, qnan, qnan};
+  if (i0 < G.numVerts && i1 < G.numVerts && i2 < G.numVerts) {
+    const float* p0 = (const float*)(G.vertices + (size_t)i0 * G.vertexStride);
+    const float* p1 = (const float*)(G.vertices + (size_t)i1 * G.vertexStride);
+    const float* p2 = (const float*)(G.vertices + (size_t)i2 * G.vertexStride);
+    bool valid = true;
+    for (int k = 0; k < 3; k++) {
+      v[k] = p0[k]; v[3 + k] = p1[k]; v[6 + k] = p2[k];
+    }
+    for (int k = 0; k < 9; k++) valid &= (v[k] > -RQ_FLT_LARGE) & (v[k] < RQ_FLT_LARGE);
+    if (!valid) for (int k = 0; k < 9; k++) v[k] = qnan;
+  }
+  const float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
+  const float4 c2 = make_float4(v[8], c.y, c.z, c.w);
+  if (odd) { rec[0] = c2; rec[1] = a; rec[2] = b; } else { rec[0] = a; rec[1] = b; rec[2] = c2; }
+}
+
+struct RefitSums { double sahInnerQ, sahLeafQ, sahInnerX, sahLeafX; };
+
+__global__ void __launch_bounds__(128)
+k_refit_nodes(RQNode* __restrict__ nodes, const RQTri* __restrict__ tris, uint32_t first, uint32_t count, RefitSums* sums) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  if (q < count) {
+    RQNode N;
+    {
+      const uint4* s4 = (const uint4*)(nodes + first + q); uint4* d4 = (uint4*)&N;
+      #pragma unroll
+      for (int i = 0; i < 8; i++) d4[i] = s4[i];
+    }
+    const uint32_t imask = N.masks >> 24, tvalid = N.masks & 0x00FFFFFFu;
+    float clo[8][3], chi[8][3]; bool present[8], empty[8];
+    float nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int k = 0; k < 8; k++) {
+      present[k] = false; empty[k] = true;
+      for (int a = 0; a < 3; a++) { clo[k][a] = FLT_MAX; chi[k][a] = -FLT_MAX; }
+      if (imask & (1u << k)) {
+        present[k] = true;
+        const RQNode* ch = nodes + N.childBase + __popc(imask & ((1u << k) - 1u));
+        for (int a = 0; a < 3; a++) { clo[k][a] = ch->lo[a]; chi[k][a] = ch->hi[a]; }
+      } else {
+        const uint32_t bits = (tvalid >> (3 * k)) & 7u;
+        if (bits) {
+          present[k] = true;
+          for (uint32_t j = 0; j < 3; j++) {
+            if (!(bits & (1u << j))) continue;
+            const uint32_t b = 3u * k + j;
+            const uint32_t ti = N.triBase + __popc(tvalid & ((1u << b) - 1u));
+            const float4* src = (const float4*)(tris + ti);
+            float4 ta, tb, tc;
+            if (ti & 1u) { tc = src[0]; ta = src[1]; tb = src[2]; } else { ta = src[0]; tb = src[1]; tc = src[2]; }
+            // fminf / fmaxf drop NaN operands: a triangle invalidated by k_refit_tris adds nothing
+            clo[k][0] = fminf(clo[k][0], fminf(fminf(ta.x, ta.w), tb.z)); chi[k][0] = fmaxf(chi[k][0], fmaxf(fmaxf(ta.x, ta.w), tb.z));
+            clo[k][1] = fminf(clo[k][1], fminf(fminf(ta.y, tb.x), tb.w)); chi[k][1] = fmaxf(chi[k][1], fmaxf(fmaxf(ta.y, tb.x), tb.w));
+            clo[k][2] = fminf(clo[k][2], fminf(fminf(ta.z, tb.y), tc.x)); chi[k][2] = fmaxf(chi[k][2], fmaxf(fmaxf(ta.z, tb.y), tc.x));
+          }
+        }
+      }
+      if (present[k]) {
+        empty[k] = !(clo[k][0] <= chi[k][0] && clo[k][1] <= chi[k][1] && clo[k][2] <= chi[k][2]);
+        if (!empty[k]) for (int a = 0; a < 3; a++) { nlo[a] = fminf(nlo[a], clo[k][a]); nhi[a] = fmaxf(nhi[a], chi[k][a]); }
+      }
+    }
+    const bool nodeEmpty = !(nlo[0] <= nhi[0] && nlo[1] <= nhi[1] && nlo[2] <= nhi[2]);
+    float inv[3], step[3];
+    for (int a = 0; a < 3; a++) {
+      N.p[a] = nodeEmpty ? 0.f : nlo[a];
+      const float ext = nodeEmpty ? 0.f : __fsub_ru(nhi[a], nlo[a]);
+      uint8_t eb = expForExtent(ext);
+      while (eb < 254 && __fmul_ru(ext, __uint_as_float((uint32_t)(254 - eb) << 23)) > 255.0f) eb++;
+      N.e[a] = eb;
+      step[a] = __uint_as_float((uint32_t)eb << 23);
+      inv[a] = __uint_as_float((uint32_t)(254 - eb) << 23);
+    }
+    for (int k = 0; k < 8; k++) {
+      for (int a = 0; a < 3; a++) { N.qlo[a][k] = 255; N.qhi[a][k] = 0; }   // absent / empty slot: never entered
+      if (!present[k] || empty[k]) continue;
+      float dq[3];
+      for (int a = 0; a < 3; a++) {
+        float fl = floorf(__fmul_rd(__fsub_rd(clo[k][a], N.p[a]), inv[a]));
+        float fh = ceilf(__fmul_ru(__fsub_ru(chi[k][a], N.p[a]), inv[a]));
+        fl = fminf(fmaxf(fl, 0.f), 255.f); fh = fminf(fmaxf(fh, 0.f), 255.f);
+        N.qlo[a][k] = (uint8_t)fl; N.qhi[a][k] = (uint8_t)fh;
+        dq[a] = (fh - fl) * step[a];
+      }
+      const double Aq = (double)halfArea(dq[0], dq[1], dq[2]);
+      const double Ax = (double)halfArea(chi[k][0] - clo[k][0], chi[k][1] - clo[k][1], chi[k][2] - clo[k][2]);
+      if (imask & (1u << k)) { s[0] += Aq; s[2] += Ax; } else { s[1] += Aq; s[3] += Ax; }
+    }
+    // an empty node keeps an inverted exact box, so its parent skips it as well
+    for (int a = 0; a < 3; a++) { N.lo[a] = nodeEmpty ? FLT_MAX : nlo[a]; N.hi[a] = nodeEmpty ? -FLT_MAX : nhi[a]; }
+    if (first + q == 0 && !nodeEmpty) {
+      const double A = (double)halfArea(nhi[0] - nlo[0], nhi[1] - nlo[1], nhi[2] - nlo[2]);
+      s[0] += A; s[2] += A;                                     // the root's own box
+    }
+    {
+      const uint4* s4 = (const uint4*)&N; uint4* d4 = (uint4*)(nodes + first + q);
+      #pragma unroll
+      for (int i = 0; i < 8; i++) d4[i] = s4[i];
+    }
+  }
+  #pragma unroll
+  for (int k = 0; k < 4; k++)
+    for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+  if ((threadIdx.x & 31) == 0 && (s[0] != 0.0 || s[1] != 0.0)) {
+    atomicAdd(&sums->sahInnerQ, s[0]); atomicAdd(&sums->sahLeafQ, s[1]);
+    atomicAdd(&sums->sahInnerX, s[2]); atomicAdd(&sums->sahLeafX, s[3]);
+  }
+}
+
+}  // namespace
+
+int rqRefitBVH(const RQGeomDesc* geomsByID, int numSlots, RQDeviceImage* img, rqStream stream_, RQBuildStats* stats) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!img || !img->base || img->numLevels == 0 || img->numLevels > RQ_MAX_LEVELS) return (int)cudaErrorInvalidValue;
+  ScratchScope scratch(stream);
+  t_scratchStream = stream;
+  int err = 0;
+  RQImageHeader& H = img->header;
+  RQNode* nodes = (RQNode*)((char*)img->base + H.nodesOffset);
+  RQTri* tris = (RQTri*)((char*)img->base + H.trisOffset);
+  DevBuf<RQGeomDesc> dGeoms; DevBuf<RefitSums> dSums;
+  RefitSums hs; float rootBox[6];
+  cudaEvent_t ev[3]; for (auto& e : ev) e = nullptr;
+  memset(&hs, 0, sizeof(hs));
+
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(ev[0], stream));
+  CK(dGeoms.alloc(numSlots > 0 ? numSlots : 1)); CK(dSums.alloc(1));
+  if (numSlots > 0) CK(cudaMemcpyAsync(dGeoms.p, geomsByID, sizeof(RQGeomDesc) * numSlots, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemsetAsync(dSums.p, 0, sizeof(RefitSums), stream));
+  if (H.numTris) {
+    k_refit_tris<<<blocksFor(H.numTris, 256), 256, 0, stream>>>(dGeoms.p, (uint32_t)(numSlots > 0 ? numSlots : 0), tris, H.numTris);
+    rqCountLaunch(1);
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(ev[1], stream));
+  for (int l = (int)img->numLevels - 1; l >= 0; l--) {
+    const uint32_t first = l ? img->levelEnd[l - 1] : 0u, count = img->levelEnd[l] - first;
+    if (!count) continue;
+    k_refit_nodes<<<blocksFor(count, 128), 128, 0, stream>>>(nodes, tris, first, count, dSums.p);
+    rqCountLaunch(1);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&hs, dSums.p, sizeof(hs), cudaMemcpyDeviceToHost, stream));
+  CK(cudaMemcpyAsync(rootBox, (const char*)nodes + 80, sizeof(rootBox), cudaMemcpyDeviceToHost, stream));   // RQNode::lo, hi of node 0
+  CK(cudaStreamSynchronize(stream));
+  {
+    const bool any = rootBox[0] <= rootBox[3] && rootBox[1] <= rootBox[4] && rootBox[2] <= rootBox[5];
+    for (int k = 0; k < 3; k++) { H.lo[k] = any ? rootBox[k] : INFINITY; H.hi[k] = any ? rootBox[3 + k] : -INFINITY; }
+    const double rootA = any ? (double)halfArea(H.hi[0] - H.lo[0], H.hi[1] - H.lo[1], H.hi[2] - H.lo[2]) : 0.0;
+    H.sah = rootA > 0 ? (hs.sahInnerQ + hs.sahLeafQ) / rootA : 0.0;
+    CK(cudaMemcpyAsync(img->base, &H, sizeof(H), cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(ev[2], stream));
+    CK(cudaStreamSynchronize(stream));
+    if (stats) {
+      stats->sah = H.sah;
+      stats->sahExact = rootA > 0 ? (hs.sahInnerX + hs.sahLeafX) / rootA : 0.0;
+      stats->msSort = stats->msHierarchy = stats->msEmit = 0.f;
+      cudaEventElapsedTime(&stats->msTotal, ev[0], ev[2]);
+      cudaEventElapsedTime(&stats->msPrims, ev[0], ev[1]);
+      cudaEventElapsedTime(&stats->msRefit, ev[1], ev[2]);
+      stats->builderIterations = 0;
+      stats->refitCount++;
+    }
+  }
+  for (auto& e : ev) if (e) cudaEventDestroy(e);
+  return 0;
+
+fail:
+  for (auto& e : ev) if (e) cudaEventDestroy(e);
   cudaGetLastError();
   return err ? err : (int)cudaErrorUnknown;
 }

@@ -17,9 +17,15 @@ struct RQBuildParams {
 };
 
 // A committed BVH living in device memory: one allocation, header first.
+#define RQ_MAX_LEVELS 208
 struct RQDeviceImage {
   void*         base;       // device pointer to the image (RQImageHeader at offset 0)
   RQImageHeader header;     // host copy of the header
+  // Nodes are emitted one tree level per launch, so level L occupies the contiguous node range
+  // [L ? levelEnd[L-1] : 0, levelEnd[L]); the refit walks these ranges bottom-up.  numLevels = 0
+  // for an image adopted from elsewhere (rtcxSetSceneImage): such an image cannot be refitted.
+  uint32_t      numLevels;
+  uint32_t      levelEnd[RQ_MAX_LEVELS];
 };
 
 // Builds the BVH for the given meshes on `stream` (geoms is a HOST array whose index/vertex
@@ -27,6 +33,13 @@ struct RQDeviceImage {
 int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const RQBuildParams* params,
                rqStream stream, RQDeviceImage* out, RQBuildStats* stats);
 void rqFreeImage(RQDeviceImage* img);
+
+// Refit (RTC_BUILD_QUALITY_REFIT, reference: kernels/bvh/bvh_refit.cpp, bvh_builder_twolevel.h:95-140):
+// the topology of `img` is kept; every triangle record re-reads its three vertices through the
+// index buffer of its mesh (geomsByID is a HOST array indexed by geomID, device-readable pointers,
+// numTris = 0 for absent slots) and all node boxes are recomputed and re-quantised bottom-up, one
+// launch per tree level.  Updates img->header (bounds, SAH) on host and device.
+int rqRefitBVH(const RQGeomDesc* geomsByID, int numSlots, RQDeviceImage* img, rqStream stream, RQBuildStats* stats);
 
 // Ray-stream kernels.  `rays` is device-readable AoS memory: RTCRayHit (intersect) or RTCRay
 // (occluded) records `stride` bytes apart.  instID0 is written to hit.instID[0] on a hit.

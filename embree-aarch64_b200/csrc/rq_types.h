@@ -101,7 +101,7 @@ struct RQBuildStats {
   float    msTotal, msPrims, msSort, msHierarchy, msRefit, msEmit;
   uint64_t bytes;
   uint32_t builderIterations; // PLOC merge iterations (0 for the radix tree)
-  uint32_t pad;
+  uint32_t refitCount;        // refits applied to this BVH since its last full build (0 = freshly built)
 };
 
 // Per-call traversal counters (instrumented kernel variant only).

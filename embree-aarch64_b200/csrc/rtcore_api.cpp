@@ -85,6 +85,7 @@ struct Device : RefCounted {
   // Same-box A/B on B200 / PCIe Gen5 (profiles/r01g_ab.log): 0 -> 664 Mrays/s, 1 -> 606, 2 -> 603: SM-issued PCIe
   // transactions are 32-64 bytes and lose to the copy engines' large TLPs, so staging stays the default.
   int zeroCopy = 0;
+  int refitEnabled = 1;                   // refit=0: RTC_BUILD_QUALITY_REFIT geometries are rebuilt like any other
 
   cudaStream_t stream() const { return userStream ? userStream : ownStream; }
   void bind() const { if (hasGpu) cudaSetDevice(ordinal); }
@@ -150,6 +151,7 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "split_closest") d->splitClosest = atoi(v.c_str());
     else if (k == "stack_smem") d->stackSmem = std::max(0, std::min(16, atoi(v.c_str())));
     else if (k == "zerocopy") d->zeroCopy = atoi(v.c_str());
+    else if (k == "refit") d->refitEnabled = atoi(v.c_str());
     else if (k == "tvote") d->tVote = std::max(0, std::min(32, atoi(v.c_str())));
     else if (k == "split_occluded") d->splitOccluded = atoi(v.c_str());
     else if (k == "refill") d->refillClosest = std::max(1, std::min(32, atoi(v.c_str())));
@@ -192,11 +194,13 @@ struct Geometry : RefCounted {
   BufferView vertices, indices;
   bool committed = false, enabled = true;
   unsigned modCounter = 0, mask = 0xFFFFFFFFu;
+  unsigned topoCounter = 0;                              // bumped by every change a refit cannot absorb (anything but new vertex positions)
   void* userPtr = nullptr;
   RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
   Geometry(Device* d, RTCGeometryType t) : dev(d), type(t) { dev->retain(); }
   ~Geometry() override { vertices.clear(); indices.clear(); dev->release(); }
-  void update() { ++modCounter; committed = false; }
+  void update() { ++modCounter; ++topoCounter; committed = false; }
+  void updateVertices() { ++modCounter; committed = false; }   // rtcUpdateGeometryBuffer(RTC_BUFFER_TYPE_VERTEX)
 };
 
 struct Scene : RefCounted {
@@ -204,7 +208,7 @@ struct Scene : RefCounted {
   std::mutex geomMutex, buildMutex;
   std::vector<Geometry*> geoms;                          // index = geomID
   std::set<unsigned> freeIDs; unsigned nextID = 0;       // lowest-free-first (common/sys/alloc.h:100-125)
-  std::vector<unsigned> seenMod;
+  std::vector<unsigned> seenMod, seenTopo;
   RTCSceneFlags flags = RTC_SCENE_FLAG_NONE; RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
   bool modified = true, everCommitted = false;
   RQDeviceImage image{nullptr, {}};
@@ -246,15 +250,24 @@ struct TempDev {                                         // device copies of hos
 void commitScene(Scene* sc) {
   Device* dev = sc->dev;
   std::unique_lock<std::mutex> lock(sc->buildMutex);     // one committer at a time; joiners simply wait
+  // Refit instead of rebuild (reference: RTC_BUILD_QUALITY_REFIT meshes of the two-level builder,
+  // bvh_builder_twolevel.h:95-140 -> bvh_refit.cpp): the scene itself is unchanged (no attach /
+  // detach / flags / quality), and every geometry touched since the last commit only got new vertex
+  // positions (rtcUpdateGeometryBuffer on the vertex buffer) and has build quality REFIT.
+  bool refit = dev->refitEnabled && !sc->modified && sc->everCommitted && sc->image.base && sc->image.numLevels > 0;
   {
     std::lock_guard<std::mutex> gl(sc->geomMutex);
     bool changed = sc->modified || !sc->everCommitted;
-    if (sc->seenMod.size() != sc->geoms.size()) { sc->seenMod.resize(sc->geoms.size(), 0xFFFFFFFFu); changed = true; }
+    if (sc->seenMod.size() != sc->geoms.size()) { sc->seenMod.resize(sc->geoms.size(), 0xFFFFFFFFu); changed = true; refit = false; }
+    if (sc->seenTopo.size() != sc->geoms.size()) { sc->seenTopo.resize(sc->geoms.size(), 0xFFFFFFFFu); refit = false; }
     for (size_t i = 0; i < sc->geoms.size(); i++) {
       Geometry* g = sc->geoms[i];
       if (!g) continue;
       if (g->enabled && !g->committed) fail(RTC_ERROR_INVALID_OPERATION, "geometry not committed");   // geometry.cpp:103-107
-      if (g->modCounter != sc->seenMod[i]) changed = true;
+      if (g->modCounter != sc->seenMod[i]) {
+        changed = true;
+        if (g->topoCounter != sc->seenTopo[i] || g->quality != RTC_BUILD_QUALITY_REFIT) refit = false;
+      }
     }
     if (!changed) return;
   }
@@ -270,7 +283,7 @@ void commitScene(Scene* sc) {
     for (size_t i = 0; i < sc->geoms.size(); i++) {
       Geometry* g = sc->geoms[i];
       if (!g) continue;
-      sc->seenMod[i] = g->modCounter;
+      sc->seenMod[i] = g->modCounter; sc->seenTopo[i] = g->topoCounter;
       if (!g->enabled || g->indices.count == 0) continue;
       RQGeomDesc d; memset(&d, 0, sizeof(d));
       const char* ip = g->indices.data(); const char* vp = g->vertices.data();
@@ -283,15 +296,29 @@ void commitScene(Scene* sc) {
       descs.push_back(d);
     }
   }
-  RQDeviceImage img{nullptr, {}};
-  RQBuildStats st;
-  cudaCheck(rqBuildBVH(descs.data(), (int)descs.size(), (uint32_t)sc->flags, &dev->build, (rqStream)s, &img, &st), "BVH build");
-  if (sc->image.base) rqFreeImage(&sc->image);
-  sc->image = img; sc->stats = st;
+  if (refit) {
+    std::vector<RQGeomDesc> byID(sc->geoms.size());
+    memset(byID.data(), 0, sizeof(RQGeomDesc) * byID.size());
+    for (const RQGeomDesc& d : descs) byID[d.geomID] = d;
+    cudaCheck(rqRefitBVH(byID.data(), (int)byID.size(), &sc->image, (rqStream)s, &sc->stats), "BVH refit");
+  } else {
+    RQDeviceImage img; memset(&img, 0, sizeof(img));
+    RQBuildStats st;
+    RQBuildParams bp = dev->build;
+    // scene build quality: LOW = the fast radix-tree front end (role of the reference's Morton builder for
+    // RTC_BUILD_QUALITY_LOW, scene.cpp:118-124), HIGH = PLOC with a wide search radius (the reference adds
+    // spatial splits here, which this builder does not do)
+    if (sc->quality == RTC_BUILD_QUALITY_LOW) bp.builder = 0;
+    else if (sc->quality == RTC_BUILD_QUALITY_HIGH) { bp.builder = 1; bp.plocRadius = std::max(bp.plocRadius, 16); }
+    cudaCheck(rqBuildBVH(descs.data(), (int)descs.size(), (uint32_t)sc->flags, &bp, (rqStream)s, &img, &st), "BVH build");
+    if (sc->image.base) rqFreeImage(&sc->image);
+    sc->image = img; sc->stats = st;
+  }
   sc->modified = false; sc->everCommitted = true;
   if (sc->progress) sc->progress(sc->progressPtr, 1.0);
   if (dev->benchmark || dev->verbose >= 2) {
     // same fields as the reference's line (bvh.cpp:173-178): seconds, prims/s, SAH, bytes
+    const RQBuildStats& st = sc->stats;
     printf("BENCHMARK_BUILD %g %g %g %llu BVH8q<triangle>.b200\n", st.msTotal * 1e-3, st.numPrimsValid / (st.msTotal * 1e-3 + 1e-12),
            st.sah, (unsigned long long)st.bytes);
     fflush(stdout);
@@ -576,8 +603,8 @@ RTC_API RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
 RTC_API void rtcRetainGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); g->retain(); RTC_CATCH(devOf(g)) }
 RTC_API void rtcReleaseGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; Device* d = devOf(g); RTC_TRY VERIFY_HANDLE(h); g->release(); RTC_CATCH(d) }
 RTC_API void rtcCommitGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); ++g->modCounter; g->committed = true; RTC_CATCH(devOf(g)) }
-RTC_API void rtcEnableGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); if (!g->enabled) { g->enabled = true; ++g->modCounter; } RTC_CATCH(devOf(g)) }
-RTC_API void rtcDisableGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); if (g->enabled) { g->enabled = false; ++g->modCounter; } RTC_CATCH(devOf(g)) }
+RTC_API void rtcEnableGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); if (!g->enabled) { g->enabled = true; ++g->modCounter; ++g->topoCounter; } RTC_CATCH(devOf(g)) }
+RTC_API void rtcDisableGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); if (g->enabled) { g->enabled = false; ++g->modCounter; ++g->topoCounter; } RTC_CATCH(devOf(g)) }
 RTC_API void rtcSetGeometryTimeStepCount(RTCGeometry h, unsigned int n) {
   Geometry* g = (Geometry*)h;
   RTC_TRY VERIFY_HANDLE(h);
@@ -663,7 +690,10 @@ RTC_API void* rtcGetGeometryBufferData(RTCGeometry h, enum RTCBufferType type, u
   RTC_CATCH(devOf(g))
   return nullptr;
 }
-RTC_API void rtcUpdateGeometryBuffer(RTCGeometry h, enum RTCBufferType, unsigned int) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); g->update(); RTC_CATCH(devOf(g)) }
+RTC_API void rtcUpdateGeometryBuffer(RTCGeometry h, enum RTCBufferType type, unsigned int) {
+  Geometry* g = (Geometry*)h;
+  RTC_TRY VERIFY_HANDLE(h); if (type == RTC_BUFFER_TYPE_VERTEX) g->updateVertices(); else g->update(); RTC_CATCH(devOf(g))
+}
 RTC_API void rtcSetGeometryUserData(RTCGeometry h, void* p) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); g->userPtr = p; RTC_CATCH(devOf(g)) }
 RTC_API void* rtcGetGeometryUserData(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); return g->userPtr; RTC_CATCH(devOf(g)) return nullptr; }
 RTC_API void rtcSetGeometryIntersectFilterFunction(RTCGeometry h, RTCFilterFunctionN f) {
@@ -951,7 +981,7 @@ RTC_API void rtcxSetSceneImage(RTCScene hs, const void* src, size_t bytes) {
     if (!e) e = cudaStreamSynchronize(dev->stream());
     if (e) { cudaFree(p); cudaCheck(e, "image copy"); }
     if (s->image.base) rqFreeImage(&s->image);
-    s->image.base = p; s->image.header = H;
+    s->image.base = p; s->image.header = H; s->image.numLevels = 0;   // adopted image: level ranges unknown, never refitted
     s->flags = (RTCSceneFlags)H.flags;
     memset(&s->stats, 0, sizeof(s->stats));
     s->stats.numNodes = H.numNodes; s->stats.numTris = H.numTris; s->stats.depth = H.depth; s->stats.sah = H.sah; s->stats.bytes = H.totalBytes;

@@ -28,6 +28,7 @@ RTC_SCENE_FLAG_NONE = 0
 RTC_SCENE_FLAG_DYNAMIC = 1
 RTC_SCENE_FLAG_COMPACT = 2
 RTC_SCENE_FLAG_ROBUST = 4
+(RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM, RTC_BUILD_QUALITY_HIGH, RTC_BUILD_QUALITY_REFIT) = range(4)
 RTC_INTERSECT_CONTEXT_FLAG_INCOHERENT = 0
 RTC_INTERSECT_CONTEXT_FLAG_COHERENT = 1
 (RTC_ERROR_NONE, RTC_ERROR_UNKNOWN, RTC_ERROR_INVALID_ARGUMENT, RTC_ERROR_INVALID_OPERATION,
@@ -58,7 +59,7 @@ class BuildStats(C.Structure):
                 ("sah", C.c_double), ("sahExact", C.c_double),
                 ("msTotal", C.c_float), ("msPrims", C.c_float), ("msSort", C.c_float),
                 ("msHierarchy", C.c_float), ("msRefit", C.c_float), ("msEmit", C.c_float),
-                ("bytes", C.c_ulonglong), ("builderIterations", C.c_uint), ("pad", C.c_uint)]
+                ("bytes", C.c_ulonglong), ("builderIterations", C.c_uint), ("refitCount", C.c_uint)]
 
 
 class TraceCounters(C.Structure):
@@ -121,6 +122,7 @@ class RTCore:
         _sig(L, "rtcGetGeometryBufferData", vp, [vp, C.c_int, u])
         _sig(L, "rtcUpdateGeometryBuffer", None, [vp, C.c_int, u])
         _sig(L, "rtcSetGeometryTimeStepCount", None, [vp, u])
+        _sig(L, "rtcSetGeometryBuildQuality", None, [vp, C.c_int])
         _sig(L, "rtcNewBuffer", vp, [vp, sz])
         _sig(L, "rtcNewSharedBuffer", vp, [vp, vp, sz])
         _sig(L, "rtcGetBufferData", vp, [vp])

@@ -25,7 +25,7 @@ struct RTCXBuildStats {
   float msTotal, msPrims, msSort, msHierarchy, msRefit, msEmit;   /* device time per build phase  */
   unsigned long long bytes;     /* size of the device image                                       */
   unsigned int builderIterations; /* PLOC merge iterations (0 for the radix-tree front end)       */
-  unsigned int pad;
+  unsigned int refitCount;      /* refits since the last full build (RTC_BUILD_QUALITY_REFIT path) */
 };
 
 struct RTCXTraceCounters {

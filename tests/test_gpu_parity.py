@@ -297,6 +297,110 @@ def test_empty_scenes_updates_and_disable(product, gpu_device):
     L.rtcReleaseScene(sc)
 
 
+def _wave(v0, phase):
+    """Deformation used by the refit tests: a travelling wave on y plus a drift on x (float32 throughout)."""
+    v = v0.copy()
+    v[:, 1] += (0.35 * np.sin(1.3 * v0[:, 0] + phase) * np.cos(0.9 * v0[:, 2] - 0.5 * phase)).astype(np.float32)
+    v[:, 0] += np.float32(0.05 * phase)
+    return v
+
+
+def test_refit_matches_fresh_build(product, gpu_device, oracle):
+    """RTC_BUILD_QUALITY_REFIT geometries whose vertex buffer is updated are refitted
+    (topology kept, boxes re-quantised bottom-up); answers must equal those of a BVH built from
+    scratch over the new positions (oracle), including dropped (NaN) triangles and scene bounds."""
+    L = product.lib
+    base = [fx.displaced_plane(96, extent=4.0), fx.triangle_sphere((0.3, 1.2, -0.2), 0.8, 40)]
+    sc = L.rtcNewScene(gpu_device)
+    keep, geoms = [], []
+    for v, t in base:
+        gid, g = product.add_mesh(gpu_device, sc, v, t, keep)
+        L.rtcSetGeometryBuildQuality(g, rt.RTC_BUILD_QUALITY_REFIT)
+        L.rtcCommitGeometry(g)
+        geoms.append(g)
+    L.rtcCommitScene(sc)
+    st0 = product.build_stats(sc)
+    assert st0["refitCount"] == 0
+    rays = np.concatenate([fx.incoherent_rays(40000, org=(0.1, 2.5, 0.2), seed=3),
+                           fx.primary_rays(160, 160, org=(0.5, 6.0, 0.5), look=(0, -1, 0), up=(0, 0, 1))])
+    vbufs = [keep[0], keep[2]]                                             # the shared (padded) vertex arrays
+    for step, phase in enumerate((0.7, 1.9, 3.1), start=1):
+        cur = []
+        for (v0, t), buf in zip(base, vbufs):
+            v = _wave(np.asarray(v0, dtype=np.float32), phase)
+            if step == 2 and len(v) > 1000:
+                v[123] = np.nan                                            # triangles using this vertex vanish (scene_triangle_mesh.h:131-153)
+            buf[:v.size] = v.ravel()
+            cur.append((v, t))
+        for g in geoms:
+            L.rtcUpdateGeometryBuffer(g, rt.RTC_BUFFER_TYPE_VERTEX, 0)
+            L.rtcCommitGeometry(g)
+        L.rtcCommitScene(sc)
+        st = product.build_stats(sc)
+        assert st["refitCount"] == step and st["numNodes"] == st0["numNodes"] and st["numTris"] == st0["numTris"], st
+        assert 1.0 < st["sahExact"] <= st["sah"] < 200.0
+        h = oracle.build(cur)
+        b = rt.Bounds()
+        L.rtcGetSceneBounds(sc, C.byref(b))
+        ours_b = np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], dtype=np.float32)
+        assert np.array_equal(ours_b, oracle.bounds(h)), (ours_b, oracle.bounds(h))
+        a, w = rays.copy(), rays.copy()
+        product.intersect(sc, a)
+        oracle.intersect(h, w)
+        res = parity.compare_closest(a, w)
+        assert res["pass"] and res["hits_ours"] > 10000, res
+        sa = fx.shadow_rays(w)
+        sw = sa.copy()
+        product.occluded(sc, sa)
+        oracle.occluded(h, sw)
+        assert parity.compare_occluded(sa, sw)["pass"]
+        oracle.free(h)
+    # a topology change falls back to a full build
+    L.rtcDisableGeometry(geoms[1])
+    L.rtcCommitScene(sc)
+    assert product.build_stats(sc)["refitCount"] == 0
+    # MEDIUM quality geometry is rebuilt, never refitted
+    L.rtcEnableGeometry(geoms[1])
+    L.rtcSetGeometryBuildQuality(geoms[0], rt.RTC_BUILD_QUALITY_MEDIUM)
+    L.rtcCommitGeometry(geoms[0])
+    L.rtcCommitScene(sc)
+    L.rtcUpdateGeometryBuffer(geoms[0], rt.RTC_BUFFER_TYPE_VERTEX, 0)
+    L.rtcCommitGeometry(geoms[0])
+    L.rtcCommitScene(sc)
+    assert product.build_stats(sc)["refitCount"] == 0 and L.rtcGetDeviceError(gpu_device) == 0
+    for g in geoms:
+        L.rtcReleaseGeometry(g)
+    L.rtcReleaseScene(sc)
+
+
+def test_scene_build_quality_low_and_high(product, gpu_device, oracle):
+    """RTC_BUILD_QUALITY_LOW / HIGH select the fast / the thorough front end; answers do not change."""
+    L = product.lib
+    meshes = [fx.displaced_plane(64, extent=3.0), fx.triangle_sphere((0, 1, 0), 0.7, 24)]
+    h = oracle.build(meshes)
+    rays = fx.incoherent_rays(30000, org=(0.2, 2.0, 0.1), seed=11)
+    want = rays.copy()
+    oracle.intersect(h, want)
+    sah = {}
+    for q in (rt.RTC_BUILD_QUALITY_LOW, rt.RTC_BUILD_QUALITY_MEDIUM, rt.RTC_BUILD_QUALITY_HIGH):
+        keep = []
+        sc = L.rtcNewScene(gpu_device)
+        L.rtcSetSceneBuildQuality(sc, q)
+        for v, t in meshes:
+            _, g = product.add_mesh(gpu_device, sc, v, t, keep)
+            L.rtcReleaseGeometry(g)
+        L.rtcCommitScene(sc)
+        st = product.build_stats(sc)
+        sah[q] = st["sah"]
+        assert (st["builderIterations"] == 0) == (q == rt.RTC_BUILD_QUALITY_LOW) or q == rt.RTC_BUILD_QUALITY_MEDIUM
+        a = rays.copy()
+        product.intersect(sc, a)
+        assert parity.compare_closest(a, want)["pass"]
+        L.rtcReleaseScene(sc)
+    assert sah[rt.RTC_BUILD_QUALITY_HIGH] <= sah[rt.RTC_BUILD_QUALITY_LOW] * 1.02
+    oracle.free(h)
+
+
 def test_concurrent_queries_from_threads(product, gpu_device):
     """Queries are re-entrant on a committed scene (SURVEY 8b threading)."""
     g = cases.load_golden("two_geoms")
