@@ -960,35 +960,79 @@ RTC_API void rtcxCopySceneImage(RTCScene hs, void* dst, size_t bytes) {
     cudaCheck(cudaStreamSynchronize(s->dev->stream()), "image copy");
   RTC_CATCH(devOf(s))
 }
+namespace {
+// adopt a byte copy of a BVH image from device- or host-readable memory; throws on a bad image
+void adoptImage(Scene* s, const void* src, size_t bytes) {
+  Device* dev = s->dev;
+  if (!dev->hasGpu) fail(RTC_ERROR_UNKNOWN, "no CUDA device");
+  if (bytes < sizeof(RQImageHeader)) fail(RTC_ERROR_INVALID_ARGUMENT, "image too small");
+  dev->bind();
+  std::unique_lock<std::mutex> lock(s->buildMutex);
+  RQImageHeader H;
+  cudaCheck(cudaMemcpy(&H, src, sizeof(H), cudaMemcpyDefault), "image header");
+  if (H.magic != RQ_IMAGE_MAGIC || H.totalBytes != bytes || H.nodesOffset != 128 ||
+      H.trisOffset != H.nodesOffset + (uint64_t)H.numNodes * sizeof(RQNode) ||
+      H.trisOffset + (uint64_t)H.numTris * sizeof(RQTri) > H.totalBytes)
+    fail(RTC_ERROR_INVALID_ARGUMENT, "not a BVH image");
+  void* p = nullptr;
+  cudaCheck(cudaMalloc(&p, bytes), "image alloc");
+  int e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyDefault, dev->stream());
+  if (!e) e = cudaStreamSynchronize(dev->stream());
+  if (e) { cudaFree(p); cudaCheck(e, "image copy"); }
+  if (s->image.base) rqFreeImage(&s->image);
+  s->image.base = p; s->image.header = H; s->image.numLevels = 0;   // adopted image: level ranges unknown, never refitted
+  s->flags = (RTCSceneFlags)H.flags;
+  memset(&s->stats, 0, sizeof(s->stats));
+  s->stats.numNodes = H.numNodes; s->stats.numTris = H.numTris; s->stats.depth = H.depth; s->stats.sah = H.sah; s->stats.bytes = H.totalBytes;
+  s->stats.numPrimsValid = H.numTris;
+  s->modified = false; s->everCommitted = true;
+  { std::lock_guard<std::mutex> gl(s->geomMutex); s->seenMod.assign(s->geoms.size(), 0); for (size_t i = 0; i < s->geoms.size(); i++) if (s->geoms[i]) s->seenMod[i] = s->geoms[i]->modCounter; }
+}
+}  // namespace
 RTC_API void rtcxSetSceneImage(RTCScene hs, const void* src, size_t bytes) {
   Scene* s = (Scene*)hs;
+  RTC_TRY VERIFY_HANDLE(hs); VERIFY_HANDLE(src); adoptImage(s, src, bytes); RTC_CATCH(devOf(s))
+}
+// The flat image is position independent, so a file holding its bytes is a loadable BVH
+// (the reference has no serialisation).
+RTC_API int rtcxSaveSceneImage(RTCScene hs, const char* path) {
+  Scene* s = (Scene*)hs;
   RTC_TRY
-    VERIFY_HANDLE(hs); VERIFY_HANDLE(src);
-    Device* dev = s->dev;
-    if (!dev->hasGpu) fail(RTC_ERROR_UNKNOWN, "no CUDA device");
-    if (bytes < sizeof(RQImageHeader)) fail(RTC_ERROR_INVALID_ARGUMENT, "image too small");
-    dev->bind();
-    std::unique_lock<std::mutex> lock(s->buildMutex);
-    RQImageHeader H;
-    cudaCheck(cudaMemcpy(&H, src, sizeof(H), cudaMemcpyDefault), "image header");
-    if (H.magic != RQ_IMAGE_MAGIC || H.totalBytes != bytes || H.nodesOffset != 128 ||
-        H.trisOffset != H.nodesOffset + (uint64_t)H.numNodes * sizeof(RQNode) ||
-        H.trisOffset + (uint64_t)H.numTris * sizeof(RQTri) > H.totalBytes)
-      fail(RTC_ERROR_INVALID_ARGUMENT, "not a BVH image");
-    void* p = nullptr;
-    cudaCheck(cudaMalloc(&p, bytes), "image alloc");
-    int e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyDefault, dev->stream());
-    if (!e) e = cudaStreamSynchronize(dev->stream());
-    if (e) { cudaFree(p); cudaCheck(e, "image copy"); }
-    if (s->image.base) rqFreeImage(&s->image);
-    s->image.base = p; s->image.header = H; s->image.numLevels = 0;   // adopted image: level ranges unknown, never refitted
-    s->flags = (RTCSceneFlags)H.flags;
-    memset(&s->stats, 0, sizeof(s->stats));
-    s->stats.numNodes = H.numNodes; s->stats.numTris = H.numTris; s->stats.depth = H.depth; s->stats.sah = H.sah; s->stats.bytes = H.totalBytes;
-    s->stats.numPrimsValid = H.numTris;
-    s->modified = false; s->everCommitted = true;
-    { std::lock_guard<std::mutex> gl(s->geomMutex); s->seenMod.assign(s->geoms.size(), 0); for (size_t i = 0; i < s->geoms.size(); i++) if (s->geoms[i]) s->seenMod[i] = s->geoms[i]->modCounter; }
+    VERIFY_HANDLE(hs); VERIFY_HANDLE(path);
+    if (!s->everCommitted || s->modified) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");
+    const size_t bytes = (size_t)s->image.header.totalBytes;
+    std::vector<char> host(bytes);
+    s->dev->bind();
+    cudaCheck(cudaMemcpyAsync(host.data(), s->image.base, bytes, cudaMemcpyDeviceToHost, s->dev->stream()), "image download");
+    cudaCheck(cudaStreamSynchronize(s->dev->stream()), "image download");
+    FILE* f = fopen(path, "wb");
+    if (!f) fail(RTC_ERROR_INVALID_ARGUMENT, "cannot open file for writing");
+    const size_t w = fwrite(host.data(), 1, bytes, f);
+    const int c = fclose(f);
+    if (w != bytes || c != 0) fail(RTC_ERROR_UNKNOWN, "short write");
+    return 0;
   RTC_CATCH(devOf(s))
+  return -1;
+}
+RTC_API int rtcxLoadSceneImage(RTCScene hs, const char* path) {
+  Scene* s = (Scene*)hs;
+  RTC_TRY
+    VERIFY_HANDLE(hs); VERIFY_HANDLE(path);
+    FILE* f = fopen(path, "rb");
+    if (!f) fail(RTC_ERROR_INVALID_ARGUMENT, "cannot open file for reading");
+    std::vector<char> host;
+    try {
+      fseek(f, 0, SEEK_END); const long n = ftell(f); fseek(f, 0, SEEK_SET);
+      if (n < (long)sizeof(RQImageHeader)) { fclose(f); f = nullptr; fail(RTC_ERROR_INVALID_ARGUMENT, "not a BVH image"); }
+      host.resize((size_t)n);
+      const size_t r = fread(host.data(), 1, (size_t)n, f);
+      fclose(f); f = nullptr;
+      if (r != (size_t)n) fail(RTC_ERROR_UNKNOWN, "short read");
+    } catch (...) { if (f) fclose(f); throw; }
+    adoptImage(s, host.data(), host.size());                   // validates the header, uploads, marks committed
+    return 0;
+  RTC_CATCH(devOf(s))
+  return -1;
 }
 RTC_API void rtcxIntersect1MCounted(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHit* rh, unsigned int M, size_t stride,
                                     struct RTCXTraceCounters* out) {

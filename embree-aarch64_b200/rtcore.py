@@ -149,6 +149,8 @@ class RTCore:
             _sig(L, "rtcxGetSceneImage", vp, [vp, C.POINTER(sz)])
             _sig(L, "rtcxSetSceneImage", None, [vp, vp, sz])
             _sig(L, "rtcxCopySceneImage", None, [vp, vp, sz])
+            _sig(L, "rtcxSaveSceneImage", C.c_int, [vp, C.c_char_p])
+            _sig(L, "rtcxLoadSceneImage", C.c_int, [vp, C.c_char_p])
             _sig(L, "rtcxIntersect1MCounted", None, [vp, ctxp, vp, u, sz, C.POINTER(TraceCounters)])
             _sig(L, "rtcxOccluded1MCounted", None, [vp, ctxp, vp, u, sz, C.POINTER(TraceCounters)])
             _sig(L, "rtcxGetLaunchCount", C.c_ulonglong, [])

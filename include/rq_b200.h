@@ -60,6 +60,11 @@ RTC_API void rtcxSetSceneImage(RTCScene scene, const void* deviceImage, size_t b
  * send buffer of the broadcast. */
 RTC_API void rtcxCopySceneImage(RTCScene scene, void* dst, size_t bytes);
 
+/* The image as a file: save the committed BVH of `scene`, or make `scene` adopt a saved one
+ * (validated like rtcxSetSceneImage).  Return 0 on success, -1 on error (see rtcGetDeviceError). */
+RTC_API int rtcxSaveSceneImage(RTCScene scene, const char* path);
+RTC_API int rtcxLoadSceneImage(RTCScene scene, const char* path);
+
 /* Same as rtcIntersect1M / rtcOccluded1M, run with the instrumented kernel variant; the counters
  * are the measured numerator of the traversal roofline. */
 RTC_API void rtcxIntersect1MCounted(RTCScene scene, struct RTCIntersectContext* context, struct RTCRayHit* rayhit,

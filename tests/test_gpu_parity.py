@@ -439,6 +439,31 @@ def test_image_roundtrip_replica(product, gpu_device):
     product.lib.rtcReleaseScene(sc2)
 
 
+def test_image_save_and_load(product, gpu_device, tmp_path):
+    """the flat image written to a file is a loadable BVH."""
+    g = cases.load_golden("two_geoms")
+    sc, keep = build(product, gpu_device, g)
+    path = str(tmp_path / "scene.rqb").encode()
+    assert product.lib.rtcxSaveSceneImage(sc, path) == 0
+    sc2 = product.lib.rtcNewScene(gpu_device)
+    assert product.lib.rtcxLoadSceneImage(sc2, path) == 0
+    a, b = g["rays"].copy(), g["rays"].copy()
+    product.intersect(sc, a)
+    product.intersect(sc2, b)
+    assert np.array_equal(a, b) and parity.compare_closest(b, g["closest"])["pass"]
+    with open(path.decode(), "r+b") as f:                                  # corrupt the magic: rejected, scene keeps its image
+        f.write(b"garbage!")
+    assert product.lib.rtcxLoadSceneImage(sc2, path) == -1
+    assert product.lib.rtcGetDeviceError(gpu_device) == rt.RTC_ERROR_INVALID_ARGUMENT
+    assert product.lib.rtcxLoadSceneImage(sc2, b"/nonexistent/dir/x.rqb") == -1
+    assert product.lib.rtcGetDeviceError(gpu_device) == rt.RTC_ERROR_INVALID_ARGUMENT
+    c = g["rays"].copy()
+    product.intersect(sc2, c)
+    assert np.array_equal(a, c)
+    product.lib.rtcReleaseScene(sc)
+    product.lib.rtcReleaseScene(sc2)
+
+
 def test_build_statistics_and_counters(product, gpu_device):
     meshes = fx.scene_c1()
     sc, keep = product.build_scene(gpu_device, meshes)
