@@ -80,12 +80,27 @@ k_setup_prims(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t N,
     while (a < b) { int m = (a + b + 1) >> 1; if (geoms[m].primBase <= g) a = m; else b = m - 1; }
     const RQGeomDesc G = geoms[a];
     const uint32_t local = g - G.primBase;
-    const uint32_t* ip = (const uint32_t*)(G.indices + (size_t)local * G.indexStride);
-    const uint32_t i0 = ip[0], i1 = ip[1], i2 = ip[2];
     RQTri t;
-    t.primID = local; t.geomID = G.geomID; t.pad = 1;
+    t.primID = local; t.geomID = G.geomID; t.pad = RQ_PAD_INVALID;
     for (int k = 0; k < 3; k++) { t.v0[k] = 0.f; t.v1[k] = 0.f; t.v2[k] = 0.f; }
-    if (i0 < G.numVerts && i1 < G.numVerts && i2 < G.numVerts) {
+    uint32_t i0 = RQ_INVALID, i1 = RQ_INVALID, i2 = RQ_INVALID;
+    if (G.type == 1u) {
+      // instance primitive: v0 = lower, v1 = upper corner of its world bounds (v2 = lower again), so every
+      // later stage that takes min/max over the three "vertices" sees exactly that box
+      valid = true;
+      for (int k = 0; k < 3; k++) {
+        t.v0[k] = G.lo[k]; t.v1[k] = G.hi[k]; t.v2[k] = G.lo[k];
+        valid &= (G.lo[k] > -RQ_FLT_LARGE) & (G.hi[k] < RQ_FLT_LARGE) & (G.lo[k] <= G.hi[k]);   // scene_instance.h:92-95 (isvalid)
+      }
+      if (valid) {
+        t.pad = RQ_PAD_INSTANCE | G.instIndex;
+        for (int k = 0; k < 3; k++) { lo[k] = G.lo[k]; hi[k] = G.hi[k]; clo[k] = chi[k] = 0.5f * lo[k] + 0.5f * hi[k]; }
+      }
+    } else {
+      const uint32_t* ip = (const uint32_t*)(G.indices + (size_t)local * G.indexStride);
+      i0 = ip[0]; i1 = ip[1]; i2 = ip[2];
+    }
+    if (G.type != 1u && i0 < G.numVerts && i1 < G.numVerts && i2 < G.numVerts) {
       const float* p0 = (const float*)(G.vertices + (size_t)i0 * G.vertexStride);
       const float* p1 = (const float*)(G.vertices + (size_t)i1 * G.vertexStride);
       const float* p2 = (const float*)(G.vertices + (size_t)i2 * G.vertexStride);
@@ -148,7 +163,7 @@ k_morton(const RQTri* __restrict__ trisIn, uint32_t N, const Bounds12* __restric
   const float4* src = (const float4*)(trisIn + g);
   const float4 a = src[0], b = src[1], c = src[2];
   uint64_t key = ~0ull;                                       // invalid primitives sort to the end
-  if (__float_as_uint(c.w) == 0) {
+  if (__float_as_uint(c.w) != RQ_PAD_INVALID) {
     const float v0[3] = {a.x, a.y, a.z}, v1[3] = {a.w, b.x, b.y}, v2[3] = {b.z, b.w, c.x};
     uint32_t q[3];
     for (int k = 0; k < 3; k++) {
@@ -969,6 +984,7 @@ k_refit_tris(const RQGeomDesc* __restrict__ geomsByID, uint32_t numSlots, RQTri*
   const uint32_t odd = i & 1u;                                  // odd records: last 16 bytes first (rq_types.h)
   const float4 c = rec[odd ? 0 : 2];
   const uint32_t primID = __float_as_uint(c.y), geomID = __float_as_uint(c.z);
+  if (__float_as_uint(c.w) != 0u) return;                       // instance records keep their box (a moved instance forces a rebuild)
   if (geomID >= numSlots) return;
   const RQGeomDesc G = geomsByID[geomID];
   if (primID >= G.numTris || G.indices == nullptr || G.vertices == nullptr) return;

@@ -40,6 +40,7 @@ struct TraceParams {
   uint32_t refillBelow;      // idle lanes fetch new rays when fewer than this many lanes are traversing
   unsigned int* workCounter; // global ray cursor, zero at launch
   RQTraceCounters* counters;
+  const RQInstance* instances; // INST kernels only: table indexed by the instance records of the top-level BVH
 };
 
 __device__ __forceinline__ float rcpSafe(float d) {           // common/math/vec3fa.h:172-177
@@ -79,11 +80,20 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
 // ray goes idle; when fewer than P.refillBelow lanes of the warp are still traversing, the idle
 // lanes fetch new rays (one atomicAdd per warp per refill), so SIMD lanes stay busy although ray
 // lifetimes differ by an order of magnitude (miss after 4 nodes vs hit after 40).
-template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int SPILL>
+//
+// INST = the scene contains RTC_GEOMETRY_TYPE_INSTANCE geometries (single level; reference:
+// kernels/geometry/instance_intersector.cpp:48-105).  A triangle record whose pad word has bit 31
+// set is an instance: the lane saves its pending top-level state on the traversal stack, maps the
+// ray into the instance's space (org' = xfmPoint(world2local, org), dir' = xfmVector(world2local,
+// dir); tnear / tfar carry over unchanged because dir is not renormalised), traverses the
+// instanced scene's BVH through per-lane node / triangle base pointers and, once its part of the
+// stack is empty again, restores the world-space ray.  Hits report the instanced scene's
+// geomID / primID, Ng in instance space and instID[0] = geomID of the instance.
+template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int SPILL, bool INST = false>
 #ifndef RQ_MIN_CTAS
 #define RQ_MIN_CTAS 8   /* 64 registers: 8 CTAs = 32 warps per SM; (128,1) let ptxas take 95 registers and cost 20 % (profiles/r01k_ab.log) */
 #endif
-__global__ void __launch_bounds__(128, RQ_MIN_CTAS)
+__global__ void __launch_bounds__(128, INST ? 5 : RQ_MIN_CTAS)
 k_trace(const TraceParams P) {
   // Traversal stack: one 8-byte node-group entry per tree level.  The first P.sdepth levels live
   // in shared memory, entry-major ([level][thread]) so that lanes with different stack depths still
@@ -127,6 +137,10 @@ k_trace(const TraceParams P) {
   float hu = 0.f, hv = 0.f; RQVec3 hNg = rq_v3(0.f, 0.f, 0.f); uint32_t hPrim = 0, hGeom = 0;
   unsigned long long cntRays = 0, cntNodes = 0, cntTris = 0, cntHits = 0, cntEmpty = 0, cntHitNodes = 0, cntLate = 0; unsigned cntStack = 0, rayNodes = 0;
   bool exhausted = false;                                       // warp-uniform: the global counter ran past numRays
+  // INST only: BVH arrays the lane currently traverses, the saved world-space ray, the instance it is in
+  const char* cnodes = P.nodes; const char* ctris = P.tris;
+  float wox = 0.f, woy = 0.f, woz = 0.f, wdx = 0.f, wdy = 0.f, wdz = 0.f;
+  uint32_t curInst = RQ_INVALID, hInst = P.instID0; int spBase = 0;
 
   for (;;) {
     // ================= refill: idle lanes take the next rays of the stream =================
@@ -162,6 +176,7 @@ k_trace(const TraceParams P) {
               tnearBox = fmaxf(tnear, 0.0f);
               octinv = 7u - ((dx < 0.f ? 1u : 0u) | (dy < 0.f ? 2u : 0u) | (dz < 0.f ? 4u : 0u));
               ng = make_uint2(0u, 0x80000000u);                 // virtual parent: one inner hit -> node 0
+              if (INST) { cnodes = P.nodes; ctris = P.tris; curInst = RQ_INVALID; hInst = P.instID0; }
               if (COUNT) { cntRays++; rayNodes = 0; }
             }
           }
@@ -200,12 +215,46 @@ k_trace(const TraceParams P) {
           const uint32_t b = 31u - (uint32_t)__clz((int)tmask);
           tmask &= ~(1u << b);
           const uint32_t ti = triBase + __popc(tvalid & ((1u << b) - 1u));
-          const char* tp = P.tris + (size_t)ti * 48;
+          const char* tp = (INST ? ctris : P.tris) + (size_t)ti * 48;
           const uint32_t odd = ti & 1u;                         // odd records store their last 16 bytes first (32-byte alignment of the wide load)
           uint32_t tw[8];
           ldg256(tp + (odd ? 16 : 0), tw);
           const float4 t2 = __ldg((const float4*)(tp + (odd ? 0 : 32)));
           if (COUNT) cntTris++;
+          if (INST && (__float_as_uint(t2.w) & 0x80000000u)) {
+            // ---- instance record: enter the instanced scene ----
+            const uint4* ip = (const uint4*)(P.instances + (__float_as_uint(t2.w) & 0x7FFFFFFFu));
+            const uint4 i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2), i3 = __ldg(ip + 3), i4 = __ldg(ip + 4);
+            // pending top-level state -> three stack entries (capacity: the host adds them to the depth bound)
+            const uint2 sv[3] = {ng, make_uint2(tmask, triBase), make_uint2(tvalid, 0u)};
+            #pragma unroll
+            for (int e = 0; e < 3; e++) {
+              if ((uint32_t)sp < sdepth) s_stack[(uint32_t)sp * 128u + threadIdx.x] = sv[e];
+              else if (SPILL && sp < (int)sdepth + SPILL) spill[(uint32_t)sp - sdepth] = sv[e];
+              sp++;
+            }
+            spBase = sp;
+            wox = ox; woy = oy; woz = oz; wdx = dx; wdy = dy; wdz = dz;
+            // world2local, column major: vx = (i0.x,i0.y,i0.z) vy = (i0.w,i1.x,i1.y) vz = (i1.z,i1.w,i2.x) p = (i2.y,i2.z,i2.w)
+            const float vxx = __uint_as_float(i0.x), vxy = __uint_as_float(i0.y), vxz = __uint_as_float(i0.z);
+            const float vyx = __uint_as_float(i0.w), vyy = __uint_as_float(i1.x), vyz = __uint_as_float(i1.y);
+            const float vzx = __uint_as_float(i1.z), vzy = __uint_as_float(i1.w), vzz = __uint_as_float(i2.x);
+            const float px = __uint_as_float(i2.y), py = __uint_as_float(i2.z), pz = __uint_as_float(i2.w);
+            // xfmPoint / xfmVector with the reference's FMA nesting (common/math/affinespace.h:102, linearspace3.h:156)
+            ox = __fmaf_rn(wox, vxx, __fmaf_rn(woy, vyx, __fmaf_rn(woz, vzx, px)));
+            oy = __fmaf_rn(wox, vxy, __fmaf_rn(woy, vyy, __fmaf_rn(woz, vzy, py)));
+            oz = __fmaf_rn(wox, vxz, __fmaf_rn(woy, vyz, __fmaf_rn(woz, vzz, pz)));
+            dx = __fmaf_rn(wdx, vxx, __fmaf_rn(wdy, vyx, __fmul_rn(wdz, vzx)));
+            dy = __fmaf_rn(wdx, vxy, __fmaf_rn(wdy, vyy, __fmul_rn(wdz, vzy)));
+            dz = __fmaf_rn(wdx, vxz, __fmaf_rn(wdy, vyz, __fmul_rn(wdz, vzz)));
+            idx_ = rcpSafe(dx); idy_ = rcpSafe(dy); idz_ = rcpSafe(dz);
+            octinv = 7u - ((dx < 0.f ? 1u : 0u) | (dy < 0.f ? 2u : 0u) | (dz < 0.f ? 4u : 0u));
+            cnodes = (const char*)(((unsigned long long)i3.y << 32) | i3.x);
+            ctris = (const char*)(((unsigned long long)i3.w << 32) | i3.z);
+            curInst = i4.x;
+            ng = make_uint2(0u, 0x80000000u); tmask = 0u;           // virtual parent of the instanced root
+            break;
+          }
           const RQVec3 v0 = rq_v3(__uint_as_float(tw[0]), __uint_as_float(tw[1]), __uint_as_float(tw[2]));
           const RQVec3 v1 = rq_v3(__uint_as_float(tw[3]), __uint_as_float(tw[4]), __uint_as_float(tw[5]));
           const RQVec3 v2 = rq_v3(__uint_as_float(tw[6]), __uint_as_float(tw[7]), t2.x);
@@ -214,10 +263,11 @@ k_trace(const TraceParams P) {
                                  : rq_moeller(O, D, tnear, tfar, v0, v1, v2, h);
           if (ok) {
             found = true;
-            if (OCCLUDED) { tmask = 0u; ng.y = 0u; sp = 0; }    // any hit ends the ray (finishes in the N phase)
+            if (OCCLUDED) { tmask = 0u; ng.y = 0u; sp = 0; if (INST) curInst = RQ_INVALID; }    // any hit ends the ray (finishes in the N phase)
             else {
               tfar = h.t; hu = h.u; hv = h.v; hNg = h.Ng;
               hPrim = __float_as_uint(t2.y); hGeom = __float_as_uint(t2.z);
+              if (INST) hInst = (curInst != RQ_INVALID) ? curInst : P.instID0;
             }
           }
           if (SPLIT) break;
@@ -225,6 +275,24 @@ k_trace(const TraceParams P) {
       }
       // ---------------- N phase ----------------
       if (runN && active && tmask == 0u) {
+        bool leftInstance = false;
+        if (INST && !(ng.y & 0xFF000000u) && curInst != RQ_INVALID && sp == spBase) {
+          // ---- the instanced scene is done: back to world space and to the saved top-level state ----
+          uint2 sv[3];
+          #pragma unroll
+          for (int e = 2; e >= 0; e--) {
+            --sp;
+            if ((uint32_t)sp < sdepth) sv[e] = s_stack[(uint32_t)sp * 128u + threadIdx.x];
+            else if (SPILL) sv[e] = spill[(uint32_t)sp - sdepth];
+            else sv[e] = make_uint2(0u, 0u);
+          }
+          ng = sv[0]; tmask = sv[1].x; triBase = sv[1].y; tvalid = sv[2].x;
+          ox = wox; oy = woy; oz = woz; dx = wdx; dy = wdy; dz = wdz;
+          idx_ = rcpSafe(dx); idy_ = rcpSafe(dy); idz_ = rcpSafe(dz);
+          octinv = 7u - ((dx < 0.f ? 1u : 0u) | (dy < 0.f ? 2u : 0u) | (dz < 0.f ? 4u : 0u));
+          cnodes = P.nodes; ctris = P.tris; curInst = RQ_INVALID;
+          leftInstance = true;                                  // pending triangles / nodes of the top level continue next iteration
+        } else
         if (!(ng.y & 0xFF000000u)) {                            // node group exhausted: pop, or the ray is finished
           if (sp > (int)sdepth + SPILL) sp = (int)sdepth + SPILL;  // entries beyond the stack were dropped (cannot happen: capacity >= depth)
           if (sp == 0) {
@@ -238,11 +306,11 @@ k_trace(const TraceParams P) {
                 *(float*)(rp + 32) = tfar;
                 if (ALIGNED) {
                   *(float4*)(rp + 48) = make_float4(hNg.x, hNg.y, hNg.z, hu);
-                  *(float4*)(rp + 64) = make_float4(hv, __uint_as_float(hPrim), __uint_as_float(hGeom), __uint_as_float(P.instID0));
+                  *(float4*)(rp + 64) = make_float4(hv, __uint_as_float(hPrim), __uint_as_float(hGeom), __uint_as_float(INST ? hInst : P.instID0));
                 } else {
                   float* f = (float*)(rp + 48);
                   f[0] = hNg.x; f[1] = hNg.y; f[2] = hNg.z; f[3] = hu; f[4] = hv;
-                  ((uint32_t*)f)[5] = hPrim; ((uint32_t*)f)[6] = hGeom; ((uint32_t*)f)[7] = P.instID0;
+                  ((uint32_t*)f)[5] = hPrim; ((uint32_t*)f)[6] = hGeom; ((uint32_t*)f)[7] = INST ? hInst : P.instID0;
                 }
               }
             }
@@ -252,7 +320,7 @@ k_trace(const TraceParams P) {
             else if (SPILL) ng = spill[(uint32_t)sp - sdepth];
           }
         }
-        if (active) {
+        if (active && !(INST && leftInstance)) {
           // ---- descend: take the nearest pending inner child (highest bit) ----
           const uint32_t bit = 31u - (uint32_t)__clz((int)ng.y);
           ng.y &= ~(1u << bit);
@@ -264,7 +332,7 @@ k_trace(const TraceParams P) {
           }
           const uint32_t slot = (bit - 24u) ^ octinv;
           const uint32_t rel = __popc(ng.y & 0xFFu & ((1u << slot) - 1u));
-          const char* np = P.nodes + (size_t)(ng.x + rel) * 128;
+          const char* np = (INST ? cnodes : P.nodes) + (size_t)(ng.x + rel) * 128;
           uint32_t na[8], nb[8], nc[8];
           ldg256(np, na); ldg256(np + 32, nb); ldg256(np + 64, nc);
           const uint4 n0 = make_uint4(na[0], na[1], na[2], na[3]), n1 = make_uint4(na[4], na[5], na[6], na[7]);
@@ -379,6 +447,12 @@ template <bool OCC, bool ROBUST, bool COUNT, bool ALIGNED>
 cudaError_t launchStack(TraceParams& P, uint32_t depth, cudaStream_t s) {
   if (P.sdepth > depth) P.sdepth = depth;
   const uint32_t spill = depth - P.sdepth;
+  if (P.instances) {
+    // instanced scenes: one stack configuration (shared levels + 32 local entries), no counters
+    if (spill > 32) return cudaErrorInvalidValue;
+    if (P.split) return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, true, 32, true>, P, s);
+    return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, false, 32, true>, P, s);
+  }
   if (spill == 0) {
     if (P.split) return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, true, 0>, P, s);
     return launchOne(k_trace<OCC, ROBUST, COUNT, ALIGNED, false, 0>, P, s);
@@ -405,6 +479,7 @@ static int launchTrace(bool occ, const RQTraceArgs* a, cudaStream_t s) {
   P.workCounter = a->workCounter;
   P.refillBelow = a->refillBelow ? a->refillBelow : 26u;
   P.split = a->split; P.tVote = a->tVote; P.sdepth = a->stackSmem;
+  P.instances = (const RQInstance*)a->instances;
   if (!P.workCounter) return (int)cudaErrorInvalidValue;
   {
     cudaError_t ez = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), s);   // stream ordered with the launch

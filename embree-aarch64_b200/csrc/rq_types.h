@@ -58,6 +58,21 @@ struct alignas(16) RQTri {
 };
 static_assert(sizeof(RQTri) == 48, "RQTri must be 48 bytes");
 
+// One instance of another committed scene (RTC_GEOMETRY_TYPE_INSTANCE, single level), 80 bytes =
+// five 16-byte loads.  A triangle record of the top-level BVH whose `pad` word is
+// RQ_PAD_INSTANCE | i stands for instances[i]; its v0 / v1 hold the world-space bounds.
+#define RQ_PAD_INVALID  1u
+#define RQ_PAD_INSTANCE 0x80000000u
+struct alignas(16) RQInstance {
+  float    w2l[12];         // world -> instance space, column major: vx, vy, vz, p (AffineSpace3fa)
+  uint64_t nodes;           // device address of the instanced scene's RQNode array
+  uint64_t tris;            // device address of its RQTri array
+  uint32_t geomID;          // geomID of the instance geometry in the top-level scene -> hit.instID[0]
+  uint32_t depth;           // levels of the instanced BVH
+  uint32_t pad[2];
+};
+static_assert(sizeof(RQInstance) == 80, "RQInstance is five 16-byte words");
+
 // One triangle mesh as the builder sees it (device-readable pointers, arbitrary 4-byte-multiple strides).
 struct RQGeomDesc {
   const uint8_t* indices;    // RTC_FORMAT_UINT3 records
@@ -68,6 +83,9 @@ struct RQGeomDesc {
   uint32_t numVerts;
   uint32_t primBase;         // first global primitive number of this mesh
   uint32_t geomID;
+  uint32_t type;             // 0 = triangle mesh; 1 = instance: one primitive with the bounds below (numTris = 1)
+  uint32_t instIndex;        // index into the scene's RQInstance table
+  float    lo[3], hi[3];     // instance only: world-space bounds = xfmBounds(local2world, bounds of the instanced scene)
 };
 
 // Flat image of a committed BVH: header + nodes + triangles, all offset based, so a byte copy

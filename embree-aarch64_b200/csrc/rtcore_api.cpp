@@ -189,8 +189,13 @@ struct BufferView {
   const char* data() const { return buf ? buf->ptr + offset : nullptr; }
 };
 
+struct Scene;
 struct Geometry : RefCounted {
   Device* dev; RTCGeometryType type;
+  // RTC_GEOMETRY_TYPE_INSTANCE (kernels/common/scene_instance.h): the instanced scene and local2world,
+  // column major (vx, vy, vz, p) like AffineSpace3fa
+  Scene* instanced = nullptr;
+  float l2w[12] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};
   BufferView vertices, indices;
   bool committed = false, enabled = true;
   unsigned modCounter = 0, mask = 0xFFFFFFFFu;
@@ -198,7 +203,7 @@ struct Geometry : RefCounted {
   void* userPtr = nullptr;
   RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
   Geometry(Device* d, RTCGeometryType t) : dev(d), type(t) { dev->retain(); }
-  ~Geometry() override { vertices.clear(); indices.clear(); dev->release(); }
+  ~Geometry() override;
   void update() { ++modCounter; ++topoCounter; committed = false; }
   void updateVertices() { ++modCounter; committed = false; }   // rtcUpdateGeometryBuffer(RTC_BUFFER_TYPE_VERTEX)
 };
@@ -212,15 +217,18 @@ struct Scene : RefCounted {
   RTCSceneFlags flags = RTC_SCENE_FLAG_NONE; RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
   bool modified = true, everCommitted = false;
   RQDeviceImage image{nullptr, {}};
+  RQInstance* dInstances = nullptr; unsigned numInstances = 0; unsigned traceDepth = 0;   // instance table of a scene with instance geometries
   RQBuildStats stats{};
   RTCProgressMonitorFunction progress = nullptr; void* progressPtr = nullptr;
   explicit Scene(Device* d) : dev(d) { dev->retain(); memset(&stats, 0, sizeof(stats)); }
   ~Scene() override {
     for (Geometry* g : geoms) if (g) g->release();
     if (image.base) { dev->bind(); rqFreeImage(&image); }
+    if (dInstances) { dev->bind(); cudaFree(dInstances); }
     dev->release();
   }
 };
+Geometry::~Geometry() { vertices.clear(); indices.clear(); if (instanced) instanced->release(); dev->release(); }
 
 bool isDevicePointer(const void* p) {
   cudaPointerAttributes a;
