@@ -218,6 +218,9 @@ struct Scene : RefCounted {
   bool modified = true, everCommitted = false;
   RQDeviceImage image{nullptr, {}};
   RQInstance* dInstances = nullptr; unsigned numInstances = 0; unsigned traceDepth = 0;   // instance table of a scene with instance geometries
+  unsigned long long epoch = 0;                          // bumped by every commit / image adoption
+  std::vector<std::pair<Scene*, unsigned long long>> instancedEpochs;   // distinct instanced scenes (each retained) and the epoch their device pointers were taken at
+  void clearInstanced() { for (auto& e : instancedEpochs) e.first->release(); instancedEpochs.clear(); }
   RQBuildStats stats{};
   RTCProgressMonitorFunction progress = nullptr; void* progressPtr = nullptr;
   explicit Scene(Device* d) : dev(d) { dev->retain(); memset(&stats, 0, sizeof(stats)); }
@@ -225,6 +228,7 @@ struct Scene : RefCounted {
     for (Geometry* g : geoms) if (g) g->release();
     if (image.base) { dev->bind(); rqFreeImage(&image); }
     if (dInstances) { dev->bind(); cudaFree(dInstances); }
+    clearInstanced();
     dev->release();
   }
 };
@@ -277,6 +281,7 @@ void commitScene(Scene* sc) {
         if (g->topoCounter != sc->seenTopo[i] || g->quality != RTC_BUILD_QUALITY_REFIT) refit = false;
       }
     }
+    for (const auto& e : sc->instancedEpochs) if (e.first->epoch != e.second) { changed = true; refit = false; }   // an instanced scene was re-committed
     if (!changed) return;
   }
   if (!dev->hasGpu) fail(RTC_ERROR_UNKNOWN, "no CUDA device: cannot build (there is no CPU fallback)");
@@ -285,6 +290,8 @@ void commitScene(Scene* sc) {
   if (sc->progress && !sc->progress(sc->progressPtr, 0.0)) fail(RTC_ERROR_CANCELLED, "progress monitor forced termination");
 
   std::vector<RQGeomDesc> descs;
+  std::vector<RQInstance> insts;
+  unsigned instDepth = 0;
   TempDev tmp;
   {
     std::lock_guard<std::mutex> gl(sc->geomMutex);
@@ -292,6 +299,53 @@ void commitScene(Scene* sc) {
       Geometry* g = sc->geoms[i];
       if (!g) continue;
       sc->seenMod[i] = g->modCounter; sc->seenTopo[i] = g->topoCounter;
+      if (g->enabled && g->type == RTC_GEOMETRY_TYPE_INSTANCE) {
+        // one primitive whose box is xfmBounds(local2world, bounds of the instanced scene) (scene_instance.h:61-66);
+        // the instanced scene must be committed first, as in the reference
+        Scene* in = g->instanced;
+        if (!in) continue;
+        if (in == sc) fail(RTC_ERROR_INVALID_OPERATION, "a scene cannot instantiate itself");
+        if (!in->everCommitted || in->modified || !in->image.base) fail(RTC_ERROR_INVALID_OPERATION, "instanced scene not committed");
+        if (in->numInstances) fail(RTC_ERROR_INVALID_OPERATION, "multi-level instancing is not supported (RTC_MAX_INSTANCE_LEVEL_COUNT = 1)");
+        if (((in->flags ^ sc->flags) & RTC_SCENE_FLAG_ROBUST) != 0)
+          fail(RTC_ERROR_INVALID_OPERATION, "an instanced scene must use the same RTC_SCENE_FLAG_ROBUST setting as the scene instantiating it");
+        refit = false;
+        RQInstance I; memset(&I, 0, sizeof(I));
+        RQGeomDesc d; memset(&d, 0, sizeof(d));
+        const float* m = g->l2w;
+        // world2local = rcp(local2world): adjoint / det and -(l^-1 * p) (linearspace3.h:44-50, affinespace.h rcp), in double
+        {
+          const double vx[3] = {m[0], m[1], m[2]}, vy[3] = {m[3], m[4], m[5]}, vz[3] = {m[6], m[7], m[8]}, p[3] = {m[9], m[10], m[11]};
+          const double c0[3] = {vy[1] * vz[2] - vy[2] * vz[1], vy[2] * vz[0] - vy[0] * vz[2], vy[0] * vz[1] - vy[1] * vz[0]};   // cross(vy, vz)
+          const double c1[3] = {vz[1] * vx[2] - vz[2] * vx[1], vz[2] * vx[0] - vz[0] * vx[2], vz[0] * vx[1] - vz[1] * vx[0]};   // cross(vz, vx)
+          const double c2[3] = {vx[1] * vy[2] - vx[2] * vy[1], vx[2] * vy[0] - vx[0] * vy[2], vx[0] * vy[1] - vx[1] * vy[0]};   // cross(vx, vy)
+          const double det = vx[0] * c0[0] + vx[1] * c0[1] + vx[2] * c0[2];
+          // inverse = transposed(rows c0, c1, c2) / det  =>  column k of the inverse = (c0[k], c1[k], c2[k]) / det
+          double il[9];
+          for (int k = 0; k < 3; k++) { il[3 * k + 0] = c0[k] / det; il[3 * k + 1] = c1[k] / det; il[3 * k + 2] = c2[k] / det; }
+          for (int k = 0; k < 9; k++) I.w2l[k] = (float)il[k];
+          for (int r = 0; r < 3; r++) I.w2l[9 + r] = (float)(-(il[r] * p[0] + il[3 + r] * p[1] + il[6 + r] * p[2]));
+        }
+        const RQImageHeader& IH = in->image.header;
+        I.nodes = (uint64_t)((char*)in->image.base + IH.nodesOffset);
+        I.tris = (uint64_t)((char*)in->image.base + IH.trisOffset);
+        I.geomID = (uint32_t)i; I.depth = IH.depth;
+        instDepth = std::max(instDepth, (unsigned)IH.depth);
+        // xfmBounds: the 8 corners through xfmPoint with the reference's FMA nesting (affinespace.h:102-118)
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int c = 0; c < 8; c++) {
+          const float x = (c & 4) ? IH.hi[0] : IH.lo[0], y = (c & 2) ? IH.hi[1] : IH.lo[1], z = (c & 1) ? IH.hi[2] : IH.lo[2];
+          for (int r = 0; r < 3; r++) {
+            const float v = fmaf(x, m[r], fmaf(y, m[3 + r], fmaf(z, m[6 + r], m[9 + r])));
+            lo[r] = fminf(lo[r], v); hi[r] = fmaxf(hi[r], v);      // NaN corners are ignored; an empty instanced scene yields an inverted box
+          }
+        }
+        d.type = 1; d.numTris = 1; d.geomID = (uint32_t)i; d.instIndex = (uint32_t)insts.size();
+        for (int r = 0; r < 3; r++) { d.lo[r] = lo[r]; d.hi[r] = hi[r]; }
+        insts.push_back(I);
+        descs.push_back(d);
+        continue;
+      }
       if (!g->enabled || g->indices.count == 0) continue;
       RQGeomDesc d; memset(&d, 0, sizeof(d));
       const char* ip = g->indices.data(); const char* vp = g->vertices.data();
@@ -316,13 +370,34 @@ void commitScene(Scene* sc) {
     // scene build quality: LOW = the fast radix-tree front end (role of the reference's Morton builder for
     // RTC_BUILD_QUALITY_LOW, scene.cpp:118-124), HIGH = PLOC with a wide search radius (the reference adds
     // spatial splits here, which this builder does not do)
+    if (!insts.empty()) bp.maxLeafTris = 1;                  // every instance gets its own child box: entering one costs a ray transform + a root fetch
     if (sc->quality == RTC_BUILD_QUALITY_LOW) bp.builder = 0;
     else if (sc->quality == RTC_BUILD_QUALITY_HIGH) { bp.builder = 1; bp.plocRadius = std::max(bp.plocRadius, 16); }
     cudaCheck(rqBuildBVH(descs.data(), (int)descs.size(), (uint32_t)sc->flags, &bp, (rqStream)s, &img, &st), "BVH build");
     if (sc->image.base) rqFreeImage(&sc->image);
     sc->image = img; sc->stats = st;
+    // instance table (traversal reads it through TraceParams::instances)
+    if (sc->dInstances) { cudaFree(sc->dInstances); sc->dInstances = nullptr; }
+    sc->numInstances = (unsigned)insts.size();
+    sc->clearInstanced();
+    {
+      std::lock_guard<std::mutex> gl(sc->geomMutex);
+      for (Geometry* g : sc->geoms)
+        if (g && g->enabled && g->type == RTC_GEOMETRY_TYPE_INSTANCE && g->instanced) {
+          bool seen = false;
+          for (auto& e : sc->instancedEpochs) seen |= (e.first == g->instanced);
+          if (!seen) { g->instanced->retain(); sc->instancedEpochs.push_back({g->instanced, g->instanced->epoch}); }
+        }
+    }
+    sc->traceDepth = img.header.depth;
+    if (!insts.empty()) {
+      cudaCheck(cudaMalloc((void**)&sc->dInstances, insts.size() * sizeof(RQInstance)), "instance table");
+      cudaCheck(cudaMemcpyAsync(sc->dInstances, insts.data(), insts.size() * sizeof(RQInstance), cudaMemcpyHostToDevice, s), "instance table");
+      cudaCheck(cudaStreamSynchronize(s), "instance table");
+      sc->traceDepth = img.header.depth + 3 + instDepth;       // the lane parks 3 entries of top-level state while inside an instance
+    }
   }
-  sc->modified = false; sc->everCommitted = true;
+  sc->modified = false; sc->everCommitted = true; sc->epoch++;
   if (sc->progress) sc->progress(sc->progressPtr, 1.0);
   if (dev->benchmark || dev->verbose >= 2) {
     // same fields as the reference's line (bvh.cpp:173-178): seconds, prims/s, SAH, bytes
@@ -339,12 +414,17 @@ void commitScene(Scene* sc) {
 void checkQuery(Scene* sc, RTCIntersectContext* ctx) {
   if (!sc->everCommitted || sc->modified) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");   // scene.cpp:13,30
   if (ctx && ctx->filter) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the GPU");
+  // the instance table holds device pointers into the instanced scenes' images: a re-commit there invalidates them
+  for (const auto& e : sc->instancedEpochs)
+    if (e.first->epoch != e.second || e.first->modified)
+      fail(RTC_ERROR_INVALID_OPERATION, "an instanced scene changed: commit the instantiating scene again");
 }
 
 void fillArgs(Scene* sc, RTCIntersectContext* ctx, RQTraceArgs& a, bool stream) {
   memset(&a, 0, sizeof(a));
   a.image = sc->image.base; a.nodesOffset = sc->image.header.nodesOffset; a.trisOffset = sc->image.header.trisOffset;
-  a.depth = sc->image.header.depth;
+  a.depth = sc->numInstances ? sc->traceDepth : sc->image.header.depth;
+  a.instances = sc->numInstances ? sc->dInstances : nullptr;
   a.robust = (sc->flags & RTC_SCENE_FLAG_ROBUST) ? 1u : 0u;
   a.instID0 = ctx ? ctx->instID[0] : RTC_INVALID_GEOMETRY_ID;
   a.streamSemantics = stream ? 1u : 0u;
@@ -602,8 +682,8 @@ RTC_API RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
   Device* d = (Device*)h;
   RTC_TRY
     VERIFY_HANDLE(h);
-    if (type != RTC_GEOMETRY_TYPE_TRIANGLE)
-      fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE is supported by the B200 ray-query device");
+    if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_INSTANCE)
+      fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE and RTC_GEOMETRY_TYPE_INSTANCE are supported by the B200 ray-query device");
     return (RTCGeometry) new Geometry(d, type);
   RTC_CATCH(d)
   return nullptr;
@@ -632,6 +712,7 @@ RTC_API void rtcSetGeometryBuildQuality(RTCGeometry h, enum RTCBuildQuality q) {
 
 namespace {
 void setBuffer(Geometry* g, RTCBufferType type, unsigned slot, RTCFormat format, Buffer* buf, size_t offset, size_t stride, unsigned num) {
+  if (g->type != RTC_GEOMETRY_TYPE_TRIANGLE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
   if ((((size_t)buf->ptr + offset) & 3) || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
   if (type == RTC_BUFFER_TYPE_VERTEX) {
     if (format != RTC_FORMAT_FLOAT3) fail(RTC_ERROR_INVALID_OPERATION, "invalid vertex buffer format");
@@ -711,6 +792,66 @@ RTC_API void rtcSetGeometryIntersectFilterFunction(RTCGeometry h, RTCFilterFunct
 RTC_API void rtcSetGeometryOccludedFilterFunction(RTCGeometry h, RTCFilterFunctionN f) {
   Geometry* g = (Geometry*)h;
   RTC_TRY VERIFY_HANDLE(h); if (f) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the GPU"); RTC_CATCH(devOf(g))
+}
+
+// ---- instances (kernels/common/rtcore.cpp:1008-1125, scene_instance.cpp) ----
+RTC_API void rtcSetGeometryInstancedScene(RTCGeometry h, RTCScene hs) {
+  Geometry* g = (Geometry*)h; Scene* sc = (Scene*)hs;
+  RTC_TRY
+    VERIFY_HANDLE(h); VERIFY_HANDLE(hs);
+    if (g->type != RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
+    if (g->dev != sc->dev) fail(RTC_ERROR_INVALID_ARGUMENT, "inputs are from different devices");
+    sc->retain();
+    if (g->instanced) g->instanced->release();
+    g->instanced = sc;
+    g->update();
+  RTC_CATCH(devOf(g))
+}
+RTC_API void rtcSetGeometryTransform(RTCGeometry h, unsigned int timeStep, enum RTCFormat format, const void* xfm) {
+  Geometry* g = (Geometry*)h;
+  RTC_TRY
+    VERIFY_HANDLE(h); VERIFY_HANDLE(xfm);
+    if (g->type != RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
+    if (timeStep != 0) fail(RTC_ERROR_INVALID_OPERATION, "motion blur is not supported by the B200 ray-query device");
+    const float* m = (const float*)xfm;
+    float* o = g->l2w;                                        // vx, vy, vz, p  (loadTransform, rtcore.cpp:1008-1039)
+    switch (format) {
+      case RTC_FORMAT_FLOAT3X4_ROW_MAJOR:
+        o[0] = m[0]; o[1] = m[4]; o[2] = m[8];  o[3] = m[1]; o[4] = m[5]; o[5] = m[9];
+        o[6] = m[2]; o[7] = m[6]; o[8] = m[10]; o[9] = m[3]; o[10] = m[7]; o[11] = m[11];
+        break;
+      case RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR:
+        for (int i = 0; i < 12; i++) o[i] = m[i];
+        break;
+      case RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR:
+        for (int c = 0; c < 4; c++) for (int r = 0; r < 3; r++) o[3 * c + r] = m[4 * c + r];
+        break;
+      default: fail(RTC_ERROR_INVALID_OPERATION, "invalid matrix format");
+    }
+    g->update();
+  RTC_CATCH(devOf(g))
+}
+RTC_API void rtcGetGeometryTransform(RTCGeometry h, float, enum RTCFormat format, void* xfm) {
+  Geometry* g = (Geometry*)h;
+  RTC_TRY
+    VERIFY_HANDLE(h); VERIFY_HANDLE(xfm);
+    float* m = (float*)xfm;
+    const float* o = g->l2w;                                  // identity for non-instance geometries, as in the reference (geometry.h getTransform)
+    switch (format) {                                         // storeTransform, rtcore.cpp:1041-1069
+      case RTC_FORMAT_FLOAT3X4_ROW_MAJOR:
+        m[0] = o[0]; m[1] = o[3]; m[2] = o[6]; m[3] = o[9];
+        m[4] = o[1]; m[5] = o[4]; m[6] = o[7]; m[7] = o[10];
+        m[8] = o[2]; m[9] = o[5]; m[10] = o[8]; m[11] = o[11];
+        break;
+      case RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR:
+        for (int i = 0; i < 12; i++) m[i] = o[i];
+        break;
+      case RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR:
+        for (int c = 0; c < 4; c++) { for (int r = 0; r < 3; r++) m[4 * c + r] = o[3 * c + r]; m[4 * c + 3] = (c == 3) ? 1.f : 0.f; }
+        break;
+      default: fail(RTC_ERROR_INVALID_OPERATION, "invalid matrix format");
+    }
+  RTC_CATCH(devOf(g))
 }
 
 // ================================================================================================
@@ -952,6 +1093,7 @@ RTC_API const void* rtcxGetSceneImage(RTCScene hs, size_t* bytes) {
   RTC_TRY
     VERIFY_HANDLE(hs);
     if (!s->everCommitted || s->modified) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");
+    if (s->numInstances) fail(RTC_ERROR_INVALID_OPERATION, "the image of a scene with instances refers to other scenes and cannot be exported");
     if (bytes) *bytes = (size_t)s->image.header.totalBytes;
     return s->image.base;
   RTC_CATCH(devOf(s))
@@ -962,6 +1104,7 @@ RTC_API void rtcxCopySceneImage(RTCScene hs, void* dst, size_t bytes) {
   RTC_TRY
     VERIFY_HANDLE(hs); VERIFY_HANDLE(dst);
     if (!s->everCommitted || s->modified) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");
+    if (s->numInstances) fail(RTC_ERROR_INVALID_OPERATION, "the image of a scene with instances refers to other scenes and cannot be exported");
     if (bytes != s->image.header.totalBytes) fail(RTC_ERROR_INVALID_ARGUMENT, "size does not match the image");
     s->dev->bind();
     cudaCheck(cudaMemcpyAsync(dst, s->image.base, bytes, cudaMemcpyDefault, s->dev->stream()), "image copy");
@@ -988,6 +1131,8 @@ void adoptImage(Scene* s, const void* src, size_t bytes) {
   if (!e) e = cudaStreamSynchronize(dev->stream());
   if (e) { cudaFree(p); cudaCheck(e, "image copy"); }
   if (s->image.base) rqFreeImage(&s->image);
+  if (s->dInstances) { cudaFree(s->dInstances); s->dInstances = nullptr; }
+  s->numInstances = 0; s->clearInstanced(); s->epoch++;
   s->image.base = p; s->image.header = H; s->image.numLevels = 0;   // adopted image: level ranges unknown, never refitted
   s->flags = (RTCSceneFlags)H.flags;
   memset(&s->stats, 0, sizeof(s->stats));
@@ -1008,6 +1153,7 @@ RTC_API int rtcxSaveSceneImage(RTCScene hs, const char* path) {
   RTC_TRY
     VERIFY_HANDLE(hs); VERIFY_HANDLE(path);
     if (!s->everCommitted || s->modified) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");
+    if (s->numInstances) fail(RTC_ERROR_INVALID_OPERATION, "the image of a scene with instances refers to other scenes and cannot be exported");
     const size_t bytes = (size_t)s->image.header.totalBytes;
     std::vector<char> host(bytes);
     s->dev->bind();
@@ -1073,10 +1219,7 @@ B200RQ_STUB(void, rtcSetGeometryIntersectFunction, (RTCGeometry g, void*), devOf
 B200RQ_STUB(void, rtcSetGeometryOccludedFunction, (RTCGeometry g, void*), devOf((Geometry*)g), )
 B200RQ_STUB(void, rtcFilterIntersection, (const void*, const void*), B200RQ_NODEV, )
 B200RQ_STUB(void, rtcFilterOcclusion, (const void*, const void*), B200RQ_NODEV, )
-B200RQ_STUB(void, rtcSetGeometryInstancedScene, (RTCGeometry g, RTCScene), devOf((Geometry*)g), )
-B200RQ_STUB(void, rtcSetGeometryTransform, (RTCGeometry g, unsigned int, enum RTCFormat, const void*), devOf((Geometry*)g), )
 B200RQ_STUB(void, rtcSetGeometryTransformQuaternion, (RTCGeometry g, unsigned int, const void*), devOf((Geometry*)g), )
-B200RQ_STUB(void, rtcGetGeometryTransform, (RTCGeometry g, float, enum RTCFormat, void*), devOf((Geometry*)g), )
 B200RQ_STUB(void, rtcSetGeometryTessellationRate, (RTCGeometry g, float), devOf((Geometry*)g), )
 B200RQ_STUB(void, rtcSetGeometryTopologyCount, (RTCGeometry g, unsigned int), devOf((Geometry*)g), )
 B200RQ_STUB(void, rtcSetGeometrySubdivisionMode, (RTCGeometry g, unsigned int, enum RTCSubdivisionMode), devOf((Geometry*)g), )

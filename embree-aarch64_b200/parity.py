@@ -15,7 +15,7 @@ def compare_closest(ours, ref, edge_eps=1e-4, t_rel=1e-5, uv_abs=1e-4):
     n = len(ours)
     ho, hr = ours["geomID"] != INVALID, ref["geomID"] != INVALID
     both = ho & hr
-    same_id = both & (ours["geomID"] == ref["geomID"]) & (ours["primID"] == ref["primID"])
+    same_id = both & (ours["geomID"] == ref["geomID"]) & (ours["primID"] == ref["primID"]) & (ours["instID"] == ref["instID"])
     # barycentric distance to the nearest edge, from whichever side reported a hit
     def edge_dist(r):
         return np.minimum(np.minimum(r["u"], r["v"]), 1.0 - r["u"] - r["v"])

@@ -24,6 +24,10 @@ RTC_BUFFER_TYPE_INDEX = 0
 RTC_BUFFER_TYPE_VERTEX = 1
 RTC_GEOMETRY_TYPE_TRIANGLE = 0
 RTC_GEOMETRY_TYPE_QUAD = 1
+RTC_GEOMETRY_TYPE_INSTANCE = 121
+RTC_FORMAT_FLOAT3X4_ROW_MAJOR = 0x9134
+RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR = 0x9234
+RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR = 0x9244
 RTC_SCENE_FLAG_NONE = 0
 RTC_SCENE_FLAG_DYNAMIC = 1
 RTC_SCENE_FLAG_COMPACT = 2
@@ -123,6 +127,9 @@ class RTCore:
         _sig(L, "rtcUpdateGeometryBuffer", None, [vp, C.c_int, u])
         _sig(L, "rtcSetGeometryTimeStepCount", None, [vp, u])
         _sig(L, "rtcSetGeometryBuildQuality", None, [vp, C.c_int])
+        _sig(L, "rtcSetGeometryInstancedScene", None, [vp, vp])
+        _sig(L, "rtcSetGeometryTransform", None, [vp, u, C.c_int, vp])
+        _sig(L, "rtcGetGeometryTransform", None, [vp, C.c_float, C.c_int, vp])
         _sig(L, "rtcNewBuffer", vp, [vp, sz])
         _sig(L, "rtcNewSharedBuffer", vp, [vp, vp, sz])
         _sig(L, "rtcGetBufferData", vp, [vp])
@@ -196,6 +203,38 @@ class RTCore:
             self.lib.rtcReleaseGeometry(g)
         self.lib.rtcCommitScene(sc)
         return sc, keep
+
+    def add_instance(self, device, scene, instanced_scene, l2w, fmt=RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR):
+        """Attach an instance of `instanced_scene` (committed) to `scene`.  l2w: 12 floats, column major
+        (vx, vy, vz, p) unless another RTC_FORMAT_* is given.  Returns (geomID, geometry handle)."""
+        m = np.ascontiguousarray(l2w, dtype=np.float32).ravel()
+        g = self.lib.rtcNewGeometry(device, RTC_GEOMETRY_TYPE_INSTANCE)
+        self.lib.rtcSetGeometryInstancedScene(g, instanced_scene)
+        self.lib.rtcSetGeometryTransform(g, 0, fmt, m.ctypes.data)
+        self.lib.rtcCommitGeometry(g)
+        gid = self.lib.rtcAttachGeometry(scene, g)
+        return gid, g
+
+    def build_instanced(self, device, objects, base_meshes, instances, flags=RTC_SCENE_FLAG_NONE):
+        """objects: list of mesh lists (one instanced scene each); base_meshes: triangle meshes attached to the
+        top-level scene first (geomIDs 0..); instances: list of (object index, l2w).  Returns (top scene,
+        [object scenes], keepalive)."""
+        keep, obj = [], []
+        for meshes in objects:
+            sc, k = self.build_scene(device, meshes, flags)
+            obj.append(sc)
+            keep.append(k)
+        top = self.lib.rtcNewScene(device)
+        if flags:
+            self.lib.rtcSetSceneFlags(top, flags)
+        for v, t in base_meshes:
+            _, g = self.add_mesh(device, top, v, t, keep)
+            self.lib.rtcReleaseGeometry(g)
+        for oi, m in instances:
+            _, g = self.add_instance(device, top, obj[oi], m)
+            self.lib.rtcReleaseGeometry(g)
+        self.lib.rtcCommitScene(top)
+        return top, obj, keep
 
     @staticmethod
     def _ptr(rays):

@@ -421,3 +421,90 @@ RQO_API void rqo_occluded1M(void* h, void* ray, uint32_t M, size_t stride) {
     if (trace_one(sc, &tmp, &th, 1, INVALID_ID)) r->tfar = -INFINITY;
   }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Single-level instancing (RTC_GEOMETRY_TYPE_INSTANCE).  Follows
+ *   kernels/geometry/instance_intersector.cpp:48-105   ray -> instance space, trace the instanced scene, restore
+ *   kernels/common/scene_instance.h:61-66,140-143      bounds = xfmBounds(local2world, scene bounds); world2local = rcp(local2world)
+ *   common/math/affinespace.h:102-118, linearspace3.h:44-50,155-156   xfmPoint / xfmVector / inverse = adjoint / det
+ * The top level is restated as a plain loop over the instances (closest hit does not depend on the visiting order);
+ * hits carry the instanced scene's geomID / primID, Ng in instance space and instID[0] = geomID of the instance.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { void* scene; float l2w[12]; uint32_t geomID; } rqo_instance;       /* l2w column major: vx, vy, vz, p */
+typedef struct { const scene_t* scene; float w2l[12]; uint32_t geomID; box3 wb; } inst_t;
+typedef struct { const scene_t* base; inst_t* inst; int ninst; box3 bounds; } top_t;
+
+static v3 xfm_point(const float* m, v3 p) {
+  return V(madd(p.x, m[0], madd(p.y, m[3], madd(p.z, m[6], m[9]))), madd(p.x, m[1], madd(p.y, m[4], madd(p.z, m[7], m[10]))),
+           madd(p.x, m[2], madd(p.y, m[5], madd(p.z, m[8], m[11]))));
+}
+static v3 xfm_vector(const float* m, v3 v) {
+  return V(madd(v.x, m[0], madd(v.y, m[3], v.z * m[6])), madd(v.x, m[1], madd(v.y, m[4], v.z * m[7])), madd(v.x, m[2], madd(v.y, m[5], v.z * m[8])));
+}
+
+RQO_API void* rqo_build_top(void* base, const rqo_instance* insts, int n) {
+  top_t* t = (top_t*)calloc(1, sizeof(top_t));
+  t->base = (const scene_t*)base; t->ninst = 0; t->inst = (inst_t*)calloc(n > 0 ? n : 1, sizeof(inst_t));
+  t->bounds = box_empty();
+  if (t->base && t->base->root) box_extend(&t->bounds, &t->base->bounds);
+  for (int i = 0; i < n; i++) {
+    const float* m = insts[i].l2w;
+    const scene_t* sc = (const scene_t*)insts[i].scene;
+    inst_t I; I.scene = sc; I.geomID = insts[i].geomID;
+    const v3 vx = V(m[0], m[1], m[2]), vy = V(m[3], m[4], m[5]), vz = V(m[6], m[7], m[8]), p = V(m[9], m[10], m[11]);
+    const v3 c0 = cross3(vy, vz), c1 = cross3(vz, vx), c2 = cross3(vx, vy);          /* rows of the adjoint's transpose */
+    const float det = dot3(vx, c0);
+    const float il[9] = {c0.x / det, c1.x / det, c2.x / det, c0.y / det, c1.y / det, c2.y / det, c0.z / det, c1.z / det, c2.z / det};
+    for (int k = 0; k < 9; k++) I.w2l[k] = il[k];
+    const v3 ip = xfm_vector(il, p);
+    I.w2l[9] = -ip.x; I.w2l[10] = -ip.y; I.w2l[11] = -ip.z;
+    I.wb = box_empty();
+    if (sc && sc->root) {
+      for (int c = 0; c < 8; c++) {
+        const v3 q = xfm_point(m, V((c & 4) ? sc->bounds.hi.x : sc->bounds.lo.x, (c & 2) ? sc->bounds.hi.y : sc->bounds.lo.y, (c & 1) ? sc->bounds.hi.z : sc->bounds.lo.z));
+        box3 b; b.lo = q; b.hi = q; box_extend(&I.wb, &b);
+      }
+      if (vertex_valid(I.wb.lo) && vertex_valid(I.wb.hi)) { box_extend(&t->bounds, &I.wb); t->inst[t->ninst++] = I; }
+    }
+  }
+  return t;
+}
+RQO_API void rqo_free_top(void* h) { top_t* t = (top_t*)h; if (!t) return; free(t->inst); free(t); }
+RQO_API void rqo_top_bounds(void* h, float out[6]) { top_t* t = (top_t*)h; out[0] = t->bounds.lo.x; out[1] = t->bounds.lo.y; out[2] = t->bounds.lo.z; out[3] = t->bounds.hi.x; out[4] = t->bounds.hi.y; out[5] = t->bounds.hi.z; }
+
+static int trace_top(const top_t* t, ray_t* ray, rhit_t* hit, int occluded, uint32_t ctxInst) {
+  int found = 0;
+  if (t->base && t->base->root) { found |= trace_one(t->base, ray, hit, occluded, ctxInst); if (occluded && found) return 1; }
+  for (int i = 0; i < t->ninst; i++) {
+    const inst_t* I = &t->inst[i];
+    ray_t lr = *ray;                                                /* tnear, tfar carry over (instance_intersector.cpp:62-63) */
+    const v3 o = xfm_point(I->w2l, V(ray->org_x, ray->org_y, ray->org_z)), d = xfm_vector(I->w2l, V(ray->dir_x, ray->dir_y, ray->dir_z));
+    lr.org_x = o.x; lr.org_y = o.y; lr.org_z = o.z; lr.dir_x = d.x; lr.dir_y = d.y; lr.dir_z = d.z;
+    if (trace_one(I->scene, &lr, hit, occluded, I->geomID)) {
+      found = 1;
+      if (occluded) return 1;
+      ray->tfar = lr.tfar;
+    }
+  }
+  return found;
+}
+RQO_API void rqo_top_intersect1M(void* h, void* rayhit, uint32_t M, size_t stride, uint32_t instID) {
+  const top_t* t = (const top_t*)h;
+  for (uint32_t i = 0; i < M; i++) {
+    ray_t* r = (ray_t*)((char*)rayhit + (size_t)i * stride);
+    rhit_t* ht = (rhit_t*)((char*)r + 48);
+    if (!(r->tnear <= r->tfar)) continue;
+    ray_t tmp = *r; rhit_t th; memset(&th, 0, sizeof(th));
+    if (trace_top(t, &tmp, &th, 0, instID)) { r->tfar = tmp.tfar; *ht = th; }
+  }
+}
+RQO_API void rqo_top_occluded1M(void* h, void* ray, uint32_t M, size_t stride) {
+  const top_t* t = (const top_t*)h;
+  for (uint32_t i = 0; i < M; i++) {
+    ray_t* r = (ray_t*)((char*)ray + (size_t)i * stride);
+    if (!(r->tnear <= r->tfar) || r->tfar < 0.0f) continue;
+    if (M > 1 && !(r->tnear >= 0.0f)) continue;
+    ray_t tmp = *r; rhit_t th;
+    if (trace_top(t, &tmp, &th, 1, INVALID_ID)) r->tfar = -INFINITY;
+  }
+}

@@ -16,6 +16,10 @@ class _Mesh(C.Structure):
                 ("numTris", C.c_uint), ("numVerts", C.c_uint), ("geomID", C.c_uint)]
 
 
+class _Instance(C.Structure):
+    _fields_ = [("scene", C.c_void_p), ("l2w", C.c_float * 12), ("geomID", C.c_uint)]
+
+
 def build_lib():
     subprocess.check_call(["make", "-s", "-C", HERE, "librq_oracle.so"])
     return LIB
@@ -35,6 +39,12 @@ class Oracle:
         L.rqo_bounds.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.rqo_intersect1M.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t, C.c_uint]
         L.rqo_occluded1M.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t]
+        L.rqo_build_top.restype = C.c_void_p
+        L.rqo_build_top.argtypes = [C.c_void_p, C.POINTER(_Instance), C.c_int]
+        L.rqo_free_top.argtypes = [C.c_void_p]
+        L.rqo_top_bounds.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.rqo_top_intersect1M.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t, C.c_uint]
+        L.rqo_top_occluded1M.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t]
         fp = C.POINTER(C.c_float)
         for n in ("rqo_moeller", "rqo_pluecker"):
             f = getattr(L, n)
@@ -55,6 +65,30 @@ class Oracle:
 
     def free(self, h):
         self.lib.rqo_free(h)
+
+    # ---- single-level instancing: a top-level scene = optional triangle scene + instances of other scenes ----
+    def build_top(self, base, instances):
+        """base: handle from build() or None; instances: list of (scene handle, l2w (12,) column major vx,vy,vz,p, geomID)."""
+        arr = (_Instance * max(len(instances), 1))()
+        for i, (h, m, gid) in enumerate(instances):
+            arr[i].scene = h
+            arr[i].l2w = (C.c_float * 12)(*[float(x) for x in np.asarray(m, dtype=np.float32).ravel()])
+            arr[i].geomID = gid
+        return self.lib.rqo_build_top(base, arr, len(instances))
+
+    def free_top(self, h):
+        self.lib.rqo_free_top(h)
+
+    def top_bounds(self, h):
+        o = (C.c_float * 6)()
+        self.lib.rqo_top_bounds(h, o)
+        return np.array(list(o), dtype=np.float32)
+
+    def top_intersect(self, h, rays, inst_id=0xFFFFFFFF):
+        self.lib.rqo_top_intersect1M(h, rays.ctypes.data, len(rays), rays.strides[0], inst_id)
+
+    def top_occluded(self, h, rays):
+        self.lib.rqo_top_occluded1M(h, rays.ctypes.data, len(rays), rays.strides[0])
 
     def sah(self, h):
         return self.lib.rqo_sah(h)

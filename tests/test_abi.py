@@ -189,8 +189,8 @@ def test_commit_state_machine_without_gpu(product, hostdev):
     assert L.rtcGetSceneFlags(sc) == rt.RTC_SCENE_FLAG_ROBUST
     L.rtcSetSceneBuildQuality(sc, 7)
     assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
-    L.rtcSetGeometryTransform.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_void_p]
-    L.rtcSetGeometryTransform(g, 0, 0, None)                                 # out-of-scope entry point
+    L.rtcSetGeometryTessellationRate.argtypes = [C.c_void_p, C.c_float]
+    L.rtcSetGeometryTessellationRate(g, 4.0)                                 # out-of-scope entry point
     assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
     assert L.rtcGetDeviceProperty(hostdev, 0) == 31201 and L.rtcGetDeviceProperty(hostdev, 96) == 1
     assert L.rtcGetDeviceProperty(hostdev, 66) == 0 and L.rtcGetDeviceProperty(hostdev, 35) == 1
@@ -210,3 +210,41 @@ def test_oracle_is_not_on_the_product_path():
                 assert "rq_oracle" not in txt and "oracle/" not in txt and "libembree3_ref" not in txt, os.path.join(dp, f)
     out = subprocess.check_output(["ldd", os.path.join(pk, "lib", "libembree3.so")]).decode()
     assert "oracle" not in out and "torch" not in out
+
+
+def test_instance_geometry_host_logic(product, hostdev):
+    """rtcSetGeometryTransform / rtcGetGeometryTransform formats (rtcore.cpp:1008-1069) and instance-only calls."""
+    L = product.lib
+    g = L.rtcNewGeometry(hostdev, rt.RTC_GEOMETRY_TYPE_INSTANCE)
+    assert g and err(product, hostdev) == 0
+    col = np.arange(1, 13, dtype=np.float32)                        # vx=(1,2,3) vy=(4,5,6) vz=(7,8,9) p=(10,11,12)
+    L.rtcSetGeometryTransform(g, 0, rt.RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, col.ctypes.data)
+    out = np.zeros(16, dtype=np.float32)
+    L.rtcGetGeometryTransform(g, 0.0, rt.RTC_FORMAT_FLOAT3X4_ROW_MAJOR, out.ctypes.data)
+    assert np.array_equal(out[:12], np.array([1, 4, 7, 10, 2, 5, 8, 11, 3, 6, 9, 12], dtype=np.float32))
+    L.rtcGetGeometryTransform(g, 0.0, rt.RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR, out.ctypes.data)
+    assert np.array_equal(out, np.array([1, 2, 3, 0, 4, 5, 6, 0, 7, 8, 9, 0, 10, 11, 12, 1], dtype=np.float32))
+    row = np.array([1, 4, 7, 10, 2, 5, 8, 11, 3, 6, 9, 12], dtype=np.float32)
+    L.rtcSetGeometryTransform(g, 0, rt.RTC_FORMAT_FLOAT3X4_ROW_MAJOR, row.ctypes.data)
+    L.rtcGetGeometryTransform(g, 0.0, rt.RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, out.ctypes.data)
+    assert np.array_equal(out[:12], col)
+    m44 = np.array([1, 2, 3, 0, 4, 5, 6, 0, 7, 8, 9, 0, 10, 11, 12, 1], dtype=np.float32)
+    L.rtcSetGeometryTransform(g, 0, rt.RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR, m44.ctypes.data)
+    L.rtcGetGeometryTransform(g, 0.0, rt.RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, out.ctypes.data)
+    assert np.array_equal(out[:12], col) and err(product, hostdev) == 0
+    L.rtcSetGeometryTransform(g, 0, 0x9133, col.ctypes.data)                     # FLOAT3X3: invalid matrix format
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    L.rtcSetGeometryTransform(g, 1, rt.RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, col.ctypes.data)   # time step 1: no motion blur
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    t = L.rtcNewGeometry(hostdev, rt.RTC_GEOMETRY_TYPE_TRIANGLE)
+    sc = L.rtcNewScene(hostdev)
+    L.rtcSetGeometryInstancedScene(t, sc)                                         # not an instance geometry
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    L.rtcSetGeometryInstancedScene(g, None)
+    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_ARGUMENT
+    L.rtcSetGeometryInstancedScene(g, sc)
+    L.rtcSetGeometryInstancedScene(g, sc)                                         # replacing keeps the reference counts balanced
+    assert err(product, hostdev) == 0
+    L.rtcReleaseScene(sc)                                                         # the geometry still holds the instanced scene
+    L.rtcReleaseGeometry(g)
+    L.rtcReleaseGeometry(t)

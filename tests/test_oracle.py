@@ -133,3 +133,27 @@ def test_oracle_matches_live_reference(oracle, reflib, scale, seed):
     oracle.free(h)
     reflib.lib.rtcReleaseScene(sc)
     reflib.lib.rtcReleaseDevice(dev)
+
+
+@pytest.mark.parametrize("name", ["inst_forest", "inst_forest_robust", "inst_only"])
+def test_instancing_restatement_matches_reference_golden(oracle, name):
+    """Single-level instancing (instance_intersector.cpp:48-105): the restatement against vectors of the real library."""
+    import instancing
+    c = instancing.CASES[name]()
+    g = instancing.load_golden(name)
+    assert np.array_equal(c["rays"].view(np.uint8), g["rays"].view(np.uint8))
+    top, handles = instancing.build_oracle(oracle, c)
+    assert np.allclose(oracle.top_bounds(top), g["bounds"], rtol=1e-6, atol=1e-6)
+    r = g["rays"].copy()
+    oracle.top_intersect(top, r)
+    res = parity.compare_closest(r, g["closest"])
+    assert res["pass"] and res["hits_ours"] > 1000, res
+    hit = r["geomID"] != 0xFFFFFFFF
+    if c["base"]:
+        assert (r["instID"][hit] == 0xFFFFFFFF).any() and (r["instID"][hit] != 0xFFFFFFFF).any()
+    s = g["shadow_in"].copy()
+    oracle.top_occluded(top, s)
+    assert parity.compare_occluded(s, g["shadow_out"])["pass"]
+    oracle.free_top(top)
+    for h in handles:
+        oracle.free(h)

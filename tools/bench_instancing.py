@@ -1,0 +1,116 @@
+"""Instanced-scene throughput: G x G instances of the configs[0] sphere (32 760 triangles each)
+over a displaced ground plane, incoherent diffuse-style rays; ours on the GPU (device-resident stream, CUDA
+events) and the reference library on the host cores for a bounded sample.
+usage: python tools/bench_instancing.py [--grid 64] [--rays 4194304] [--no-reference]"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+pkg = importlib.import_module("embree-aarch64_b200")
+rt, fx = pkg.rtcore, pkg.fixtures
+import instancing  # noqa: E402
+
+
+def scene(grid):
+    obj = [fx.triangle_sphere((0.0, 0.0, 0.0), 0.45, 91)]
+    ext = 0.75 * grid
+    base = [fx.displaced_plane(256, extent=ext)]
+    inst = []
+    h = grid // 2
+    for x in range(-h, grid - h):
+        for z in range(-h, grid - h):
+            inst.append((0, instancing._xfm(0.37 * x + 0.11 * z, 0.05 * z, [1.0, 0.8 + 0.01 * ((x + z) % 7), 1.0],
+                                            [1.5 * x + 0.7, 1.0 + 0.1 * ((x * z) % 3), 1.5 * z + 0.7])))
+    return [obj], base, inst, ext
+
+
+def rays_for(n, ext, seed=3):
+    rs = fx.RandomSampler(np.arange(n), seed)
+    o = np.stack([(rs.get_float() * 2 - 1) * ext * 0.9, 1.5 + 3.0 * rs.get_float(), (rs.get_float() * 2 - 1) * ext * 0.9], 1).astype(np.float32)
+    d = np.stack([rs.get_float() * 2 - 1, -(0.15 + rs.get_float()), rs.get_float() * 2 - 1], 1).astype(np.float32)
+    r = rt.new_rays(n)
+    return fx._set(r, o, d, 1e-3, np.inf)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", type=int, default=64)
+    ap.add_argument("--rays", type=int, default=1 << 22)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--no-reference", action="store_true")
+    a = ap.parse_args()
+    import torch
+    objects, base, inst, ext = scene(a.grid)
+    rays = rays_for(a.rays, ext)
+    lib = rt.RTCore()
+    dev = lib.new_device("")
+    t0 = time.perf_counter()
+    top, objs, keep = lib.build_instanced(dev, objects, base, inst, 0)
+    build_ms = (time.perf_counter() - t0) * 1e3
+    assert lib.lib.rtcGetDeviceError(dev) == 0
+    st = lib.build_stats(top)
+    pristine = torch.from_numpy(rays.view(np.uint8).reshape(len(rays), 80).copy()).cuda()
+    work = pristine.clone()
+    s = torch.cuda.Stream()
+    lib.lib.rtcxSetDeviceStream(dev, C.c_void_p(s.cuda_stream))
+    times = []
+    with torch.cuda.stream(s):
+        for r in range(a.reps + 2):
+            work.copy_(pristine)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            lib.intersect_ptr(top, work.data_ptr(), len(rays))
+            e1.record(s)
+            s.synchronize()
+            if r >= 2:
+                times.append(e0.elapsed_time(e1))
+    out = work.cpu().numpy().reshape(-1).view(rt.RAYHIT_DTYPE)
+    hit = out["geomID"] != 0xFFFFFFFF
+    ms = float(np.median(times))
+    res = {"workload": f"{len(inst)} instances of a 32760-triangle sphere ({len(inst) * 32760 / 1e6:.1f} M instanced triangles) + {fx.num_tris(base)}-triangle ground, "
+                       f"{len(rays)} incoherent rays, device-resident stream",
+           "ours_mrays_per_s": len(rays) / ms / 1e3, "ours_ms": ms, "hit_fraction": float(hit.mean()),
+           "instance_hit_fraction": float((out["instID"][hit] != 0xFFFFFFFF).mean()), "top_level_prims": st["numPrimsValid"],
+           "top_level_nodes": st["numNodes"], "setup_wall_ms_incl_object_build": build_ms}
+    if not a.no_reference:
+        from oracle.rq_oracle import REF_LIB
+        if os.path.exists(REF_LIB):
+            ref = rt.RTCore(REF_LIB)
+            rdev = ref.new_device("")
+            rtop, robjs, rkeep = ref.build_instanced(rdev, objects, base, inst, 0)
+            n = min(len(rays), 1 << 20)
+            sample = rays[:n].copy()
+            nthreads = os.cpu_count() or 1
+            chunks = np.array_split(np.arange(n), nthreads)
+
+            def work_fn(idx):
+                part = sample[idx[0]:idx[-1] + 1]
+                for c0 in range(0, len(part), 4096):
+                    ref.intersect(rtop, part[c0:c0 + 4096])
+            best = 1e9
+            for rep in range(3):
+                sample[:] = rays[:n]
+                th = [threading.Thread(target=work_fn, args=(c,)) for c in chunks if len(c)]
+                t0 = time.perf_counter()
+                [t.start() for t in th]
+                [t.join() for t in th]
+                best = min(best, time.perf_counter() - t0)
+            parity = importlib.import_module("embree-aarch64_b200.parity")
+            cmp_ = parity.compare_closest(out[:n], sample)
+            res.update({"reference_mrays_per_s": n / best / 1e6, "reference_threads": nthreads, "reference_sample_rays": n,
+                        "parity_vs_reference": {k: cmp_[k] for k in ("pass", "agreement", "hitmiss_disagree", "id_disagree_unexplained", "max_t_rel", "max_uv_abs")}})
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
