@@ -313,18 +313,29 @@ void commitScene(Scene* sc) {
         RQInstance I; memset(&I, 0, sizeof(I));
         RQGeomDesc d; memset(&d, 0, sizeof(d));
         const float* m = g->l2w;
-        // world2local = rcp(local2world): adjoint / det and -(l^-1 * p) (linearspace3.h:44-50, affinespace.h rcp), in double
+        // world2local = rcp(local2world) = (adjoint / det, -(l^-1 * p)) (linearspace3.h:44-50, affinespace.h rcp), evaluated
+        // like the reference's lowest-ISA object does (scene_instance.cpp:131 is built for SSE2: every product and sum rounds
+        // separately, dot = (x + y) + z, adjoint * rcp(det)).  Answers inside an instance move by |translation| * few ulp when
+        // this is evaluated differently, so the same order is kept here.
         {
-          const double vx[3] = {m[0], m[1], m[2]}, vy[3] = {m[3], m[4], m[5]}, vz[3] = {m[6], m[7], m[8]}, p[3] = {m[9], m[10], m[11]};
-          const double c0[3] = {vy[1] * vz[2] - vy[2] * vz[1], vy[2] * vz[0] - vy[0] * vz[2], vy[0] * vz[1] - vy[1] * vz[0]};   // cross(vy, vz)
-          const double c1[3] = {vz[1] * vx[2] - vz[2] * vx[1], vz[2] * vx[0] - vz[0] * vx[2], vz[0] * vx[1] - vz[1] * vx[0]};   // cross(vz, vx)
-          const double c2[3] = {vx[1] * vy[2] - vx[2] * vy[1], vx[2] * vy[0] - vx[0] * vy[2], vx[0] * vy[1] - vx[1] * vy[0]};   // cross(vx, vy)
-          const double det = vx[0] * c0[0] + vx[1] * c0[1] + vx[2] * c0[2];
-          // inverse = transposed(rows c0, c1, c2) / det  =>  column k of the inverse = (c0[k], c1[k], c2[k]) / det
-          double il[9];
-          for (int k = 0; k < 3; k++) { il[3 * k + 0] = c0[k] / det; il[3 * k + 1] = c1[k] / det; il[3 * k + 2] = c2[k] / det; }
-          for (int k = 0; k < 9; k++) I.w2l[k] = (float)il[k];
-          for (int r = 0; r < 3; r++) I.w2l[9 + r] = (float)(-(il[r] * p[0] + il[3 + r] * p[1] + il[6 + r] * p[2]));
+          volatile float t0, t1;                                // volatile: no FMA contraction whatever the host flags
+          auto mulsub = [&](float a, float b, float c, float d) { t0 = a * b; t1 = c * d; return (float)(t0 - t1); };
+          const float vx[3] = {m[0], m[1], m[2]}, vy[3] = {m[3], m[4], m[5]}, vz[3] = {m[6], m[7], m[8]}, p[3] = {m[9], m[10], m[11]};
+          const float c0[3] = {mulsub(vy[1], vz[2], vy[2], vz[1]), mulsub(vy[2], vz[0], vy[0], vz[2]), mulsub(vy[0], vz[1], vy[1], vz[0])};   // cross(vy, vz)
+          const float c1[3] = {mulsub(vz[1], vx[2], vz[2], vx[1]), mulsub(vz[2], vx[0], vz[0], vx[2]), mulsub(vz[0], vx[1], vz[1], vx[0])};   // cross(vz, vx)
+          const float c2[3] = {mulsub(vx[1], vy[2], vx[2], vy[1]), mulsub(vx[2], vy[0], vx[0], vy[2]), mulsub(vx[0], vy[1], vx[1], vy[0])};   // cross(vx, vy)
+          volatile float d0 = vx[0] * c0[0], d1 = vx[1] * c0[1], d2 = vx[2] * c0[2];
+          volatile float ds = d0 + d1;
+          const float det = ds + d2;
+          const float rd = 1.0f / det;
+          volatile float il[9];                                 // column k of the inverse = (c0[k], c1[k], c2[k]) * rcp(det)
+          for (int k = 0; k < 3; k++) { il[3 * k + 0] = c0[k] * rd; il[3 * k + 1] = c1[k] * rd; il[3 * k + 2] = c2[k] * rd; }
+          for (int k = 0; k < 9; k++) I.w2l[k] = il[k];
+          for (int r = 0; r < 3; r++) {
+            volatile float a = p[2] * il[6 + r], b2 = p[1] * il[3 + r], c = p[0] * il[r];
+            volatile float s1 = a + b2;
+            I.w2l[9 + r] = -(s1 + c);
+          }
         }
         const RQImageHeader& IH = in->image.header;
         I.nodes = (uint64_t)((char*)in->image.base + IH.nodesOffset);

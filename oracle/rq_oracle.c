@@ -442,6 +442,13 @@ static v3 xfm_vector(const float* m, v3 v) {
   return V(madd(v.x, m[0], madd(v.y, m[3], v.z * m[6])), madd(v.x, m[1], madd(v.y, m[4], v.z * m[7])), madd(v.x, m[2], madd(v.y, m[5], v.z * m[8])));
 }
 
+/* sensitivity probe (tests only): 0 = the reference's float inverse as its SSE2 object evaluates it (default), 1 = inverse evaluated in
+ * double and rounded once, 2 = float with fused multiply-adds.  Answers on instanced geometry differ between them by about
+ * |translation| * few ulp in instance space (u/v of small triangles move by up to 1e-4); the reference's own rcp(det) is an
+ * approximation + one Newton step (common/math/math.h:58-75), which no portable code reproduces bit for bit. */
+static int g_w2l_mode = 0;
+RQO_API void rqo_set_w2l_mode(int m) { g_w2l_mode = m; }
+
 RQO_API void* rqo_build_top(void* base, const rqo_instance* insts, int n) {
   top_t* t = (top_t*)calloc(1, sizeof(top_t));
   t->base = (const scene_t*)base; t->ninst = 0; t->inst = (inst_t*)calloc(n > 0 ? n : 1, sizeof(inst_t));
@@ -458,6 +465,29 @@ RQO_API void* rqo_build_top(void* base, const rqo_instance* insts, int n) {
     for (int k = 0; k < 9; k++) I.w2l[k] = il[k];
     const v3 ip = xfm_vector(il, p);
     I.w2l[9] = -ip.x; I.w2l[10] = -ip.y; I.w2l[11] = -ip.z;
+    if (g_w2l_mode == 0) {
+      /* the reference evaluates rcp(local2world) in its lowest-ISA object (scene_instance.cpp:131 built for SSE2): products and sums
+       * round separately (no FMA), dot = (x + y) + z, adjoint * rcp(det) */
+      const float m0x = vy.y * vz.z - vy.z * vz.y, m0y = vy.z * vz.x - vy.x * vz.z, m0z = vy.x * vz.y - vy.y * vz.x;
+      const float m1x = vz.y * vx.z - vz.z * vx.y, m1y = vz.z * vx.x - vz.x * vx.z, m1z = vz.x * vx.y - vz.y * vx.x;
+      const float m2x = vx.y * vy.z - vx.z * vy.y, m2y = vx.z * vy.x - vx.x * vy.z, m2z = vx.x * vy.y - vx.y * vy.x;
+      const float dt = (vx.x * m0x + vx.y * m0y) + vx.z * m0z;
+      const float rd = 1.0f / dt;
+      const float jl[9] = {m0x * rd, m1x * rd, m2x * rd, m0y * rd, m1y * rd, m2y * rd, m0z * rd, m1z * rd, m2z * rd};
+      for (int k = 0; k < 9; k++) I.w2l[k] = jl[k];
+      for (int r = 0; r < 3; r++) I.w2l[9 + r] = -((p.z * jl[6 + r] + p.y * jl[3 + r]) + p.x * jl[r]);
+    }
+    if (g_w2l_mode == 1) {
+      const double dvx[3] = {m[0], m[1], m[2]}, dvy[3] = {m[3], m[4], m[5]}, dvz[3] = {m[6], m[7], m[8]}, dp[3] = {m[9], m[10], m[11]};
+      const double d0[3] = {dvy[1] * dvz[2] - dvy[2] * dvz[1], dvy[2] * dvz[0] - dvy[0] * dvz[2], dvy[0] * dvz[1] - dvy[1] * dvz[0]};
+      const double d1[3] = {dvz[1] * dvx[2] - dvz[2] * dvx[1], dvz[2] * dvx[0] - dvz[0] * dvx[2], dvz[0] * dvx[1] - dvz[1] * dvx[0]};
+      const double d2[3] = {dvx[1] * dvy[2] - dvx[2] * dvy[1], dvx[2] * dvy[0] - dvx[0] * dvy[2], dvx[0] * dvy[1] - dvx[1] * dvy[0]};
+      const double dd = dvx[0] * d0[0] + dvx[1] * d0[1] + dvx[2] * d0[2];
+      double dl[9];
+      for (int k = 0; k < 3; k++) { dl[3 * k + 0] = d0[k] / dd; dl[3 * k + 1] = d1[k] / dd; dl[3 * k + 2] = d2[k] / dd; }
+      for (int k = 0; k < 9; k++) I.w2l[k] = (float)dl[k];
+      for (int r = 0; r < 3; r++) I.w2l[9 + r] = (float)(-(dl[r] * dp[0] + dl[3 + r] * dp[1] + dl[6 + r] * dp[2]));
+    }
     I.wb = box_empty();
     if (sc && sc->root) {
       for (int c = 0; c < 8; c++) {

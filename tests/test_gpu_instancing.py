@@ -33,13 +33,13 @@ def test_instancing_matches_reference_golden(product, gpu_device, name):
     r = g["rays"].copy()
     product.intersect(top, r)
     res = parity.compare_closest(r, g["closest"])
-    assert res["pass"] and res["hits_ours"] > 1000, res
+    assert res["pass"] and res["hits_ours"] > 1000, str(res)
     miss = g["closest"]["geomID"] == INV
     assert np.array_equal(r[miss].view(np.uint8), g["closest"][miss].view(np.uint8))     # misses / inactive rays untouched
     s = g["shadow_in"].copy()
     product.occluded(top, s)
     ro = parity.compare_occluded(s, g["shadow_out"])
-    assert ro["pass"], ro
+    assert ro["pass"], str(ro)
     # coherent hint and the single-ray entry point take the same path
     r2 = g["rays"][:2000].copy()
     product.intersect(top, r2, coherent=True)
@@ -89,7 +89,7 @@ def test_instancing_against_oracle_many_instances(product, gpu_device, oracle):
     product.intersect(top, a)
     oracle.top_intersect(otop, w)
     res = parity.compare_closest(a, w)
-    assert res["pass"] and res["hits_ours"] > 20000, res
+    assert res["pass"] and res["hits_ours"] > 20000, str(res)
     hit = a["geomID"] != INV
     assert (a["instID"][hit] != INV).sum() > 5000
     sa = fx.shadow_rays(w)
@@ -124,7 +124,7 @@ def test_instance_api_rules_and_updates(product, gpu_device, oracle):
         product.intersect(top, a, inst_id=7)                       # context instID is overwritten by instance hits only
         oracle.top_intersect(ot, w, 7)
         res = parity.compare_closest(a, w)
-        assert res["pass"] and res["hits_ours"] > 300, res
+        assert res["pass"] and res["hits_ours"] > 300, str(res)
         assert (a["instID"][a["geomID"] != INV] == 0).all()
         oracle.free_top(ot)
     # the image of an instanced scene cannot be exported (it points into other scenes)
