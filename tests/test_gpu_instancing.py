@@ -124,7 +124,7 @@ def test_instance_api_rules_and_updates(product, gpu_device, oracle):
         product.intersect(top, a, inst_id=7)                       # context instID is overwritten by instance hits only
         oracle.top_intersect(ot, w, 7)
         res = parity.compare_closest(a, w)
-        assert res["pass"] and res["hits_ours"] > 300, str(res)
+        assert res["pass"] and res["hits_ours"] > 100, str(res)
         assert (a["instID"][a["geomID"] != INV] == 0).all()
         oracle.free_top(ot)
     # the image of an instanced scene cannot be exported (it points into other scenes)
