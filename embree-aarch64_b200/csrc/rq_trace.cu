@@ -41,6 +41,8 @@ struct TraceParams {
   unsigned int* workCounter; // global ray cursor, zero at launch
   RQTraceCounters* counters;
   const RQInstance* instances; // INST kernels only: table indexed by the instance records of the top-level BVH
+  char* hitList;               // LIST kernels only: compact output, one record per ray that hit (48 B closest, 4 B occluded) ...
+  unsigned int* hitCount;      // ... appended through this counter (zero at launch); nothing is written to `out`
 };
 
 __device__ __forceinline__ float rcpSafe(float d) {           // common/math/vec3fa.h:172-177
@@ -89,7 +91,12 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
 // instanced scene's BVH through per-lane node / triangle base pointers and, once its part of the
 // stack is empty again, restores the world-space ray.  Hits report the instanced scene's
 // geomID / primID, Ng in instance space and instID[0] = geomID of the instance.
-template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int SPILL, bool INST = false>
+//
+// LIST = compact output for host-staged streams: instead of scattering hit fields into the ray
+// records, a ray that hit appends one record {rid, tfar, -, - | Ng.xyz, u | v, primID, geomID, instID}
+// (closest) or its index (occluded) to a list; the host downloads only that list and scatters it
+// into the caller's buffer, so the PCIe link carries ~13 instead of 80 bytes per ray outbound.
+template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int SPILL, bool INST = false, bool LIST = false>
 #ifndef RQ_MIN_CTAS
 #define RQ_MIN_CTAS 8   /* 64 registers: 8 CTAs = 32 warps per SM; (128,1) let ptxas take 95 registers and cost 20 % (profiles/r01k_ab.log) */
 #endif
@@ -297,6 +304,23 @@ k_trace(const TraceParams P) {
           if (sp > (int)sdepth + SPILL) sp = (int)sdepth + SPILL;  // entries beyond the stack were dropped (cannot happen: capacity >= depth)
           if (sp == 0) {
             active = false;
+            if (found && LIST) {
+              // warp-aggregated append: the lanes that finish a hit ray in this very iteration share one atomic
+              const unsigned fm = __activemask();
+              const int fl = __ffs(fm) - 1;
+              unsigned fbase = 0;
+              if ((int)lane == fl) fbase = atomicAdd(P.hitCount, (unsigned)__popc(fm));
+              fbase = __shfl_sync(fm, fbase, fl);
+              const unsigned fslot = fbase + (unsigned)__popc(fm & ((1u << lane) - 1u));
+              if (OCCLUDED) {
+                ((uint32_t*)P.hitList)[fslot] = rid;
+              } else {
+                float4* d = (float4*)(P.hitList + (size_t)fslot * 48);
+                d[0] = make_float4(__uint_as_float(rid), tfar, 0.f, 0.f);
+                d[1] = make_float4(hNg.x, hNg.y, hNg.z, hu);
+                d[2] = make_float4(hv, __uint_as_float(hPrim), __uint_as_float(hGeom), __uint_as_float(INST ? hInst : P.instID0));
+              }
+            } else
             if (found) {
               char* rp = P.out + (size_t)rid * P.stride;
               if (COUNT) { cntHits++; cntHitNodes += rayNodes; }
@@ -447,6 +471,16 @@ template <bool OCC, bool ROBUST, bool COUNT, bool ALIGNED>
 cudaError_t launchStack(TraceParams& P, uint32_t depth, cudaStream_t s) {
   if (P.sdepth > depth) P.sdepth = depth;
   const uint32_t spill = depth - P.sdepth;
+  if (P.hitList) {
+    // compact-output variants (host-staged streams of flat scenes): shared levels + at most 32 local entries, no counters
+    if (spill > 32 || P.instances) return cudaErrorInvalidValue;
+    if (spill == 0) {
+      if (P.split) return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, true, 0, false, true>, P, s);
+      return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, false, 0, false, true>, P, s);
+    }
+    if (P.split) return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, true, 32, false, true>, P, s);
+    return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, false, 32, false, true>, P, s);
+  }
   if (P.instances) {
     // instanced scenes: one stack configuration (shared levels + 32 local entries), no counters
     if (spill > 32) return cudaErrorInvalidValue;
@@ -480,6 +514,12 @@ static int launchTrace(bool occ, const RQTraceArgs* a, cudaStream_t s) {
   P.refillBelow = a->refillBelow ? a->refillBelow : 26u;
   P.split = a->split; P.tVote = a->tVote; P.sdepth = a->stackSmem;
   P.instances = (const RQInstance*)a->instances;
+  P.hitList = (char*)a->hitList; P.hitCount = a->hitCount;
+  if (P.hitList) {
+    if (!P.hitCount) return (int)cudaErrorInvalidValue;
+    cudaError_t ec = cudaMemsetAsync(P.hitCount, 0, sizeof(unsigned int), s);
+    if (ec != cudaSuccess) return (int)ec;
+  }
   if (!P.workCounter) return (int)cudaErrorInvalidValue;
   {
     cudaError_t ez = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), s);   // stream ordered with the launch

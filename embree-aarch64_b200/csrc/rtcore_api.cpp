@@ -13,6 +13,9 @@
 
 #include <cuda_runtime.h>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -70,6 +73,13 @@ struct Device : RefCounted {
   cudaStream_t ringStream[kRing] = {nullptr, nullptr, nullptr, nullptr};
   void* ringBuf[kRing] = {nullptr, nullptr, nullptr, nullptr};
   size_t ringCap[kRing] = {0, 0, 0, 0};
+  // compact hit download (d2h=3): per ring slot a device hit list + counter and their page-locked host mirrors
+  void* listDev[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  void* listHost[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  size_t listCap[kRing] = {0, 0, 0, 0};
+  unsigned int* countHost = nullptr;      // kRing page-locked words
+  unsigned int* countDev = nullptr;       // kRing device words, 32 bytes apart
+  cudaEvent_t evCount[kRing] = {nullptr, nullptr, nullptr, nullptr}, evList[kRing] = {nullptr, nullptr, nullptr, nullptr};
   RQTraceCounters* dCounters = nullptr;
   unsigned int* dWork = nullptr;          // ray cursors of the persistent kernels: one per ring stream + one for the device stream
   std::mutex launchMutex;                 // (cursor reset + launch) pairs on the device stream are enqueued atomically
@@ -85,6 +95,12 @@ struct Device : RefCounted {
   // Same-box A/B on B200 / PCIe Gen5 (profiles/r01g_ab.log): 0 -> 664 Mrays/s, 1 -> 606, 2 -> 603: SM-issued PCIe
   // transactions are 32-64 bytes and lose to the copy engines' large TLPs, so staging stays the default.
   int zeroCopy = 0;
+  // hit download of staged host streams: 0 = the whole span back (one linear copy), 1 = only bytes [32, record size) of every
+  // record (tfar .. hit; a strided 2-D copy, the ray part never changes), 2 = as 1 but tfar alone for occlusion streams,
+  // 3 = compact: the kernel appends one record per hit ray to a list, only the list is downloaded and a host thread scatters
+  // it into the caller's buffer.  Same-box A/B (profiles/r01o_ab_d2h_rows.log): 0 -> 662 Mrays/s end to end, 1 -> 463, 2 -> 446
+  // (the copy engines handle 48-byte rows badly)
+  int d2hMode = 0;
   int refitEnabled = 1;                   // refit=0: RTC_BUILD_QUALITY_REFIT geometries are rebuilt like any other
 
   cudaStream_t stream() const { return userStream ? userStream : ownStream; }
@@ -94,6 +110,14 @@ struct Device : RefCounted {
     if (hasGpu) {
       cudaSetDevice(ordinal);
       for (int i = 0; i < kRing; i++) { if (ringBuf[i]) cudaFree(ringBuf[i]); if (ringStream[i]) cudaStreamDestroy(ringStream[i]); }
+      for (int i = 0; i < kRing; i++) {
+        if (listDev[i]) cudaFree(listDev[i]);
+        if (listHost[i]) cudaFreeHost(listHost[i]);
+        if (evCount[i]) cudaEventDestroy(evCount[i]);
+        if (evList[i]) cudaEventDestroy(evList[i]);
+      }
+      if (countHost) cudaFreeHost(countHost);
+      if (countDev) cudaFree(countDev);
       if (dCounters) cudaFree(dCounters);
       if (dWork) cudaFree(dWork);
       if (ownStream) cudaStreamDestroy(ownStream);
@@ -152,6 +176,7 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "stack_smem") d->stackSmem = std::max(0, std::min(16, atoi(v.c_str())));
     else if (k == "zerocopy") d->zeroCopy = atoi(v.c_str());
     else if (k == "refit") d->refitEnabled = atoi(v.c_str());
+    else if (k == "d2h") d->d2hMode = atoi(v.c_str());
     else if (k == "tvote") d->tVote = std::max(0, std::min(32, atoi(v.c_str())));
     else if (k == "split_occluded") d->splitOccluded = atoi(v.c_str());
     else if (k == "refill") d->refillClosest = std::max(1, std::min(32, atoi(v.c_str())));
@@ -441,6 +466,115 @@ void fillArgs(Scene* sc, RTCIntersectContext* ctx, RQTraceArgs& a, bool stream) 
   a.streamSemantics = stream ? 1u : 0u;
 }
 
+// Host-staged stream with compact hit download (device option d2h=3).  PCIe carries the rays in (copy engine, one linear
+// H2D per 1 M-ray chunk) and, outbound, only one 48-byte (closest) / 4-byte (occluded) record per ray that hit; a helper
+// thread scatters each downloaded list into the caller's records while later chunks are in flight.  With both directions
+// copying whole spans the link delivers 47-49 GB/s per direction, one direction alone 55-57 GB/s (tools/pcie_probe.py).
+void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size_t stride, bool occluded, size_t recBytes) {
+  std::lock_guard<std::mutex> l(dev->stageMutex);
+  const size_t chunk = dev->chunkRays;
+  const size_t recList = occluded ? 4 : 48;
+  if (!dev->countHost) cudaCheck(cudaMallocHost((void**)&dev->countHost, sizeof(unsigned) * Device::kRing), "hit counters");
+  if (!dev->countDev) cudaCheck(cudaMalloc((void**)&dev->countDev, 32 * Device::kRing), "hit counters");
+  for (int r = 0; r < Device::kRing; r++) {
+    if (!dev->ringStream[r]) cudaCheck(cudaStreamCreateWithFlags(&dev->ringStream[r], cudaStreamNonBlocking), "stream");
+    if (!dev->evCount[r]) cudaCheck(cudaEventCreateWithFlags(&dev->evCount[r], cudaEventDisableTiming), "event");
+    if (!dev->evList[r]) cudaCheck(cudaEventCreateWithFlags(&dev->evList[r], cudaEventDisableTiming), "event");
+  }
+  struct Job { int slot; char* h; unsigned n; unsigned count; };
+  std::mutex qm; std::condition_variable qcv;
+  std::deque<Job> jobs;
+  bool finished = false, slotBusy[Device::kRing] = {false, false, false, false};
+  int workerError = 0;
+  std::thread worker([&] {
+    cudaSetDevice(dev->ordinal);
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(qm);
+        qcv.wait(lk, [&] { return !jobs.empty() || finished; });
+        if (jobs.empty()) return;
+        j = jobs.front(); jobs.pop_front();
+      }
+      const cudaError_t e = cudaEventSynchronize(dev->evList[j.slot]);
+      if (e != cudaSuccess) { workerError = (int)e; cudaGetLastError(); }
+      else if (occluded) {
+        const uint32_t* ids = (const uint32_t*)dev->listHost[j.slot];
+        for (unsigned k = 0; k < j.count; k++)
+          if (ids[k] < j.n) *(float*)(j.h + (size_t)ids[k] * stride + 32) = -INFINITY;
+      } else {
+        const char* recs = (const char*)dev->listHost[j.slot];
+        for (unsigned k = 0; k < j.count; k++) {
+          const char* rec = recs + (size_t)k * 48;
+          uint32_t rid; memcpy(&rid, rec, 4);
+          if (rid >= j.n) continue;
+          char* dst = j.h + (size_t)rid * stride;
+          memcpy(dst + 32, rec + 4, 4);                         // tfar
+          memcpy(dst + 48, rec + 16, 32);                       // Ng, u, v, primID, geomID, instID[0]
+        }
+      }
+      { std::lock_guard<std::mutex> lk(qm); slotBusy[j.slot] = false; }
+      qcv.notify_all();
+    }
+  });
+  auto stop = [&] { { std::lock_guard<std::mutex> lk(qm); finished = true; } qcv.notify_all(); if (worker.joinable()) worker.join(); };
+  try {
+    Job prev{-1, nullptr, 0, 0};
+    auto stage2 = [&](Job j) {                                  // the kernel of chunk j is done: fetch its list
+      cudaCheck(cudaEventSynchronize(dev->evCount[j.slot]), "trace");
+      j.count = std::min(dev->countHost[j.slot], j.n);
+      cudaStream_t s = dev->ringStream[j.slot];
+      if (j.count) cudaCheck(cudaMemcpyAsync(dev->listHost[j.slot], dev->listDev[j.slot], (size_t)j.count * recList, cudaMemcpyDeviceToHost, s), "hit download");
+      cudaCheck(cudaEventRecord(dev->evList[j.slot], s), "hit download");
+      { std::lock_guard<std::mutex> lk(qm); jobs.push_back(j); }
+      qcv.notify_all();
+    };
+    unsigned done = 0; int slot = 0;
+    while (done < M) {
+      const unsigned n = (unsigned)std::min<size_t>(chunk, M - done);
+      const size_t span = (size_t)(n - 1) * stride + recBytes;
+      const int r = slot % Device::kRing; slot++;
+      { std::unique_lock<std::mutex> lk(qm); qcv.wait(lk, [&] { return !slotBusy[r]; }); slotBusy[r] = true; }
+      cudaStream_t s = dev->ringStream[r];
+      if (dev->ringCap[r] < span) {
+        cudaCheck(cudaStreamSynchronize(s), "staging");
+        if (dev->ringBuf[r]) cudaFree(dev->ringBuf[r]);
+        dev->ringBuf[r] = nullptr; dev->ringCap[r] = 0;
+        cudaCheck(cudaMalloc(&dev->ringBuf[r], span + 256), "staging alloc");
+        dev->ringCap[r] = span;
+      }
+      if (dev->listCap[r] < (size_t)n * 48) {
+        cudaCheck(cudaStreamSynchronize(s), "staging");
+        if (dev->listDev[r]) cudaFree(dev->listDev[r]);
+        if (dev->listHost[r]) cudaFreeHost(dev->listHost[r]);
+        dev->listDev[r] = nullptr; dev->listHost[r] = nullptr; dev->listCap[r] = 0;
+        cudaCheck(cudaMalloc(&dev->listDev[r], (size_t)n * 48), "hit list alloc");
+        cudaCheck(cudaMallocHost(&dev->listHost[r], (size_t)n * 48), "hit list alloc");
+        dev->listCap[r] = (size_t)n * 48;
+      }
+      char* h = rays + (size_t)done * stride;
+      cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], h, span, cudaMemcpyHostToDevice, s), "ray upload");
+      a.rays = dev->ringBuf[r]; a.out = nullptr; a.numRays = n; a.stride = stride;
+      a.workCounter = dev->dWork + 8 * r;
+      a.hitList = dev->listDev[r]; a.hitCount = dev->countDev + 8 * r;
+      cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
+      cudaCheck(cudaMemcpyAsync(&dev->countHost[r], a.hitCount, sizeof(unsigned), cudaMemcpyDeviceToHost, s), "hit count");
+      cudaCheck(cudaEventRecord(dev->evCount[r], s), "hit count");
+      if (prev.slot >= 0) stage2(prev);
+      prev = Job{r, h, n, 0};
+      done += n;
+    }
+    if (prev.slot >= 0) stage2(prev);
+  } catch (...) {
+    stop();
+    for (int r = 0; r < Device::kRing; r++) if (dev->ringStream[r]) cudaStreamSynchronize(dev->ringStream[r]);
+    cudaGetLastError();
+    throw;
+  }
+  stop();
+  if (workerError) cudaCheck(workerError, "hit download");
+}
+
 // Trace M records of `stride` bytes at `rays`; occluded selects the any-hit kernel; recBytes is
 // 80 (RTCRayHit) or 48 (RTCRay).  Device-resident memory is traced in place; host memory is staged
 // through a ring of device buffers so copies of one chunk overlap the kernel of another.
@@ -481,6 +615,9 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
     }
     if (!dev->async || countersOut || mapped) cudaCheck(cudaStreamSynchronize(s), "trace");
+  } else if (dev->d2hMode == 3 && !mapped && !countersOut && !sc->numInstances && M >= 65536 && stride >= recBytes &&
+             a.depth <= 32 + (unsigned)dev->stackSmem) {
+    traceStreamCompact(dev, a, (char*)rays, M, stride, occluded, recBytes);
   } else {
     std::lock_guard<std::mutex> l(dev->stageMutex);     // host-staged calls of one device are serialised
     const size_t chunk = dev->chunkRays;
@@ -506,7 +643,14 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
       a.out = mapped ? (char*)mapped + (size_t)done * stride : nullptr;
       a.workCounter = dev->dWork + 8 * r;
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
-      if (!mapped) cudaCheck(cudaMemcpyAsync(h, dev->ringBuf[r], span, cudaMemcpyDeviceToHost, s), "hit download");
+      if (!mapped) {
+        if (dev->d2hMode && n > 1 && stride >= recBytes) {
+          const size_t width = (occluded && dev->d2hMode == 2) ? 4 : recBytes - 32;
+          cudaCheck(cudaMemcpy2DAsync(h + 32, stride, (char*)dev->ringBuf[r] + 32, stride, width, n, cudaMemcpyDeviceToHost, s), "hit download");
+        } else {
+          cudaCheck(cudaMemcpyAsync(h, dev->ringBuf[r], span, cudaMemcpyDeviceToHost, s), "hit download");
+        }
+      }
       done += n;
     }
     for (int r = 0; r < Device::kRing; r++) if (dev->ringStream[r]) cudaCheck(cudaStreamSynchronize(dev->ringStream[r]), "trace");

@@ -297,6 +297,48 @@ def test_empty_scenes_updates_and_disable(product, gpu_device):
     L.rtcReleaseScene(sc)
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_hit_download_modes(product, mode):
+    """Host-staged streams with the alternative hit downloads (d2h=1/2: strided 2-D copy of the hit part, d2h=3: compact
+    hit list scattered by a host thread) must equal the default path bit for bit, pageable and page-locked, for several
+    chunkings, strides and both query kinds; everything outside tfar / hit stays untouched."""
+    import torch
+    g = cases.load_golden("two_geoms")
+    base = product.new_device("")
+    sc0, keep0 = build(product, base, g)
+    reps = 200000 // len(g["rays"]) + 1                                  # > 65536 rays: the compact path engages
+    rays = np.tile(g["rays"], reps)
+    rays["id"] = np.arange(len(rays), dtype=np.uint32)
+    n = len(rays)
+    ref = rays.copy()
+    product.intersect(sc0, ref)
+    oref = fx.to_ray(rays)
+    product.occluded(sc0, oref)
+    for cfg in (f"d2h={mode}", f"d2h={mode},chunk_rays=50000", f"d2h={mode},chunk_rays=70001"):
+        dev = product.new_device(cfg)
+        sc, keep = build(product, dev, g)
+        a = rays.copy()
+        product.intersect(sc, a)                                         # pageable host memory
+        assert np.array_equal(a, ref), cfg
+        for stride in (80, 112):
+            host = np.full((n, stride), 0xAB, dtype=np.uint8)
+            host[:, :80] = rays.view(np.uint8).reshape(n, 80)
+            pinned = torch.from_numpy(host.copy()).pin_memory()
+            ctx = product.context()
+            product.lib.rtcIntersect1M(sc, C.byref(ctx), pinned.data_ptr(), n, stride)
+            out = pinned.numpy()
+            assert np.array_equal(out[:, :80].copy().reshape(-1).view(rt.RAYHIT_DTYPE), ref), (cfg, stride)
+            assert np.array_equal(out[:, 80:], host[:, 80:])
+        o = fx.to_ray(rays)
+        product.occluded(sc, o)
+        assert np.array_equal(o, oref), cfg
+        assert product.lib.rtcGetDeviceError(dev) == 0
+        product.lib.rtcReleaseScene(sc)
+        product.lib.rtcReleaseDevice(dev)
+    product.lib.rtcReleaseScene(sc0)
+    product.lib.rtcReleaseDevice(base)
+
+
 def _wave(v0, phase):
     """Deformation used by the refit tests: a travelling wave on y plus a drift on x (float32 throughout)."""
     v = v0.copy()
