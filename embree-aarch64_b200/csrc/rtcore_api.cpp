@@ -98,9 +98,9 @@ struct Device : RefCounted {
   // hit download of staged host streams: 0 = the whole span back (one linear copy), 1 = only bytes [32, record size) of every
   // record (tfar .. hit; a strided 2-D copy, the ray part never changes), 2 = as 1 but tfar alone for occlusion streams,
   // 3 = compact: the kernel appends one record per hit ray to a list, only the list is downloaded and a host thread scatters
-  // it into the caller's buffer.  Same-box A/B (profiles/r01o_ab_d2h_rows.log): 0 -> 662 Mrays/s end to end, 1 -> 463, 2 -> 446
-  // (the copy engines handle 48-byte rows badly)
-  int d2hMode = 0;
+  // it into the caller's buffer (default).  Same-box A/B (profiles/r01o_ab_d2h_rows.log, r01p2_ab_compact_pool.log):
+  // 0 -> 662-668 Mrays/s end to end, 1 -> 463, 2 -> 446 (the copy engines handle 48-byte rows badly), 3 -> 804
+  int d2hMode = 3;
   int scatterThreads = 8;                 // d2h=3: host threads that scatter a downloaded hit list into the caller's records
   int refitEnabled = 1;                   // refit=0: RTC_BUILD_QUALITY_REFIT geometries are rebuilt like any other
 

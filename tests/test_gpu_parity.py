@@ -304,7 +304,7 @@ def test_hit_download_modes(product, mode):
     chunkings, strides and both query kinds; everything outside tfar / hit stays untouched."""
     import torch
     g = cases.load_golden("two_geoms")
-    base = product.new_device("")
+    base = product.new_device("d2h=0")                                   # whole-span download: the plain path
     sc0, keep0 = build(product, base, g)
     reps = 200000 // len(g["rays"]) + 1                                  # > 65536 rays: the compact path engages
     rays = np.tile(g["rays"], reps)
