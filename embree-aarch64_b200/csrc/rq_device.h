@@ -61,6 +61,7 @@ struct RQTraceArgs {
   uint32_t    split;            // traversal loop shape: 1 = one triangle per iteration, 0 = whole leaf list per node
   uint32_t    stackSmem;        // traversal stack levels kept in shared memory (0 = all in local memory), the rest spills to local
   uint32_t    tVote;            // split only: 0 = both phases every iteration, K = triangle phase when >= K lanes wait for it
+  uint32_t    packed;           // 1 = `rays` holds dense 32-byte records {org.xyz, tnear, dir.xyz, tfar} (stride 32); needs hitList
   void*       hitList;          // compact output (flat scenes only): device buffer for one record per hit ray, 48 B (closest) or
   unsigned int* hitCount;       //   4 B (occluded), appended through this device counter (zeroed by the launcher); `out` is then unused
   const void* instances;        // device array of RQInstance when the scene holds instance geometries, else NULL;

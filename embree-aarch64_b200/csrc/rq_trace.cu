@@ -43,6 +43,7 @@ struct TraceParams {
   const RQInstance* instances; // INST kernels only: table indexed by the instance records of the top-level BVH
   char* hitList;               // LIST kernels only: compact output, one record per ray that hit (48 B closest, 4 B occluded) ...
   unsigned int* hitCount;      // ... appended through this counter (zero at launch); nothing is written to `out`
+  uint32_t packed;             // LIST kernels only: rays are dense 32-byte records {org.xyz, tnear, dir.xyz, tfar}
 };
 
 __device__ __forceinline__ float rcpSafe(float d) {           // common/math/vec3fa.h:172-177
@@ -164,7 +165,10 @@ k_trace(const TraceParams P) {
           rid = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
           if (rid < P.numRays) {
             const char* rp = P.rays + (size_t)rid * P.stride;
-            if (ALIGNED) {
+            if (LIST && P.packed) {                             // host-packed upload: 32 bytes per ray
+              const float4 a = __ldg((const float4*)rp), b = __ldg((const float4*)(rp + 16));
+              ox = a.x; oy = a.y; oz = a.z; tnear = a.w; dx = b.x; dy = b.y; dz = b.z; tfar = b.w;
+            } else if (ALIGNED) {
               const float4 a = *(const float4*)rp, b = *(const float4*)(rp + 16);
               ox = a.x; oy = a.y; oz = a.z; tnear = a.w; dx = b.x; dy = b.y; dz = b.z;
               tfar = *(const float*)(rp + 32);
@@ -514,7 +518,7 @@ static int launchTrace(bool occ, const RQTraceArgs* a, cudaStream_t s) {
   P.refillBelow = a->refillBelow ? a->refillBelow : 26u;
   P.split = a->split; P.tVote = a->tVote; P.sdepth = a->stackSmem;
   P.instances = (const RQInstance*)a->instances;
-  P.hitList = (char*)a->hitList; P.hitCount = a->hitCount;
+  P.hitList = (char*)a->hitList; P.hitCount = a->hitCount; P.packed = a->hitList ? a->packed : 0u;
   if (P.hitList) {
     if (!P.hitCount) return (int)cudaErrorInvalidValue;
     cudaError_t ec = cudaMemsetAsync(P.hitCount, 0, sizeof(unsigned int), s);

@@ -16,6 +16,10 @@
 #include <condition_variable>
 #include <deque>
 #include <thread>
+#include <functional>
+#if defined(__SSE2__)
+#include <immintrin.h>
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -53,6 +57,25 @@ struct RefCounted {
   virtual ~RefCounted() {}
   void retain() { refs.fetch_add(1); }
   void release() { if (refs.fetch_sub(1) == 1) delete this; }
+};
+
+// Small persistent pool of host threads (created on first use, lives as long as the device): packs rays for the upload and
+// scatters downloaded hit lists.  The reference spends all host threads on traversal itself (TBB / internal tasking).
+struct HostPool {
+  std::vector<std::thread> th; std::mutex m; std::condition_variable cv; std::deque<std::function<void()>> q; bool quit = false;
+  explicit HostPool(int n) {
+    for (int i = 0; i < n; i++)
+      th.emplace_back([this] {
+        for (;;) {
+          std::function<void()> fn;
+          { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [this] { return quit || !q.empty(); }); if (q.empty()) return; fn = std::move(q.front()); q.pop_front(); }
+          fn();
+        }
+      });
+  }
+  ~HostPool() { { std::lock_guard<std::mutex> lk(m); quit = true; } cv.notify_all(); for (auto& t : th) if (t.joinable()) t.join(); }
+  void submit(std::function<void()> fn) { { std::lock_guard<std::mutex> lk(m); q.push_back(std::move(fn)); } cv.notify_one(); }
+  size_t size() const { return th.size(); }
 };
 
 // --------------------------------------------------------------------------------------------
@@ -101,19 +124,34 @@ struct Device : RefCounted {
   // it into the caller's buffer (default).  Same-box A/B (profiles/r01o_ab_d2h_rows.log, r01p2_ab_compact_pool.log):
   // 0 -> 662-668 Mrays/s end to end, 1 -> 463, 2 -> 446 (the copy engines handle 48-byte rows badly), 3 -> 804
   int d2hMode = 3;
-  int scatterThreads = 8;                 // d2h=3: host threads that scatter a downloaded hit list into the caller's records
+  int scatterThreads = 0;                 // d2h=3: host threads that pack rays / scatter hit lists; 0 = all hardware threads, at most 16
+  int packRays = 1;                       // d2h=3: pack the 32 useful bytes of every ray on the host before the upload
+  void* packHost[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  size_t packCap[kRing] = {0, 0, 0, 0};
+  std::atomic<unsigned long long> h2dBytes{0}, d2hBytes{0};   // bytes moved over PCIe by staged queries (rtcxGetTransferBytes)
+  HostPool* pool = nullptr; std::mutex poolMutex;
+  HostPool& hostPool() {
+    std::lock_guard<std::mutex> l(poolMutex);
+    if (!pool) {
+      int n = scatterThreads > 0 ? scatterThreads : (int)std::thread::hardware_concurrency();
+      pool = new HostPool(std::max(1, std::min(n, 16)));
+    }
+    return *pool;
+  }
   int refitEnabled = 1;                   // refit=0: RTC_BUILD_QUALITY_REFIT geometries are rebuilt like any other
 
   cudaStream_t stream() const { return userStream ? userStream : ownStream; }
   void bind() const { if (hasGpu) cudaSetDevice(ordinal); }
 
   ~Device() override {
+    delete pool;
     if (hasGpu) {
       cudaSetDevice(ordinal);
       for (int i = 0; i < kRing; i++) { if (ringBuf[i]) cudaFree(ringBuf[i]); if (ringStream[i]) cudaStreamDestroy(ringStream[i]); }
       for (int i = 0; i < kRing; i++) {
         if (listDev[i]) cudaFree(listDev[i]);
         if (listHost[i]) cudaFreeHost(listHost[i]);
+        if (packHost[i]) cudaFreeHost(packHost[i]);
         if (evCount[i]) cudaEventDestroy(evCount[i]);
         if (evList[i]) cudaEventDestroy(evList[i]);
       }
@@ -178,7 +216,8 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "zerocopy") d->zeroCopy = atoi(v.c_str());
     else if (k == "refit") d->refitEnabled = atoi(v.c_str());
     else if (k == "d2h") d->d2hMode = atoi(v.c_str());
-    else if (k == "scatter_threads") d->scatterThreads = atoi(v.c_str());
+    else if (k == "scatter_threads" || k == "host_threads") d->scatterThreads = atoi(v.c_str());
+    else if (k == "pack_rays") d->packRays = atoi(v.c_str());
     else if (k == "tvote") d->tVote = std::max(0, std::min(32, atoi(v.c_str())));
     else if (k == "split_occluded") d->splitOccluded = atoi(v.c_str());
     else if (k == "refill") d->refillClosest = std::max(1, std::min(32, atoi(v.c_str())));
@@ -468,14 +507,35 @@ void fillArgs(Scene* sc, RTCIntersectContext* ctx, RQTraceArgs& a, bool stream) 
   a.streamSemantics = stream ? 1u : 0u;
 }
 
-// Host-staged stream with compact hit download (device option d2h=3).  PCIe carries the rays in (copy engine, one linear
-// H2D per 1 M-ray chunk) and, outbound, only one 48-byte (closest) / 4-byte (occluded) record per ray that hit; a helper
-// thread scatters each downloaded list into the caller's records while later chunks are in flight.  With both directions
-// copying whole spans the link delivers 47-49 GB/s per direction, one direction alone 55-57 GB/s (tools/pcie_probe.py).
+// Host-staged stream, compact both ways (device option d2h=3, the default).
+//   in : a pool of host threads packs the 32 bytes of every record the kernels read (org, tnear, dir, tfar) into a page-locked
+//        staging buffer (streaming stores), one linear H2D per 1 M-ray chunk moves 32 instead of 80 / 48 bytes per ray
+//        (pack_rays=0: the whole span is uploaded as it is);
+//   out: the kernel appends one 48-byte (closest) / 4-byte (occluded) record per ray that hit to a list; only the list is
+//        downloaded and the pool scatters it into the caller's records while later chunks are in flight.
+// Why: the link is the bound of the end-to-end path.  Whole spans both ways: 47-49 GB/s per direction (tools/pcie_probe.py),
+// 662-668 Mrays/s on configs[1]; list download: 804 Mrays/s (profiles/r01p2_ab_compact_pool.log); the host packs 80 -> 32 bytes
+// at 84 (8 threads) - 117 GB/s (16 threads) of source bytes on the B200 box's Xeon (tools/hostpack_probe.c).
+// The caller's memory is only touched by CPU loads / stores here, so it need not be page-locked.
+inline void packRay32(const char* s, char* d) {
+#if defined(__SSE4_1__) || defined(__AVX__)
+  const __m128 a = _mm_loadu_ps((const float*)s);
+  __m128 c = _mm_loadu_ps((const float*)(s + 16));
+  c = _mm_insert_ps(c, _mm_load_ss((const float*)(s + 32)), 0x30);   // dir.xyz, tfar
+  _mm_stream_ps((float*)d, a); _mm_stream_ps((float*)(d + 16), c);
+#elif defined(__SSE2__)
+  float t[8]; memcpy(t, s, 28); memcpy(t + 7, s + 32, 4);
+  _mm_stream_ps((float*)d, _mm_loadu_ps(t)); _mm_stream_ps((float*)(d + 16), _mm_loadu_ps(t + 4));
+#else
+  memcpy(d, s, 28); memcpy(d + 28, s + 32, 4);
+#endif
+}
+
 void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size_t stride, bool occluded, size_t recBytes) {
   std::lock_guard<std::mutex> l(dev->stageMutex);
   const size_t chunk = dev->chunkRays;
   const size_t recList = occluded ? 4 : 48;
+  const bool pack = dev->packRays != 0;
   if (!dev->countHost) cudaCheck(cudaMallocHost((void**)&dev->countHost, sizeof(unsigned) * Device::kRing), "hit counters");
   if (!dev->countDev) cudaCheck(cudaMalloc((void**)&dev->countDev, 32 * Device::kRing), "hit counters");
   for (int r = 0; r < Device::kRing; r++) {
@@ -483,81 +543,75 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
     if (!dev->evCount[r]) cudaCheck(cudaEventCreateWithFlags(&dev->evCount[r], cudaEventDisableTiming), "event");
     if (!dev->evList[r]) cudaCheck(cudaEventCreateWithFlags(&dev->evList[r], cudaEventDisableTiming), "event");
   }
-  struct Job { int slot; char* h; unsigned n; unsigned count; unsigned begin, end; };
-  std::mutex qm; std::condition_variable qcv;
-  std::deque<Job> jobs;                                         // one entry per (chunk, slice of its hit list)
-  bool finished = false, slotBusy[Device::kRing] = {false, false, false, false};
+  HostPool& pool = dev->hostPool();
+  const unsigned T = (unsigned)pool.size();
+  struct Chunk { int slot; char* h; unsigned n; unsigned count; };
+  std::mutex qm; std::condition_variable qcv;                   // guards slotBusy / remaining / pending / workerError
+  bool slotBusy[Device::kRing] = {false, false, false, false};
   int remaining[Device::kRing] = {0, 0, 0, 0};
+  int pending = 0;                                              // closures of this call still queued or running
   int workerError = 0;
-  // A single scatter thread manages ~15 ns per hit (two cache lines of the caller's buffer per record, DRAM latency):
-  // 4.2 ms per 1 M-ray chunk against 1.45 ms of H2D (profiles/r01p_ab.log: 319 Mrays/s).  The list of a chunk is
-  // therefore cut into slices handled by a small pool.
-  const int numWorkers = std::max(1, std::min(dev->scatterThreads, 32));
-  auto workerFn = [&] {
-    cudaSetDevice(dev->ordinal);
-    for (;;) {
-      Job j;
-      {
-        std::unique_lock<std::mutex> lk(qm);
-        qcv.wait(lk, [&] { return !jobs.empty() || finished; });
-        if (jobs.empty()) return;
-        j = jobs.front(); jobs.pop_front();
-      }
-      const cudaError_t e = cudaEventSynchronize(dev->evList[j.slot]);
-      if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(qm); workerError = (int)e; cudaGetLastError(); }
-      else if (occluded) {
-        const uint32_t* ids = (const uint32_t*)dev->listHost[j.slot];
-        for (unsigned k = j.begin; k < j.end; k++) {
-          if (k + 16 < j.end && ids[k + 16] < j.n) __builtin_prefetch(j.h + (size_t)ids[k + 16] * stride + 32, 1);
-          if (ids[k] < j.n) *(float*)(j.h + (size_t)ids[k] * stride + 32) = -INFINITY;
-        }
-      } else {
-        const char* recs = (const char*)dev->listHost[j.slot];
-        for (unsigned k = j.begin; k < j.end; k++) {
-          if (k + 16 < j.end) {
-            uint32_t nid; memcpy(&nid, recs + (size_t)(k + 16) * 48, 4);
-            if (nid < j.n) { char* nd = j.h + (size_t)nid * stride; __builtin_prefetch(nd + 32, 1); __builtin_prefetch(nd + 79, 1); }
-          }
-          const char* rec = recs + (size_t)k * 48;
-          uint32_t rid; memcpy(&rid, rec, 4);
-          if (rid >= j.n) continue;
-          char* dst = j.h + (size_t)rid * stride;
-          memcpy(dst + 32, rec + 4, 4);                         // tfar
-          memcpy(dst + 48, rec + 16, 32);                       // Ng, u, v, primID, geomID, instID[0]
-        }
-      }
-      bool freed = false;
-      { std::lock_guard<std::mutex> lk(qm); if (--remaining[j.slot] == 0) { slotBusy[j.slot] = false; freed = true; } }
-      if (freed) qcv.notify_all();
-    }
+  auto submit = [&](std::function<void()> fn) {
+    { std::lock_guard<std::mutex> lk(qm); pending++; }
+    pool.submit([&, fn] { fn(); std::lock_guard<std::mutex> lk(qm); if (--pending == 0) qcv.notify_all(); });   // notify under the lock: `qcv` dies with this call
   };
-  std::vector<std::thread> workers;
-  for (int w = 0; w < numWorkers; w++) workers.emplace_back(workerFn);
-  auto stop = [&] { { std::lock_guard<std::mutex> lk(qm); finished = true; } qcv.notify_all(); for (auto& w : workers) if (w.joinable()) w.join(); };
-  try {
-    Job prev{-1, nullptr, 0, 0, 0, 0};
-    auto stage2 = [&](Job j) {                                  // the kernel of chunk j is done: fetch its list
-      cudaCheck(cudaEventSynchronize(dev->evCount[j.slot]), "trace");
-      j.count = std::min(dev->countHost[j.slot], j.n);
-      cudaStream_t s = dev->ringStream[j.slot];
-      if (j.count) cudaCheck(cudaMemcpyAsync(dev->listHost[j.slot], dev->listDev[j.slot], (size_t)j.count * recList, cudaMemcpyDeviceToHost, s), "hit download");
-      cudaCheck(cudaEventRecord(dev->evList[j.slot], s), "hit download");
-      {
-        std::lock_guard<std::mutex> lk(qm);
-        const unsigned per = std::max(4096u, (j.count + (unsigned)numWorkers - 1) / (unsigned)numWorkers);
-        int parts = 0;
-        for (unsigned b0 = 0; b0 < j.count || parts == 0; b0 += per) {
-          Job p = j; p.begin = b0; p.end = std::min(j.count, b0 + per);
-          jobs.push_back(p); parts++;
-        }
-        remaining[j.slot] = parts;
+  auto drain = [&] { std::unique_lock<std::mutex> lk(qm); qcv.wait(lk, [&] { return pending == 0; }); };
+
+  auto scatterSlice = [&](Chunk c, unsigned begin, unsigned end) {
+    if (occluded) {
+      const uint32_t* ids = (const uint32_t*)dev->listHost[c.slot];
+      for (unsigned k = begin; k < end; k++) {
+        if (k + 16 < end && ids[k + 16] < c.n) __builtin_prefetch(c.h + (size_t)ids[k + 16] * stride + 32, 1);
+        if (ids[k] < c.n) *(float*)(c.h + (size_t)ids[k] * stride + 32) = -INFINITY;
       }
-      qcv.notify_all();
-    };
+    } else {
+      const char* recs = (const char*)dev->listHost[c.slot];
+      for (unsigned k = begin; k < end; k++) {
+        if (k + 16 < end) {
+          uint32_t nid; memcpy(&nid, recs + (size_t)(k + 16) * 48, 4);
+          if (nid < c.n) { char* nd = c.h + (size_t)nid * stride; __builtin_prefetch(nd + 32, 1); __builtin_prefetch(nd + 79, 1); }
+        }
+        const char* rec = recs + (size_t)k * 48;
+        uint32_t rid; memcpy(&rid, rec, 4);
+        if (rid >= c.n) continue;
+        char* dst = c.h + (size_t)rid * stride;
+        memcpy(dst + 32, rec + 4, 4);                           // tfar
+        memcpy(dst + 48, rec + 16, 32);                         // Ng, u, v, primID, geomID, instID[0]
+      }
+    }
+    bool freed = false;
+    { std::lock_guard<std::mutex> lk(qm); if (--remaining[c.slot] == 0) { slotBusy[c.slot] = false; freed = true; } }
+    if (freed) qcv.notify_all();
+  };
+  // the kernel of chunk c is done: fetch its list; one pool thread waits for it and fans the scatter out
+  auto stage2 = [&](Chunk c) {
+    cudaCheck(cudaEventSynchronize(dev->evCount[c.slot]), "trace");
+    c.count = std::min(dev->countHost[c.slot], c.n);
+    cudaStream_t s = dev->ringStream[c.slot];
+    if (c.count) {
+      cudaCheck(cudaMemcpyAsync(dev->listHost[c.slot], dev->listDev[c.slot], (size_t)c.count * recList, cudaMemcpyDeviceToHost, s), "hit download");
+      dev->d2hBytes += (unsigned long long)c.count * recList;
+    }
+    dev->d2hBytes += sizeof(unsigned);
+    cudaCheck(cudaEventRecord(dev->evList[c.slot], s), "hit download");
+    const unsigned per = std::max(8192u, (c.count + T - 1) / T);
+    const int parts = std::max(1, (int)((c.count + per - 1) / per));
+    { std::lock_guard<std::mutex> lk(qm); remaining[c.slot] = parts; }
+    submit([&, c, per, parts] {
+      cudaSetDevice(dev->ordinal);
+      const cudaError_t e = cudaEventSynchronize(dev->evList[c.slot]);
+      if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(qm); workerError = (int)e; cudaGetLastError(); }
+      for (int p = 1; p < parts; p++) submit([&, c, per, p] { scatterSlice(c, (unsigned)p * per, std::min(c.count, (unsigned)(p + 1) * per)); });
+      scatterSlice(c, 0, std::min(c.count, per));
+    });
+  };
+
+  try {
+    Chunk prev{-1, nullptr, 0, 0};
     unsigned done = 0; int slot = 0;
     while (done < M) {
       const unsigned n = (unsigned)std::min<size_t>(chunk, M - done);
-      const size_t span = (size_t)(n - 1) * stride + recBytes;
+      const size_t span = pack ? (size_t)n * 32 : (size_t)(n - 1) * stride + recBytes;
       const int r = slot % Device::kRing; slot++;
       { std::unique_lock<std::mutex> lk(qm); qcv.wait(lk, [&] { return !slotBusy[r]; }); slotBusy[r] = true; }
       cudaStream_t s = dev->ringStream[r];
@@ -577,26 +631,57 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
         cudaCheck(cudaMallocHost(&dev->listHost[r], (size_t)n * 48), "hit list alloc");
         dev->listCap[r] = (size_t)n * 48;
       }
+      if (pack && dev->packCap[r] < (size_t)n * 32) {
+        cudaCheck(cudaStreamSynchronize(s), "staging");
+        if (dev->packHost[r]) cudaFreeHost(dev->packHost[r]);
+        dev->packHost[r] = nullptr; dev->packCap[r] = 0;
+        cudaCheck(cudaMallocHost(&dev->packHost[r], (size_t)n * 32 + 64), "pack staging alloc");
+        dev->packCap[r] = (size_t)n * 32;
+      }
       char* h = rays + (size_t)done * stride;
-      cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], h, span, cudaMemcpyHostToDevice, s), "ray upload");
-      a.rays = dev->ringBuf[r]; a.out = nullptr; a.numRays = n; a.stride = stride;
+      if (pack) {
+        // slices of the chunk are packed by the pool; this thread takes the last slice and waits for the others
+        const unsigned parts = std::max(1u, std::min(T + 1, (n + 16383u) / 16384u));
+        unsigned left = parts - 1;                              // guarded by pm
+        std::mutex pm; std::condition_variable pcv;
+        char* dstBase = (char*)dev->packHost[r];
+        auto packSlice = [&](unsigned p) {
+          const size_t b0 = (size_t)n * p / parts, e0 = (size_t)n * (p + 1) / parts;
+          for (size_t i = b0; i < e0; i++) packRay32(h + i * stride, dstBase + i * 32);
+#if defined(__SSE2__)
+          _mm_sfence();
+#endif
+        };
+        for (unsigned p = 0; p + 1 < parts; p++)
+          submit([&, p] { packSlice(p); std::lock_guard<std::mutex> lk(pm); if (--left == 0) pcv.notify_all(); });
+        packSlice(parts - 1);
+        { std::unique_lock<std::mutex> lk(pm); pcv.wait(lk, [&] { return left == 0; }); }
+        cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], dstBase, (size_t)n * 32, cudaMemcpyHostToDevice, s), "ray upload");
+        dev->h2dBytes += (unsigned long long)n * 32;
+        a.rays = dev->ringBuf[r]; a.stride = 32; a.packed = 1;
+      } else {
+        cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], h, span, cudaMemcpyHostToDevice, s), "ray upload");
+        dev->h2dBytes += span;
+        a.rays = dev->ringBuf[r]; a.stride = stride; a.packed = 0;
+      }
+      a.out = nullptr; a.numRays = n;
       a.workCounter = dev->dWork + 8 * r;
       a.hitList = dev->listDev[r]; a.hitCount = dev->countDev + 8 * r;
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
       cudaCheck(cudaMemcpyAsync(&dev->countHost[r], a.hitCount, sizeof(unsigned), cudaMemcpyDeviceToHost, s), "hit count");
       cudaCheck(cudaEventRecord(dev->evCount[r], s), "hit count");
       if (prev.slot >= 0) stage2(prev);
-      prev = Job{r, h, n, 0, 0, 0};
+      prev = Chunk{r, h, n, 0};
       done += n;
     }
     if (prev.slot >= 0) stage2(prev);
   } catch (...) {
-    stop();
+    drain();
     for (int r = 0; r < Device::kRing; r++) if (dev->ringStream[r]) cudaStreamSynchronize(dev->ringStream[r]);
     cudaGetLastError();
     throw;
   }
-  stop();
+  drain();
   if (workerError) cudaCheck(workerError, "hit download");
 }
 
@@ -662,6 +747,7 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
       char* h = (char*)rays + (size_t)done * stride;
       cudaStream_t s = dev->ringStream[r];
       cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], h, span, cudaMemcpyHostToDevice, s), "ray upload");
+      dev->h2dBytes += span;
       a.rays = dev->ringBuf[r]; a.numRays = n; a.stride = stride;
       // page-locked caller memory: the kernel writes tfar / the hit of rays that hit straight into it
       // (posted PCIe writes, ~10 bytes per ray on average) instead of copying the whole span back
@@ -672,8 +758,10 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
         if (dev->d2hMode && n > 1 && stride >= recBytes) {
           const size_t width = (occluded && dev->d2hMode == 2) ? 4 : recBytes - 32;
           cudaCheck(cudaMemcpy2DAsync(h + 32, stride, (char*)dev->ringBuf[r] + 32, stride, width, n, cudaMemcpyDeviceToHost, s), "hit download");
+          dev->d2hBytes += (unsigned long long)width * n;
         } else {
           cudaCheck(cudaMemcpyAsync(h, dev->ringBuf[r], span, cudaMemcpyDeviceToHost, s), "hit download");
+          dev->d2hBytes += span;
         }
       }
       done += n;
@@ -1380,6 +1468,10 @@ RTC_API void rtcxOccluded1MCounted(RTCScene hs, struct RTCIntersectContext* ctx,
   RTC_TRY checkQuery(s, ctx); VERIFY_HANDLE(out); traceStream(s, ctx, r, M, stride, true, sizeof(RTCRay), (RQTraceCounters*)out); RTC_CATCH(devOf(s))
 }
 RTC_API unsigned long long rtcxGetLaunchCount(void) { return rqLaunchCount(); }
+RTC_API void rtcxGetTransferBytes(RTCDevice h, unsigned long long* h2d, unsigned long long* d2h) {
+  Device* d = (Device*)h;
+  RTC_TRY VERIFY_HANDLE(h); if (h2d) *h2d = d->h2dBytes.load(); if (d2h) *d2h = d->d2hBytes.load(); RTC_CATCH(d)
+}
 
 // ================================================================================================
 // Entry points outside the hot path: exported so existing programs link, raise INVALID_OPERATION.

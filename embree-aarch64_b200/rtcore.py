@@ -161,6 +161,7 @@ class RTCore:
             _sig(L, "rtcxIntersect1MCounted", None, [vp, ctxp, vp, u, sz, C.POINTER(TraceCounters)])
             _sig(L, "rtcxOccluded1MCounted", None, [vp, ctxp, vp, u, sz, C.POINTER(TraceCounters)])
             _sig(L, "rtcxGetLaunchCount", C.c_ulonglong, [])
+            _sig(L, "rtcxGetTransferBytes", None, [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)])
 
     # ---- small conveniences used by tests and bench ----
     def new_device(self, cfg=""):
@@ -259,6 +260,11 @@ class RTCore:
     def occluded_ptr(self, scene, ptr, n, stride=48, coherent=False):
         ctx = self.context(coherent)
         self.lib.rtcOccluded1M(scene, C.byref(ctx), ptr, n, stride)
+
+    def transfer_bytes(self, device):
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        self.lib.rtcxGetTransferBytes(device, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def build_stats(self, scene):
         s = BuildStats()

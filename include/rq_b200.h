@@ -74,5 +74,7 @@ RTC_API void rtcxOccluded1MCounted(RTCScene scene, struct RTCIntersectContext* c
 
 /* Kernels launched by this library since it was loaded. */
 RTC_API unsigned long long rtcxGetLaunchCount(void);
+/* Bytes the library has copied host->device / device->host for host-resident ray streams on `device` since it was created. */
+RTC_API void rtcxGetTransferBytes(RTCDevice device, unsigned long long* h2d_o, unsigned long long* d2h_o);
 
 #endif

@@ -314,7 +314,10 @@ def test_hit_download_modes(product, mode):
     product.intersect(sc0, ref)
     oref = fx.to_ray(rays)
     product.occluded(sc0, oref)
-    for cfg in (f"d2h={mode}", f"d2h={mode},chunk_rays=50000", f"d2h={mode},chunk_rays=70001"):
+    cfgs = [f"d2h={mode}", f"d2h={mode},chunk_rays=50000", f"d2h={mode},chunk_rays=70001"]
+    if mode == 3:
+        cfgs += ["d2h=3,pack_rays=0", "d2h=3,host_threads=3,chunk_rays=33333", "d2h=3,host_threads=1"]
+    for cfg in cfgs:
         dev = product.new_device(cfg)
         sc, keep = build(product, dev, g)
         a = rays.copy()
