@@ -17,6 +17,7 @@
 #include <deque>
 #include <thread>
 #include <functional>
+#include <chrono>
 #if defined(__SSE2__)
 #include <immintrin.h>
 #endif
@@ -606,6 +607,10 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
     });
   };
 
+  using clk = std::chrono::steady_clock;
+  double tSlot = 0, tPack = 0, tStage2 = 0, tEnq = 0;           // where the calling thread spends its time (verbose >= 2)
+  const auto tCall = clk::now();
+  auto since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
   try {
     Chunk prev{-1, nullptr, 0, 0};
     unsigned done = 0; int slot = 0;
@@ -613,7 +618,9 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
       const unsigned n = (unsigned)std::min<size_t>(chunk, M - done);
       const size_t span = pack ? (size_t)n * 32 : (size_t)(n - 1) * stride + recBytes;
       const int r = slot % Device::kRing; slot++;
+      auto t0 = clk::now();
       { std::unique_lock<std::mutex> lk(qm); qcv.wait(lk, [&] { return !slotBusy[r]; }); slotBusy[r] = true; }
+      tSlot += since(t0);
       cudaStream_t s = dev->ringStream[r];
       if (dev->ringCap[r] < span) {
         cudaCheck(cudaStreamSynchronize(s), "staging");
@@ -639,6 +646,7 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
         dev->packCap[r] = (size_t)n * 32;
       }
       char* h = rays + (size_t)done * stride;
+      t0 = clk::now();
       if (pack) {
         // slices of the chunk are packed by the pool; this thread takes the last slice and waits for the others
         const unsigned parts = std::max(1u, std::min(T + 1, (n + 16383u) / 16384u));
@@ -659,6 +667,7 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
         cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], dstBase, (size_t)n * 32, cudaMemcpyHostToDevice, s), "ray upload");
         dev->h2dBytes += (unsigned long long)n * 32;
         a.rays = dev->ringBuf[r]; a.stride = 32; a.packed = 1;
+        tPack += since(t0);
       } else {
         cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], h, span, cudaMemcpyHostToDevice, s), "ray upload");
         dev->h2dBytes += span;
@@ -670,18 +679,28 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
       cudaCheck(cudaMemcpyAsync(&dev->countHost[r], a.hitCount, sizeof(unsigned), cudaMemcpyDeviceToHost, s), "hit count");
       cudaCheck(cudaEventRecord(dev->evCount[r], s), "hit count");
+      tEnq += since(t0);
+      t0 = clk::now();
       if (prev.slot >= 0) stage2(prev);
+      tStage2 += since(t0);
       prev = Chunk{r, h, n, 0};
       done += n;
     }
+    auto t0 = clk::now();
     if (prev.slot >= 0) stage2(prev);
+    tStage2 += since(t0);
   } catch (...) {
     drain();
     for (int r = 0; r < Device::kRing; r++) if (dev->ringStream[r]) cudaStreamSynchronize(dev->ringStream[r]);
     cudaGetLastError();
     throw;
   }
+  const auto tD = clk::now();
   drain();
+  if (dev->verbose >= 2)
+    fprintf(stderr, "b200-rayquery staged %s stream: %u rays, %.2f ms total; calling thread: slot wait %.2f, pack+enqueue %.2f (pack %.2f), "
+            "count wait %.2f, final drain %.2f ms; pool %u threads\n", occluded ? "occlusion" : "closest-hit", M, since(tCall), tSlot, tEnq, tPack,
+            tStage2, since(tD), T);
   if (workerError) cudaCheck(workerError, "hit download");
 }
 
