@@ -532,96 +532,144 @@ inline void packRay32(const char* s, char* d) {
 #endif
 }
 
-void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size_t stride, bool occluded, size_t recBytes) {
-  std::lock_guard<std::mutex> l(dev->stageMutex);
-  const size_t chunk = dev->chunkRays;
-  const size_t recList = occluded ? 4 : 48;
-  const bool pack = dev->packRays != 0;
-  if (!dev->countHost) cudaCheck(cudaMallocHost((void**)&dev->countHost, sizeof(unsigned) * Device::kRing), "hit counters");
-  if (!dev->countDev) cudaCheck(cudaMalloc((void**)&dev->countDev, 32 * Device::kRing), "hit counters");
-  for (int r = 0; r < Device::kRing; r++) {
-    if (!dev->ringStream[r]) cudaCheck(cudaStreamCreateWithFlags(&dev->ringStream[r], cudaStreamNonBlocking), "stream");
-    if (!dev->evCount[r]) cudaCheck(cudaEventCreateWithFlags(&dev->evCount[r], cudaEventDisableTiming), "event");
-    if (!dev->evList[r]) cudaCheck(cudaEventCreateWithFlags(&dev->evList[r], cudaEventDisableTiming), "event");
-  }
-  HostPool& pool = dev->hostPool();
-  const unsigned T = (unsigned)pool.size();
-  struct Chunk { int slot; char* h; unsigned n; unsigned count; };
-  std::mutex qm; std::condition_variable qcv;                   // guards slotBusy / remaining / pending / workerError
+// The call is event driven -- no thread ever waits for the GPU except the caller waiting for a free ring slot:
+//   caller      : per 1 M-ray chunk: take a free slot, hand the chunk's pack slices to the pool
+//   last slice  : enqueues H2D + kernel + count download on the slot's stream, then a host callback
+//   callback 1  : (CUDA thread, no CUDA calls allowed) asks the pool to fetch the list: count is known now
+//   pool        : enqueues the list download + callback 2
+//   callback 2  : hands the scatter slices to the pool; the last slice frees the slot
+struct CompactCall;
+struct CompactChunk {
+  CompactCall* call; int slot; char* h; unsigned n; unsigned count; unsigned packLeft; unsigned scatterLeft; unsigned packParts;
+};
+struct CompactCall {
+  Device* dev; RQTraceArgs a; size_t stride; bool occluded, pack; size_t recBytes, recList; unsigned T;
+  std::mutex m; std::condition_variable cv;                     // guards everything below and the chunks' counters
   bool slotBusy[Device::kRing] = {false, false, false, false};
-  int remaining[Device::kRing] = {0, 0, 0, 0};
-  int pending = 0;                                              // closures of this call still queued or running
-  int workerError = 0;
-  auto submit = [&](std::function<void()> fn) {
-    { std::lock_guard<std::mutex> lk(qm); pending++; }
-    pool.submit([&, fn] { fn(); std::lock_guard<std::mutex> lk(qm); if (--pending == 0) qcv.notify_all(); });   // notify under the lock: `qcv` dies with this call
-  };
-  auto drain = [&] { std::unique_lock<std::mutex> lk(qm); qcv.wait(lk, [&] { return pending == 0; }); };
+  int pending = 0; unsigned chunksDone = 0; int error = 0;
+  void submit(std::function<void()> fn) {
+    { std::lock_guard<std::mutex> lk(m); pending++; }
+    dev->hostPool().submit([this, fn] { fn(); std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv.notify_all(); });
+  }
+  void fail(int e) { std::lock_guard<std::mutex> lk(m); if (!error) error = e ? e : (int)cudaErrorUnknown; cudaGetLastError(); }
+  void chunkDone(CompactChunk* c) { std::lock_guard<std::mutex> lk(m); slotBusy[c->slot] = false; chunksDone++; cv.notify_all(); }
 
-  auto scatterSlice = [&](Chunk c, unsigned begin, unsigned end) {
+  void packSlice(CompactChunk* c, unsigned p) {
+    const size_t b0 = (size_t)c->n * p / c->packParts, e0 = (size_t)c->n * (p + 1) / c->packParts;
+    char* d = (char*)dev->packHost[c->slot];
+    for (size_t i = b0; i < e0; i++) packRay32(c->h + i * stride, d + i * 32);
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+    bool last;
+    { std::lock_guard<std::mutex> lk(m); last = (--c->packLeft == 0); }
+    if (last) enqueue(c);
+  }
+  static void CUDART_CB onCount(void* p) { CompactChunk* c = (CompactChunk*)p; c->call->submit([c] { c->call->fetchList(c); }); }
+  static void CUDART_CB onList(void* p) { CompactChunk* c = (CompactChunk*)p; c->call->startScatter(c); }
+
+  void enqueue(CompactChunk* c) {                               // any thread
+    cudaSetDevice(dev->ordinal);
+    const int r = c->slot;
+    cudaStream_t s = dev->ringStream[r];
+    RQTraceArgs x = a;
+    int e = 0;
+    if (pack) {
+      e = cudaMemcpyAsync(dev->ringBuf[r], dev->packHost[r], (size_t)c->n * 32, cudaMemcpyHostToDevice, s);
+      dev->h2dBytes += (unsigned long long)c->n * 32;
+      x.stride = 32; x.packed = 1;
+    } else {
+      const size_t span = (size_t)(c->n - 1) * stride + recBytes;
+      e = cudaMemcpyAsync(dev->ringBuf[r], c->h, span, cudaMemcpyHostToDevice, s);
+      dev->h2dBytes += span;
+      x.stride = stride; x.packed = 0;
+    }
+    x.rays = dev->ringBuf[r]; x.out = nullptr; x.numRays = c->n;
+    x.workCounter = dev->dWork + 8 * r;
+    x.hitList = dev->listDev[r]; x.hitCount = dev->countDev + 8 * r;
+    if (!e) e = occluded ? rqLaunchOccluded(&x, (rqStream)s) : rqLaunchIntersect(&x, (rqStream)s);
+    if (!e) e = cudaMemcpyAsync(&dev->countHost[r], x.hitCount, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
+    if (!e) e = cudaLaunchHostFunc(s, onCount, c);
+    if (e) { fail(e); chunkDone(c); }
+  }
+  void fetchList(CompactChunk* c) {                             // pool thread, the kernel of this chunk has finished
+    cudaSetDevice(dev->ordinal);
+    const int r = c->slot;
+    cudaStream_t s = dev->ringStream[r];
+    c->count = std::min(dev->countHost[r], c->n);
+    int e = 0;
+    if (c->count) {
+      e = cudaMemcpyAsync(dev->listHost[r], dev->listDev[r], (size_t)c->count * recList, cudaMemcpyDeviceToHost, s);
+      dev->d2hBytes += (unsigned long long)c->count * recList;
+    }
+    dev->d2hBytes += sizeof(unsigned);
+    if (!e) e = cudaLaunchHostFunc(s, onList, c);
+    if (e) { fail(e); chunkDone(c); }
+  }
+  void startScatter(CompactChunk* c) {                          // CUDA callback thread: only queues work
+    const unsigned per = std::max(8192u, (c->count + T - 1) / T);
+    const unsigned parts = std::max(1u, (c->count + per - 1) / per);
+    { std::lock_guard<std::mutex> lk(m); c->scatterLeft = parts; }
+    for (unsigned p = 0; p < parts; p++) submit([this, c, per, p] { scatterSlice(c, p * per, std::min(c->count, (p + 1) * per)); });
+  }
+  void scatterSlice(CompactChunk* c, unsigned begin, unsigned end) {
     if (occluded) {
-      const uint32_t* ids = (const uint32_t*)dev->listHost[c.slot];
+      const uint32_t* ids = (const uint32_t*)dev->listHost[c->slot];
       for (unsigned k = begin; k < end; k++) {
-        if (k + 16 < end && ids[k + 16] < c.n) __builtin_prefetch(c.h + (size_t)ids[k + 16] * stride + 32, 1);
-        if (ids[k] < c.n) *(float*)(c.h + (size_t)ids[k] * stride + 32) = -INFINITY;
+        if (k + 16 < end && ids[k + 16] < c->n) __builtin_prefetch(c->h + (size_t)ids[k + 16] * stride + 32, 1);
+        if (ids[k] < c->n) *(float*)(c->h + (size_t)ids[k] * stride + 32) = -INFINITY;
       }
     } else {
-      const char* recs = (const char*)dev->listHost[c.slot];
+      const char* recs = (const char*)dev->listHost[c->slot];
       for (unsigned k = begin; k < end; k++) {
         if (k + 16 < end) {
           uint32_t nid; memcpy(&nid, recs + (size_t)(k + 16) * 48, 4);
-          if (nid < c.n) { char* nd = c.h + (size_t)nid * stride; __builtin_prefetch(nd + 32, 1); __builtin_prefetch(nd + 79, 1); }
+          if (nid < c->n) { char* nd = c->h + (size_t)nid * stride; __builtin_prefetch(nd + 32, 1); __builtin_prefetch(nd + 79, 1); }
         }
         const char* rec = recs + (size_t)k * 48;
         uint32_t rid; memcpy(&rid, rec, 4);
-        if (rid >= c.n) continue;
-        char* dst = c.h + (size_t)rid * stride;
+        if (rid >= c->n) continue;
+        char* dst = c->h + (size_t)rid * stride;
         memcpy(dst + 32, rec + 4, 4);                           // tfar
         memcpy(dst + 48, rec + 16, 32);                         // Ng, u, v, primID, geomID, instID[0]
       }
     }
-    bool freed = false;
-    { std::lock_guard<std::mutex> lk(qm); if (--remaining[c.slot] == 0) { slotBusy[c.slot] = false; freed = true; } }
-    if (freed) qcv.notify_all();
-  };
-  // the kernel of chunk c is done: fetch its list; one pool thread waits for it and fans the scatter out
-  auto stage2 = [&](Chunk c) {
-    cudaCheck(cudaEventSynchronize(dev->evCount[c.slot]), "trace");
-    c.count = std::min(dev->countHost[c.slot], c.n);
-    cudaStream_t s = dev->ringStream[c.slot];
-    if (c.count) {
-      cudaCheck(cudaMemcpyAsync(dev->listHost[c.slot], dev->listDev[c.slot], (size_t)c.count * recList, cudaMemcpyDeviceToHost, s), "hit download");
-      dev->d2hBytes += (unsigned long long)c.count * recList;
-    }
-    dev->d2hBytes += sizeof(unsigned);
-    cudaCheck(cudaEventRecord(dev->evList[c.slot], s), "hit download");
-    const unsigned per = std::max(8192u, (c.count + T - 1) / T);
-    const int parts = std::max(1, (int)((c.count + per - 1) / per));
-    { std::lock_guard<std::mutex> lk(qm); remaining[c.slot] = parts; }
-    submit([&, c, per, parts] {
-      cudaSetDevice(dev->ordinal);
-      const cudaError_t e = cudaEventSynchronize(dev->evList[c.slot]);
-      if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(qm); workerError = (int)e; cudaGetLastError(); }
-      for (int p = 1; p < parts; p++) submit([&, c, per, p] { scatterSlice(c, (unsigned)p * per, std::min(c.count, (unsigned)(p + 1) * per)); });
-      scatterSlice(c, 0, std::min(c.count, per));
-    });
-  };
+    bool last;
+    { std::lock_guard<std::mutex> lk(m); last = (--c->scatterLeft == 0); }
+    if (last) chunkDone(c);
+  }
+};
 
+void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size_t stride, bool occluded, size_t recBytes) {
+  std::lock_guard<std::mutex> l(dev->stageMutex);
+  const size_t chunk = dev->chunkRays;
+  if (!dev->countHost) cudaCheck(cudaMallocHost((void**)&dev->countHost, sizeof(unsigned) * Device::kRing), "hit counters");
+  if (!dev->countDev) cudaCheck(cudaMalloc((void**)&dev->countDev, 32 * Device::kRing), "hit counters");
+  for (int r = 0; r < Device::kRing; r++)
+    if (!dev->ringStream[r]) cudaCheck(cudaStreamCreateWithFlags(&dev->ringStream[r], cudaStreamNonBlocking), "stream");
+  CompactCall call;
+  call.dev = dev; call.a = a; call.stride = stride; call.occluded = occluded; call.pack = dev->packRays != 0;
+  call.recBytes = recBytes; call.recList = occluded ? 4 : 48; call.T = (unsigned)dev->hostPool().size();
+  const unsigned numChunks = (unsigned)((M + chunk - 1) / chunk);
+  std::vector<CompactChunk> chunks(numChunks);
   using clk = std::chrono::steady_clock;
-  double tSlot = 0, tPack = 0, tStage2 = 0, tEnq = 0;           // where the calling thread spends its time (verbose >= 2)
   const auto tCall = clk::now();
-  auto since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+  double tSlot = 0;
+  unsigned issued = 0;
+  auto finish = [&] {                                           // every issued chunk done and no closure of this call left
+    std::unique_lock<std::mutex> lk(call.m);
+    call.cv.wait(lk, [&] { return call.chunksDone == issued && call.pending == 0; });
+  };
   try {
-    Chunk prev{-1, nullptr, 0, 0};
-    unsigned done = 0; int slot = 0;
-    while (done < M) {
+    unsigned done = 0;
+    for (unsigned i = 0; i < numChunks; i++) {
       const unsigned n = (unsigned)std::min<size_t>(chunk, M - done);
-      const size_t span = pack ? (size_t)n * 32 : (size_t)(n - 1) * stride + recBytes;
-      const int r = slot % Device::kRing; slot++;
-      auto t0 = clk::now();
-      { std::unique_lock<std::mutex> lk(qm); qcv.wait(lk, [&] { return !slotBusy[r]; }); slotBusy[r] = true; }
-      tSlot += since(t0);
-      cudaStream_t s = dev->ringStream[r];
+      const size_t span = call.pack ? (size_t)n * 32 : (size_t)(n - 1) * stride + recBytes;
+      const int r = (int)(i % Device::kRing);
+      const auto t0 = clk::now();
+      { std::unique_lock<std::mutex> lk(call.m); call.cv.wait(lk, [&] { return !call.slotBusy[r]; }); }
+      tSlot += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+      cudaStream_t s = dev->ringStream[r];                      // the slot is idle: its buffers may be re-allocated
       if (dev->ringCap[r] < span) {
         cudaCheck(cudaStreamSynchronize(s), "staging");
         if (dev->ringBuf[r]) cudaFree(dev->ringBuf[r]);
@@ -638,70 +686,35 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
         cudaCheck(cudaMallocHost(&dev->listHost[r], (size_t)n * 48), "hit list alloc");
         dev->listCap[r] = (size_t)n * 48;
       }
-      if (pack && dev->packCap[r] < (size_t)n * 32) {
+      if (call.pack && dev->packCap[r] < (size_t)n * 32) {
         cudaCheck(cudaStreamSynchronize(s), "staging");
         if (dev->packHost[r]) cudaFreeHost(dev->packHost[r]);
         dev->packHost[r] = nullptr; dev->packCap[r] = 0;
         cudaCheck(cudaMallocHost(&dev->packHost[r], (size_t)n * 32 + 64), "pack staging alloc");
         dev->packCap[r] = (size_t)n * 32;
       }
-      char* h = rays + (size_t)done * stride;
-      t0 = clk::now();
-      if (pack) {
-        // slices of the chunk are packed by the pool; this thread takes the last slice and waits for the others
-        const unsigned parts = std::max(1u, std::min(T + 1, (n + 16383u) / 16384u));
-        unsigned left = parts - 1;                              // guarded by pm
-        std::mutex pm; std::condition_variable pcv;
-        char* dstBase = (char*)dev->packHost[r];
-        auto packSlice = [&](unsigned p) {
-          const size_t b0 = (size_t)n * p / parts, e0 = (size_t)n * (p + 1) / parts;
-          for (size_t i = b0; i < e0; i++) packRay32(h + i * stride, dstBase + i * 32);
-#if defined(__SSE2__)
-          _mm_sfence();
-#endif
-        };
-        for (unsigned p = 0; p + 1 < parts; p++)
-          submit([&, p] { packSlice(p); std::lock_guard<std::mutex> lk(pm); if (--left == 0) pcv.notify_all(); });
-        packSlice(parts - 1);
-        { std::unique_lock<std::mutex> lk(pm); pcv.wait(lk, [&] { return left == 0; }); }
-        cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], dstBase, (size_t)n * 32, cudaMemcpyHostToDevice, s), "ray upload");
-        dev->h2dBytes += (unsigned long long)n * 32;
-        a.rays = dev->ringBuf[r]; a.stride = 32; a.packed = 1;
-        tPack += since(t0);
-      } else {
-        cudaCheck(cudaMemcpyAsync(dev->ringBuf[r], h, span, cudaMemcpyHostToDevice, s), "ray upload");
-        dev->h2dBytes += span;
-        a.rays = dev->ringBuf[r]; a.stride = stride; a.packed = 0;
-      }
-      a.out = nullptr; a.numRays = n;
-      a.workCounter = dev->dWork + 8 * r;
-      a.hitList = dev->listDev[r]; a.hitCount = dev->countDev + 8 * r;
-      cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
-      cudaCheck(cudaMemcpyAsync(&dev->countHost[r], a.hitCount, sizeof(unsigned), cudaMemcpyDeviceToHost, s), "hit count");
-      cudaCheck(cudaEventRecord(dev->evCount[r], s), "hit count");
-      tEnq += since(t0);
-      t0 = clk::now();
-      if (prev.slot >= 0) stage2(prev);
-      tStage2 += since(t0);
-      prev = Chunk{r, h, n, 0};
+      CompactChunk* c = &chunks[i];
+      c->call = &call; c->slot = r; c->h = rays + (size_t)done * stride; c->n = n; c->count = 0; c->scatterLeft = 0;
+      c->packParts = call.pack ? std::max(1u, std::min(2 * call.T, (n + 16383u) / 16384u)) : 1u;
+      c->packLeft = c->packParts;
+      { std::lock_guard<std::mutex> lk(call.m); call.slotBusy[r] = true; }
+      issued++;
+      if (call.pack) { for (unsigned p = 0; p < c->packParts; p++) call.submit([&call, c, p] { call.packSlice(c, p); }); }
+      else call.submit([&call, c] { call.enqueue(c); });
       done += n;
     }
-    auto t0 = clk::now();
-    if (prev.slot >= 0) stage2(prev);
-    tStage2 += since(t0);
   } catch (...) {
-    drain();
+    finish();
     for (int r = 0; r < Device::kRing; r++) if (dev->ringStream[r]) cudaStreamSynchronize(dev->ringStream[r]);
     cudaGetLastError();
     throw;
   }
-  const auto tD = clk::now();
-  drain();
+  finish();
   if (dev->verbose >= 2)
-    fprintf(stderr, "b200-rayquery staged %s stream: %u rays, %.2f ms total; calling thread: slot wait %.2f, pack+enqueue %.2f (pack %.2f), "
-            "count wait %.2f, final drain %.2f ms; pool %u threads\n", occluded ? "occlusion" : "closest-hit", M, since(tCall), tSlot, tEnq, tPack,
-            tStage2, since(tD), T);
-  if (workerError) cudaCheck(workerError, "hit download");
+    fprintf(stderr, "b200-rayquery staged %s stream: %u rays in %u chunks, %.2f ms total, caller waited %.2f ms for ring slots; pool %u threads, pack %d\n",
+            occluded ? "occlusion" : "closest-hit", M, numChunks, std::chrono::duration<double, std::milli>(clk::now() - tCall).count(), tSlot,
+            call.T, (int)call.pack);
+  if (call.error) cudaCheck(call.error, "staged trace");
 }
 
 // Trace M records of `stride` bytes at `rays`; occluded selects the any-hit kernel; recBytes is
