@@ -92,7 +92,7 @@ struct Device : RefCounted {
   RTCErrorFunction errFn = nullptr; void* errPtr = nullptr;
   RTCMemoryMonitorFunction memFn = nullptr; void* memPtr = nullptr;
   // staging for host-resident ray streams: a small ring of (stream, device buffer) pairs
-  static const int kRing = 4;
+  static const int kRing = 6;
   std::mutex stageMutex;
   cudaStream_t ringStream[kRing] = {nullptr, nullptr, nullptr, nullptr};
   void* ringBuf[kRing] = {nullptr, nullptr, nullptr, nullptr};
@@ -126,7 +126,8 @@ struct Device : RefCounted {
   // 0 -> 662-668 Mrays/s end to end, 1 -> 463, 2 -> 446 (the copy engines handle 48-byte rows badly), 3 -> 804
   int d2hMode = 3;
   int scatterThreads = 0;                 // d2h=3: host threads that pack rays / scatter hit lists; 0 = all hardware threads, at most 16
-  int packRays = 1;                       // d2h=3: pack the 32 useful bytes of every ray on the host before the upload
+  int packRays = 1;                       // d2h=3: 0 = upload whole records, 1 = hybrid (pack while the pool has room, see traceStreamCompact), 2 = pack every chunk
+  int packDepth = 2;                      // hybrid: chunks allowed in the pack stage at once
   void* packHost[kRing] = {nullptr, nullptr, nullptr, nullptr};
   size_t packCap[kRing] = {0, 0, 0, 0};
   std::atomic<unsigned long long> h2dBytes{0}, d2hBytes{0};   // bytes moved over PCIe by staged queries (rtcxGetTransferBytes)
@@ -219,6 +220,7 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "d2h") d->d2hMode = atoi(v.c_str());
     else if (k == "scatter_threads" || k == "host_threads") d->scatterThreads = atoi(v.c_str());
     else if (k == "pack_rays") d->packRays = atoi(v.c_str());
+    else if (k == "pack_depth") d->packDepth = std::max(1, atoi(v.c_str()));
     else if (k == "tvote") d->tVote = std::max(0, std::min(32, atoi(v.c_str())));
     else if (k == "split_occluded") d->splitOccluded = atoi(v.c_str());
     else if (k == "refill") d->refillClosest = std::max(1, std::min(32, atoi(v.c_str())));
@@ -540,13 +542,14 @@ inline void packRay32(const char* s, char* d) {
 //   callback 2  : hands the scatter slices to the pool; the last slice frees the slot
 struct CompactCall;
 struct CompactChunk {
-  CompactCall* call; int slot; char* h; unsigned n; unsigned count; unsigned packLeft; unsigned scatterLeft; unsigned packParts;
+  CompactCall* call; int slot; char* h; unsigned n; unsigned count; unsigned packLeft; unsigned scatterLeft; unsigned packParts; bool packed;
 };
 struct CompactCall {
   Device* dev; RQTraceArgs a; size_t stride; bool occluded, pack; size_t recBytes, recList; unsigned T;
   std::mutex m; std::condition_variable cv;                     // guards everything below and the chunks' counters
   bool slotBusy[Device::kRing] = {false, false, false, false};
   int pending = 0; unsigned chunksDone = 0; int error = 0;
+  int packing = 0;                                              // chunks whose pack slices are still queued or running
   void submit(std::function<void()> fn) {
     { std::lock_guard<std::mutex> lk(m); pending++; }
     dev->hostPool().submit([this, fn] { fn(); std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv.notify_all(); });
@@ -562,7 +565,7 @@ struct CompactCall {
     _mm_sfence();
 #endif
     bool last;
-    { std::lock_guard<std::mutex> lk(m); last = (--c->packLeft == 0); }
+    { std::lock_guard<std::mutex> lk(m); last = (--c->packLeft == 0); if (last) { packing--; cv.notify_all(); } }
     if (last) enqueue(c);
   }
   static void CUDART_CB onCount(void* p) { CompactChunk* c = (CompactChunk*)p; c->call->submit([c] { c->call->fetchList(c); }); }
@@ -574,7 +577,7 @@ struct CompactCall {
     cudaStream_t s = dev->ringStream[r];
     RQTraceArgs x = a;
     int e = 0;
-    if (pack) {
+    if (c->packed) {
       e = cudaMemcpyAsync(dev->ringBuf[r], dev->packHost[r], (size_t)c->n * 32, cudaMemcpyHostToDevice, s);
       dev->h2dBytes += (unsigned long long)c->n * 32;
       x.stride = 32; x.packed = 1;
@@ -664,7 +667,7 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
     unsigned done = 0;
     for (unsigned i = 0; i < numChunks; i++) {
       const unsigned n = (unsigned)std::min<size_t>(chunk, M - done);
-      const size_t span = call.pack ? (size_t)n * 32 : (size_t)(n - 1) * stride + recBytes;
+      const size_t span = (size_t)(n - 1) * stride + recBytes;
       const int r = (int)(i % Device::kRing);
       const auto t0 = clk::now();
       { std::unique_lock<std::mutex> lk(call.m); call.cv.wait(lk, [&] { return !call.slotBusy[r]; }); }
@@ -695,11 +698,19 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
       }
       CompactChunk* c = &chunks[i];
       c->call = &call; c->slot = r; c->h = rays + (size_t)done * stride; c->n = n; c->count = 0; c->scatterLeft = 0;
-      c->packParts = call.pack ? std::max(1u, std::min(2 * call.T, (n + 16383u) / 16384u)) : 1u;
+      // Hybrid upload: the copy engine moves whole records at ~55 GB/s without any CPU work, the pool packs at ~50 GB/s of source
+      // bytes on this box (page-locked 4 KB pages) and then uploads 2.5x fewer bytes -- the two run side by side.  A chunk is
+      // packed while fewer than packDepth chunks are in the pack stage, otherwise it goes to the copy engine as it is.
+      {
+        std::lock_guard<std::mutex> lk(call.m);
+        c->packed = call.pack && (dev->packRays >= 2 || call.packing < dev->packDepth);
+        if (c->packed) call.packing++;
+        call.slotBusy[r] = true;
+      }
+      c->packParts = c->packed ? std::max(1u, std::min(2 * call.T, (n + 16383u) / 16384u)) : 1u;
       c->packLeft = c->packParts;
-      { std::lock_guard<std::mutex> lk(call.m); call.slotBusy[r] = true; }
       issued++;
-      if (call.pack) { for (unsigned p = 0; p < c->packParts; p++) call.submit([&call, c, p] { call.packSlice(c, p); }); }
+      if (c->packed) { for (unsigned p = 0; p < c->packParts; p++) call.submit([&call, c, p] { call.packSlice(c, p); }); }
       else call.submit([&call, c] { call.enqueue(c); });
       done += n;
     }
