@@ -125,8 +125,12 @@ struct Device : RefCounted {
   // it into the caller's buffer (default).  Same-box A/B (profiles/r01o_ab_d2h_rows.log, r01p2_ab_compact_pool.log):
   // 0 -> 662-668 Mrays/s end to end, 1 -> 463, 2 -> 446 (the copy engines handle 48-byte rows badly), 3 -> 804
   int d2hMode = 3;
-  int scatterThreads = 0;                 // d2h=3: host threads that pack rays / scatter hit lists; 0 = all hardware threads, at most 16
-  int packRays = 1;                       // d2h=3: 0 = upload whole records, 1 = hybrid (pack while the pool has room, see traceStreamCompact), 2 = pack every chunk
+  int scatterThreads = 8;                 // d2h=3: host threads that scatter hit lists (and pack rays); 0 = all hardware threads; at most 16
+  // d2h=3: 0 = upload whole records (default), 1 = hybrid (pack while the pool has room, see traceStreamCompact), 2 = pack every chunk.
+  // Same-box probe on configs[1] (profiles/r01r_e2e_probe.log, 16 host threads): 0 -> 777-804 Mrays/s, 1 -> 788-826, 2 -> 733-776:
+  // packing reads the caller's 80-byte records at ~50 GB/s, the same rate the copy engine uploads them, and together with the
+  // hit scatter the host memory system (~150 GB/s) becomes the bound; so the default leaves the host cores alone.
+  int packRays = 0;
   int packDepth = 2;                      // hybrid: chunks allowed in the pack stage at once
   void* packHost[kRing] = {nullptr, nullptr, nullptr, nullptr};
   size_t packCap[kRing] = {0, 0, 0, 0};
@@ -136,6 +140,7 @@ struct Device : RefCounted {
     std::lock_guard<std::mutex> l(poolMutex);
     if (!pool) {
       int n = scatterThreads > 0 ? scatterThreads : (int)std::thread::hardware_concurrency();
+      if (packRays && scatterThreads == 8) n = (int)std::thread::hardware_concurrency();   // packing wants every core
       pool = new HostPool(std::max(1, std::min(n, 16)));
     }
     return *pool;
