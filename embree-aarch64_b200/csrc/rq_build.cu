@@ -748,7 +748,9 @@ struct ScratchScope {
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
       unsigned long long thr = 0;
       cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-      if (thr < (16ull << 30)) { thr = 16ull << 30; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+      // a 50 M-triangle build needs ~22 GB of scratch: with a 16 GB threshold the pool gave pages back at every synchronisation
+      // and the next phase re-allocated them (80 ms spent in the hierarchy phase, profiles/r01s_build_c5.jsonl)
+      if (thr < (64ull << 30)) { thr = 64ull << 30; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
     }
     cudaGetLastError();
   }
