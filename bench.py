@@ -333,8 +333,8 @@ def run_ours(args):
                          "traffic": ncu.get("dram_bytes_per_launch_closest")},
             "e2e": {"value": total_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d_step),
                     "d2h_bytes_per_step": int(d2h_step), "host_record_bytes_per_step": world * (nd * 80 + ns * 48),
-                    "path": "rtcIntersect1M + rtcOccluded1M on page-locked host streams: host threads pack 32 B/ray, H2D, kernels, "
-                            "compact hit-list D2H, host scatter (all inside the timed region)",
+                    "path": "rtcIntersect1M + rtcOccluded1M on page-locked host streams: H2D of the ray records, kernels, compact "
+                            "hit-list D2H, scatter into the caller's records by the library's host threads (all inside the timed region)",
                     "host_equals_device_result": same},
             "gpu_launches": int(launches), "clocks": clocks,
         }

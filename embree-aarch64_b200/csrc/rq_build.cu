@@ -456,8 +456,10 @@ k_ploc_init(B2 t, int n, const RQTri* __restrict__ trisIn, const uint32_t* __res
 }
 
 __global__ void __launch_bounds__(PLOC_THREADS)
-k_ploc_nn(B2 t, const uint32_t* __restrict__ cid, uint32_t m, int radius, uint32_t* __restrict__ nn) {
+k_ploc_nn(B2 t, const uint32_t* __restrict__ cid, const uint32_t* __restrict__ mPtr, int radius, uint32_t* __restrict__ nn) {
   __shared__ float sb[PLOC_THREADS + 2 * PLOC_MAX_RADIUS][6];
+  const uint32_t m = *mPtr;                                     // cluster count of this iteration lives on the device (no host round trip)
+  if (blockIdx.x * PLOC_THREADS >= m) return;                   // the grid is sized for an upper bound
   const int b0 = (int)(blockIdx.x * PLOC_THREADS) - radius;
   const int span = PLOC_THREADS + 2 * radius;
   for (int s = threadIdx.x; s < span; s += PLOC_THREADS) {
@@ -487,8 +489,10 @@ k_ploc_nn(B2 t, const uint32_t* __restrict__ cid, uint32_t m, int radius, uint32
 
 // merge mutual pairs (the lower position keeps the new cluster), flag survivors, count them per block
 __global__ void __launch_bounds__(PLOC_THREADS)
-k_ploc_merge(B2 t, uint32_t* __restrict__ cid, uint32_t m, const uint32_t* __restrict__ nn, uint32_t* __restrict__ keep,
+k_ploc_merge(B2 t, uint32_t* __restrict__ cid, const uint32_t* __restrict__ mPtr, const uint32_t* __restrict__ nn, uint32_t* __restrict__ keep,
              uint32_t* __restrict__ blockCount, uint32_t* nextInner, float costNode, float costTri, int maxLeafTris) {
+  const uint32_t m = *mPtr;
+  if (blockIdx.x * PLOC_THREADS >= m) return;                   // block-uniform: nobody reaches the barrier below
   const uint32_t i = blockIdx.x * PLOC_THREADS + threadIdx.x;
   bool alive = false;
   if (i < m) {
@@ -510,9 +514,12 @@ k_ploc_merge(B2 t, uint32_t* __restrict__ cid, uint32_t m, const uint32_t* __res
 
 // exclusive scan of the per-block survivor counts (one block), total to *total
 __global__ void __launch_bounds__(1024)
-k_ploc_scan(uint32_t* __restrict__ blockCount, uint32_t numBlocks, uint32_t* total) {
+k_ploc_scan(uint32_t* __restrict__ blockCount, const uint32_t* __restrict__ mPtr, uint32_t* total, uint32_t* iterations) {
   __shared__ uint32_t part[1024];
   __shared__ uint32_t carry;
+  const uint32_t m = *mPtr;
+  const uint32_t numBlocks = (m + PLOC_THREADS - 1) / PLOC_THREADS;
+  if (threadIdx.x == 0 && m > 1) atomicAdd(iterations, 1u);     // iterations that still had something to merge
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (uint32_t base = 0; base < numBlocks; base += 1024) {
@@ -535,9 +542,11 @@ k_ploc_scan(uint32_t* __restrict__ blockCount, uint32_t numBlocks, uint32_t* tot
 }
 
 __global__ void __launch_bounds__(PLOC_THREADS)
-k_ploc_compact(const uint32_t* __restrict__ cidIn, uint32_t m, const uint32_t* __restrict__ keep,
+k_ploc_compact(const uint32_t* __restrict__ cidIn, const uint32_t* __restrict__ mPtr, const uint32_t* __restrict__ keep,
                const uint32_t* __restrict__ blockOffset, uint32_t* __restrict__ cidOut) {
   __shared__ uint32_t warpSum[PLOC_THREADS / 32];
+  const uint32_t m = *mPtr;
+  if (blockIdx.x * PLOC_THREADS >= m) return;
   const uint32_t i = blockIdx.x * PLOC_THREADS + threadIdx.x;
   const bool alive = i < m && keep[i] != 0u;
   const unsigned bal = __ballot_sync(0xffffffffu, alive);
@@ -857,27 +866,38 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       if (P.builder == 1 && n > 1) {
         // ---- PLOC: iterate nearest-neighbour search / merge / compaction until one cluster is left ----
         const int radius = P.plocRadius < 1 ? 1 : (P.plocRadius > PLOC_MAX_RADIUS ? PLOC_MAX_RADIUS : P.plocRadius);
-        CK(cid0.alloc(n)); CK(cid1.alloc(n)); CK(nnBuf.alloc(n)); CK(blockCount.alloc(blocksFor(n, PLOC_THREADS) + 1)); CK(plocCtr.alloc(2));
-        const uint32_t initCtr[2] = {n - 2u, n};
+        CK(cid0.alloc(n)); CK(cid1.alloc(n)); CK(nnBuf.alloc(n)); CK(blockCount.alloc(blocksFor(n, PLOC_THREADS) + 1)); CK(plocCtr.alloc(4));
+        // counters on the device: [0] next inner node id, [1]/[2] cluster count of the current / next iteration (ping-pong),
+        // [3] iterations that merged something.  The host reads the count back only every few iterations (to shrink the
+        // grids and to detect the end); in between the kernels are launched for the last known upper bound.
+        const uint32_t initCtr[4] = {n - 2u, n, n, 0u};
         CK(cudaMemcpyAsync(plocCtr.p, initCtr, sizeof(initCtr), cudaMemcpyHostToDevice, stream));
         k_ploc_init<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costTri, cid0.p);
         rqCountLaunch(1);
         CK(cudaEventRecord(ev[3], stream));
         uint32_t m = n; uint32_t *cin = cid0.p, *cout = cid1.p;
+        uint32_t it = 0;
         while (m > 1) {
           const unsigned nb = blocksFor(m, PLOC_THREADS);
-          k_ploc_nn<<<nb, PLOC_THREADS, 0, stream>>>(t, cin, m, radius, nnBuf.p);
-          k_ploc_merge<<<nb, PLOC_THREADS, 0, stream>>>(t, cin, m, nnBuf.p, flag.p, blockCount.p, plocCtr.p, P.costNode, P.costTri, P.maxLeafTris);
-          k_ploc_scan<<<1, 1024, 0, stream>>>(blockCount.p, nb, plocCtr.p + 1);
-          k_ploc_compact<<<nb, PLOC_THREADS, 0, stream>>>(cin, m, flag.p, blockCount.p, cout);
-          rqCountLaunch(4);
+          const uint32_t window = m > (1u << 20) ? 2u : (m > (1u << 16) ? 4u : 8u);
+          for (uint32_t w = 0; w < window; w++, it++) {
+            uint32_t* mCur = plocCtr.p + 1 + (it & 1u);
+            uint32_t* mNext = plocCtr.p + 1 + ((it + 1u) & 1u);
+            k_ploc_nn<<<nb, PLOC_THREADS, 0, stream>>>(t, cin, mCur, radius, nnBuf.p);
+            k_ploc_merge<<<nb, PLOC_THREADS, 0, stream>>>(t, cin, mCur, nnBuf.p, flag.p, blockCount.p, plocCtr.p, P.costNode, P.costTri, P.maxLeafTris);
+            k_ploc_scan<<<1, 1024, 0, stream>>>(blockCount.p, mCur, mNext, plocCtr.p + 3);
+            k_ploc_compact<<<nb, PLOC_THREADS, 0, stream>>>(cin, mCur, flag.p, blockCount.p, cout);
+            rqCountLaunch(4);
+            std::swap(cin, cout);
+          }
           uint32_t next = 0;
-          CK(cudaMemcpyAsync(&next, plocCtr.p + 1, 4, cudaMemcpyDeviceToHost, stream));
+          CK(cudaMemcpyAsync(&next, plocCtr.p + 1 + (it & 1u), 4, cudaMemcpyDeviceToHost, stream));
           CK(cudaStreamSynchronize(stream));
           if (next >= m || next == 0) { err = (int)cudaErrorUnknown; goto fail; }   // every iteration merges at least the globally closest pair
-          m = next; plocIters++;
-          std::swap(cin, cout);
+          m = next;
+          if (it > 4096) { err = (int)cudaErrorUnknown; goto fail; }
         }
+        CK(cudaMemcpyAsync(&plocIters, plocCtr.p + 3, 4, cudaMemcpyDeviceToHost, stream));
         CK(cudaGetLastError());
       } else {
         if (n > 1) { k_hierarchy<<<blocksFor(n - 1, 256), 256, 0, stream>>>(keys0.p, (int)n, left.p, right.p, parent.p, rangeFirst.p); rqCountLaunch(1); }
