@@ -33,6 +33,7 @@ struct RQDeviceImage {
 int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const RQBuildParams* params,
                rqStream stream, RQDeviceImage* out, RQBuildStats* stats);
 void rqFreeImage(RQDeviceImage* img);
+int rqAllocImage(void** p, size_t bytes, rqStream stream);   // memory rqFreeImage can release (stream-ordered pool)
 
 // Refit (RTC_BUILD_QUALITY_REFIT, reference: kernels/bvh/bvh_refit.cpp, bvh_builder_twolevel.h:95-140):
 // the topology of `img` is kept; every triangle record re-reads its three vertices through the

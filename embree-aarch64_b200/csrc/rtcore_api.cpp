@@ -1442,10 +1442,10 @@ void adoptImage(Scene* s, const void* src, size_t bytes) {
       H.trisOffset + (uint64_t)H.numTris * sizeof(RQTri) > H.totalBytes)
     fail(RTC_ERROR_INVALID_ARGUMENT, "not a BVH image");
   void* p = nullptr;
-  cudaCheck(cudaMalloc(&p, bytes), "image alloc");
+  cudaCheck(rqAllocImage(&p, bytes, (rqStream)dev->stream()), "image alloc");
   int e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyDefault, dev->stream());
   if (!e) e = cudaStreamSynchronize(dev->stream());
-  if (e) { cudaFree(p); cudaCheck(e, "image copy"); }
+  if (e) { RQDeviceImage tmpImg; memset(&tmpImg, 0, sizeof(tmpImg)); tmpImg.base = p; rqFreeImage(&tmpImg); cudaCheck(e, "image copy"); }
   if (s->image.base) rqFreeImage(&s->image);
   if (s->dInstances) { cudaFree(s->dInstances); s->dInstances = nullptr; }
   s->numInstances = 0; s->clearInstanced(); s->epoch++;
