@@ -650,7 +650,11 @@ struct CompactCall {
 
 void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size_t stride, bool occluded, size_t recBytes) {
   std::lock_guard<std::mutex> l(dev->stageMutex);
-  const size_t chunk = dev->chunkRays;
+  // 1 M-ray chunks for long streams; a short stream is cut into ~8 pieces so that upload, kernel, list download and scatter
+  // of neighbouring pieces still overlap (configs[0], 1 M rays: one chunk = 239 Mrays/s end to end, profiles/r01x_c1.json)
+  size_t chunk = dev->chunkRays;
+  if ((size_t)M < 8 * chunk) chunk = std::max<size_t>(65536, (((size_t)M + 7) / 8 + 32767) & ~(size_t)32767);
+  if (chunk > dev->chunkRays) chunk = dev->chunkRays;
   if (!dev->countHost) cudaCheck(cudaMallocHost((void**)&dev->countHost, sizeof(unsigned) * Device::kRing), "hit counters");
   if (!dev->countDev) cudaCheck(cudaMalloc((void**)&dev->countDev, 32 * Device::kRing), "hit counters");
   for (int r = 0; r < Device::kRing; r++)
