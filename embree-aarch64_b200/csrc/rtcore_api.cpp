@@ -135,6 +135,25 @@ struct Device : RefCounted {
   void* packHost[kRing] = {nullptr, nullptr, nullptr, nullptr};
   size_t packCap[kRing] = {0, 0, 0, 0};
   std::atomic<unsigned long long> h2dBytes{0}, d2hBytes{0};   // bytes moved over PCIe by staged queries (rtcxGetTransferBytes)
+  // staging contexts for short host streams: one per concurrent caller, recycled through a free list
+  struct SmallStage { cudaStream_t stream = nullptr; void* buf = nullptr; size_t cap = 0; unsigned int* work = nullptr; };
+  std::vector<SmallStage*> smallFree, smallAll; std::mutex smallMutex;
+  SmallStage* acquireSmallStage() {
+    {
+      std::lock_guard<std::mutex> l(smallMutex);
+      if (!smallFree.empty()) { SmallStage* s = smallFree.back(); smallFree.pop_back(); return s; }
+    }
+    SmallStage* s = new SmallStage();
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc((void**)&s->work, 32) != cudaSuccess) {
+      if (s->stream) cudaStreamDestroy(s->stream);
+      delete s; cudaGetLastError();
+      throw rtc_error(RTC_ERROR_OUT_OF_MEMORY, "cannot create a staging context");
+    }
+    std::lock_guard<std::mutex> l(smallMutex);
+    smallAll.push_back(s);
+    return s;
+  }
+  void releaseSmallStage(SmallStage* s) { std::lock_guard<std::mutex> l(smallMutex); smallFree.push_back(s); }
   HostPool* pool = nullptr; std::mutex poolMutex;
   HostPool& hostPool() {
     std::lock_guard<std::mutex> l(poolMutex);
@@ -162,6 +181,7 @@ struct Device : RefCounted {
         if (evCount[i]) cudaEventDestroy(evCount[i]);
         if (evList[i]) cudaEventDestroy(evList[i]);
       }
+      for (SmallStage* s : smallAll) { if (s->buf) cudaFree(s->buf); if (s->work) cudaFree(s->work); if (s->stream) cudaStreamDestroy(s->stream); delete s; }
       if (countHost) cudaFreeHost(countHost);
       if (countDev) cudaFree(countDev);
       if (dCounters) cudaFree(dCounters);
@@ -780,6 +800,28 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
   } else if (dev->d2hMode == 3 && !mapped && !countersOut && !sc->numInstances && M >= 65536 && stride >= recBytes &&
              a.depth <= 32 + (unsigned)dev->stackSmem) {
     traceStreamCompact(dev, a, (char*)rays, M, stride, occluded, recBytes);
+  } else if (!mapped && !countersOut && M < 65536) {
+    // Short host streams (a tile of rays per call, many calling threads -- how the reference's tutorials drive rtcIntersect1M,
+    // viewer_stream_device.cpp:287-341): every call borrows its own (stream, buffer, cursor) from a free list, so concurrent
+    // callers overlap on the GPU instead of queueing behind one staging mutex.
+    Device::SmallStage* st = dev->acquireSmallStage();
+    try {
+      const size_t span = (size_t)(M - 1) * stride + recBytes;
+      if (st->cap < span) {
+        if (st->buf) cudaFree(st->buf);
+        st->buf = nullptr; st->cap = 0;
+        const size_t want = std::max<size_t>(span + 256, 1u << 20);
+        cudaCheck(cudaMalloc(&st->buf, want), "staging alloc");
+        st->cap = want - 256;
+      }
+      cudaCheck(cudaMemcpyAsync(st->buf, rays, span, cudaMemcpyHostToDevice, st->stream), "ray upload");
+      a.rays = st->buf; a.out = nullptr; a.numRays = M; a.stride = stride; a.workCounter = st->work;
+      cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)st->stream) : rqLaunchIntersect(&a, (rqStream)st->stream), "trace launch");
+      cudaCheck(cudaMemcpyAsync(rays, st->buf, span, cudaMemcpyDeviceToHost, st->stream), "hit download");
+      cudaCheck(cudaStreamSynchronize(st->stream), "trace");
+      dev->h2dBytes += span; dev->d2hBytes += span;
+    } catch (...) { cudaStreamSynchronize(st->stream); cudaGetLastError(); dev->releaseSmallStage(st); throw; }
+    dev->releaseSmallStage(st);
   } else {
     std::lock_guard<std::mutex> l(dev->stageMutex);     // host-staged calls of one device are serialised
     const size_t chunk = dev->chunkRays;
@@ -807,7 +849,7 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
       a.workCounter = dev->dWork + 8 * r;
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
       if (!mapped) {
-        if (dev->d2hMode && n > 1 && stride >= recBytes) {
+        if ((dev->d2hMode == 1 || dev->d2hMode == 2) && n > 1 && stride >= recBytes) {
           const size_t width = (occluded && dev->d2hMode == 2) ? 4 : recBytes - 32;
           cudaCheck(cudaMemcpy2DAsync(h + 32, stride, (char*)dev->ringBuf[r] + 32, stride, width, n, cudaMemcpyDeviceToHost, s), "hit download");
           dev->d2hBytes += (unsigned long long)width * n;

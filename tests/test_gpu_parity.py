@@ -460,6 +460,34 @@ def test_concurrent_queries_from_threads(product, gpu_device):
     product.lib.rtcReleaseScene(sc)
 
 
+def test_many_threads_small_tiles(product, gpu_device):
+    """Tile-sized calls from many threads (how the reference's stream tutorials drive rtcIntersect1M): every call takes its own
+    staging context, results equal the single big call, no errors."""
+    g = cases.load_golden("two_geoms")
+    sc, keep = build(product, gpu_device, g)
+    rays = np.tile(g["rays"], 12)                                          # 72 000 rays
+    want = rays.copy()
+    product.intersect(sc, want)
+    got = rays.copy()
+    occ_want = fx.to_ray(rays)
+    product.occluded(sc, occ_want)
+    occ_got = fx.to_ray(rays)
+    tile = 1024
+    tiles = [(i, min(i + tile, len(rays))) for i in range(0, len(rays), tile)]
+
+    def worker(k, nthreads):
+        for b, e in tiles[k::nthreads]:
+            product.intersect(sc, got[b:e])
+            product.occluded(sc, occ_got[b:e])
+    nthreads = 12
+    th = [threading.Thread(target=worker, args=(k, nthreads)) for k in range(nthreads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert np.array_equal(got, want) and np.array_equal(occ_got, occ_want)
+    assert product.lib.rtcGetDeviceError(gpu_device) == 0
+    product.lib.rtcReleaseScene(sc)
+
+
 def test_image_roundtrip_replica(product, gpu_device):
     """A byte copy of the flat BVH image is a usable replica (what the NVLink broadcast ships)."""
     import torch
