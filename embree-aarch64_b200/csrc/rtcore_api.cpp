@@ -125,6 +125,9 @@ struct Device : RefCounted {
   // it into the caller's buffer (default).  Same-box A/B (profiles/r01o_ab_d2h_rows.log, r01p2_ab_compact_pool.log):
   // 0 -> 662-668 Mrays/s end to end, 1 -> 463, 2 -> 446 (the copy engines handle 48-byte rows badly), 3 -> 804
   int d2hMode = 3;
+  // the compact path's stage hand-offs (two host callbacks + pool wake-ups per chunk) cost ~2 ms per call: below ~4 M rays the plain
+  // path with whole-span copies wins (configs[0], 1 M rays: 4.5 ms compact vs 2.35 ms plain; profiles/r01y_small_probe.log)
+  unsigned compactMinRays = 4u << 20;
   int scatterThreads = 8;                 // d2h=3: host threads that scatter hit lists (and pack rays); 0 = all hardware threads; at most 16
   // d2h=3: 0 = upload whole records (default), 1 = hybrid (pack while the pool has room, see traceStreamCompact), 2 = pack every chunk.
   // Same-box probe on configs[1] (profiles/r01r_e2e_probe.log, 16 host threads): 0 -> 777-804 Mrays/s, 1 -> 788-826, 2 -> 733-776:
@@ -243,6 +246,7 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "zerocopy") d->zeroCopy = atoi(v.c_str());
     else if (k == "refit") d->refitEnabled = atoi(v.c_str());
     else if (k == "d2h") d->d2hMode = atoi(v.c_str());
+    else if (k == "compact_min_rays") d->compactMinRays = (unsigned)std::max(0ll, atoll(v.c_str()));
     else if (k == "scatter_threads" || k == "host_threads") d->scatterThreads = atoi(v.c_str());
     else if (k == "pack_rays") d->packRays = atoi(v.c_str());
     else if (k == "pack_depth") d->packDepth = std::max(1, atoi(v.c_str()));
@@ -797,7 +801,7 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
     }
     if (!dev->async || countersOut || mapped) cudaCheck(cudaStreamSynchronize(s), "trace");
-  } else if (dev->d2hMode == 3 && !mapped && !countersOut && !sc->numInstances && M >= 65536 && stride >= recBytes &&
+  } else if (dev->d2hMode == 3 && !mapped && !countersOut && !sc->numInstances && M >= dev->compactMinRays && M >= 65536 && stride >= recBytes &&
              a.depth <= 32 + (unsigned)dev->stackSmem) {
     traceStreamCompact(dev, a, (char*)rays, M, stride, occluded, recBytes);
   } else if (!mapped && !countersOut && M < 65536) {
@@ -824,7 +828,10 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
     dev->releaseSmallStage(st);
   } else {
     std::lock_guard<std::mutex> l(dev->stageMutex);     // host-staged calls of one device are serialised
-    const size_t chunk = dev->chunkRays;
+    // 1 M-ray chunks for long streams, ~8 pieces for shorter ones so that the copies of neighbouring pieces overlap
+    // (configs[0], 1 M rays: 3.3 ms as one chunk, 2.35 ms in 128-256 K pieces; profiles/r01y_small_probe.log)
+    size_t chunk = dev->chunkRays;
+    if ((size_t)M < 8 * chunk) chunk = std::min(chunk, std::max<size_t>(65536, (((size_t)M + 7) / 8 + 32767) & ~(size_t)32767));
     unsigned done = 0; int slot = 0;
     while (done < M) {
       const unsigned n = (unsigned)std::min<size_t>(chunk, M - done);

@@ -315,8 +315,9 @@ def test_hit_download_modes(product, mode):
     oref = fx.to_ray(rays)
     product.occluded(sc0, oref)
     cfgs = [f"d2h={mode}", f"d2h={mode},chunk_rays=50000", f"d2h={mode},chunk_rays=70001"]
-    if mode == 3:
-        cfgs += ["d2h=3,pack_rays=0", "d2h=3,host_threads=3,chunk_rays=33333", "d2h=3,host_threads=1"]
+    if mode == 3:                                                        # compact_min_rays: engage the compact path on this 200 K-ray stream
+        cfgs = [c + ",compact_min_rays=0" for c in cfgs] + ["d2h=3"]
+        cfgs += [c + ",compact_min_rays=0" for c in ("d2h=3,pack_rays=1", "d2h=3,pack_rays=2,host_threads=3,chunk_rays=33333", "d2h=3,host_threads=1")]
     for cfg in cfgs:
         dev = product.new_device(cfg)
         sc, keep = build(product, dev, g)
