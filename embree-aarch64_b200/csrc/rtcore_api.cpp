@@ -569,6 +569,7 @@ inline void packRay32(const char* s, char* d) {
 //   callback 1  : (CUDA thread, no CUDA calls allowed) asks the pool to fetch the list: count is known now
 //   pool        : enqueues the list download + callback 2
 //   callback 2  : hands the scatter slices to the pool; the last slice frees the slot
+// (An event-polling progress thread in place of the two callbacks was tried: same timings, and it deadlocks a one-thread pool.)
 struct CompactCall;
 struct CompactChunk {
   CompactCall* call; int slot; char* h; unsigned n; unsigned count; unsigned packLeft; unsigned scatterLeft; unsigned packParts; bool packed;
