@@ -569,11 +569,10 @@ inline void packRay32(const char* s, char* d) {
 //   callback 1  : (CUDA thread, no CUDA calls allowed) asks the pool to fetch the list: count is known now
 //   pool        : enqueues the list download + callback 2
 //   callback 2  : hands the scatter slices to the pool; the last slice frees the slot
-// (An event-polling progress thread in place of the two callbacks was tried: same timings, and it deadlocks a one-thread pool.)
+// (An event-polling progress thread in place of the two callbacks was tried: same timings, and it starves a one-thread pool.)
 struct CompactCall;
 struct CompactChunk {
   CompactCall* call; int slot; char* h; unsigned n; unsigned count; unsigned packLeft; unsigned scatterLeft; unsigned packParts; bool packed;
-  int stage;                                                    // 0 = waiting for the hit count, 1 = waiting for the hit list
 };
 struct CompactCall {
   Device* dev; RQTraceArgs a; size_t stride; bool occluded, pack; size_t recBytes, recList; unsigned T;
@@ -581,40 +580,6 @@ struct CompactCall {
   bool slotBusy[Device::kRing] = {false, false, false, false};
   int pending = 0; unsigned chunksDone = 0; int error = 0;
   int packing = 0;                                              // chunks whose pack slices are still queued or running
-  // Stage hand-offs: one pool thread polls the chunks' events (cudaEventQuery) while the call is active and starts the next stage
-  // the moment an event completes.  cudaLaunchHostFunc callbacks did the same job with ~0.3 ms per hop (a 1 M-ray call took
-  // 4.5 ms instead of ~2; profiles/r01y_small_probe.log).
-  std::vector<CompactChunk*> watch;                             // chunks with an event pending
-  unsigned outstanding = 0;                                     // chunks issued that have not reached the scatter stage yet
-  bool closing = false;                                         // the caller has issued its last chunk
-  void progressLoop() {
-    cudaSetDevice(dev->ordinal);
-    std::vector<CompactChunk*> snap;
-    for (;;) {
-      {
-        std::lock_guard<std::mutex> lk(m);
-        if (closing && outstanding == 0) return;
-        snap = watch;
-      }
-      bool progressed = false;
-      for (CompactChunk* c : snap) {
-        const cudaError_t q = cudaEventQuery(c->stage == 0 ? dev->evCount[c->slot] : dev->evList[c->slot]);
-        if (q == cudaErrorNotReady) continue;
-        { std::lock_guard<std::mutex> lk(m); for (size_t i = 0; i < watch.size(); i++) if (watch[i] == c) { watch.erase(watch.begin() + (long)i); break; } }
-        progressed = true;
-        if (q != cudaSuccess) { fail((int)q); retire(c); chunkDone(c); continue; }
-        if (c->stage == 0) fetchList(c); else startScatter(c);
-      }
-      if (!progressed) {
-#if defined(__SSE2__)
-        _mm_pause();
-#endif
-        std::this_thread::yield();
-      }
-    }
-  }
-  void retire(CompactChunk*) { std::lock_guard<std::mutex> lk(m); if (outstanding) outstanding--; }
-  void watchFor(CompactChunk* c, int stage) { std::lock_guard<std::mutex> lk(m); c->stage = stage; watch.push_back(c); }
   void submit(std::function<void()> fn) {
     { std::lock_guard<std::mutex> lk(m); pending++; }
     dev->hostPool().submit([this, fn] { fn(); std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv.notify_all(); });
@@ -633,6 +598,8 @@ struct CompactCall {
     { std::lock_guard<std::mutex> lk(m); last = (--c->packLeft == 0); if (last) { packing--; cv.notify_all(); } }
     if (last) enqueue(c);
   }
+  static void CUDART_CB onCount(void* p) { CompactChunk* c = (CompactChunk*)p; c->call->submit([c] { c->call->fetchList(c); }); }
+  static void CUDART_CB onList(void* p) { CompactChunk* c = (CompactChunk*)p; c->call->startScatter(c); }
 
   void enqueue(CompactChunk* c) {                               // any thread
     cudaSetDevice(dev->ordinal);
@@ -655,12 +622,11 @@ struct CompactCall {
     x.hitList = dev->listDev[r]; x.hitCount = dev->countDev + 8 * r;
     if (!e) e = occluded ? rqLaunchOccluded(&x, (rqStream)s) : rqLaunchIntersect(&x, (rqStream)s);
     if (!e) e = cudaMemcpyAsync(&dev->countHost[r], x.hitCount, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
-    if (!e) e = cudaEventRecord(dev->evCount[r], s);
-    if (e) { fail(e); retire(c); chunkDone(c); return; }
-    watchFor(c, 0);
+    if (!e) e = cudaLaunchHostFunc(s, onCount, c);
+    if (e) { fail(e); chunkDone(c); }
   }
-  void fetchList(CompactChunk* c) {                             // progress thread, the kernel of this chunk has finished
-
+  void fetchList(CompactChunk* c) {                             // pool thread, the kernel of this chunk has finished
+    cudaSetDevice(dev->ordinal);
     const int r = c->slot;
     cudaStream_t s = dev->ringStream[r];
     c->count = std::min(dev->countHost[r], c->n);
@@ -670,12 +636,10 @@ struct CompactCall {
       dev->d2hBytes += (unsigned long long)c->count * recList;
     }
     dev->d2hBytes += sizeof(unsigned);
-    if (!e) e = cudaEventRecord(dev->evList[r], s);
-    if (e) { fail(e); retire(c); chunkDone(c); return; }
-    watchFor(c, 1);
+    if (!e) e = cudaLaunchHostFunc(s, onList, c);
+    if (e) { fail(e); chunkDone(c); }
   }
-  void startScatter(CompactChunk* c) {                          // progress thread: the list is in host memory, only queues work
-    retire(c);
+  void startScatter(CompactChunk* c) {                          // CUDA callback thread: only queues work
     const unsigned per = std::max(8192u, (c->count + T - 1) / T);
     const unsigned parts = std::max(1u, (c->count + per - 1) / per);
     { std::lock_guard<std::mutex> lk(m); c->scatterLeft = parts; }
@@ -718,11 +682,8 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
   if (chunk > dev->chunkRays) chunk = dev->chunkRays;
   if (!dev->countHost) cudaCheck(cudaMallocHost((void**)&dev->countHost, sizeof(unsigned) * Device::kRing), "hit counters");
   if (!dev->countDev) cudaCheck(cudaMalloc((void**)&dev->countDev, 32 * Device::kRing), "hit counters");
-  for (int r = 0; r < Device::kRing; r++) {
+  for (int r = 0; r < Device::kRing; r++)
     if (!dev->ringStream[r]) cudaCheck(cudaStreamCreateWithFlags(&dev->ringStream[r], cudaStreamNonBlocking), "stream");
-    if (!dev->evCount[r]) cudaCheck(cudaEventCreateWithFlags(&dev->evCount[r], cudaEventDisableTiming), "event");
-    if (!dev->evList[r]) cudaCheck(cudaEventCreateWithFlags(&dev->evList[r], cudaEventDisableTiming), "event");
-  }
   CompactCall call;
   call.dev = dev; call.a = a; call.stride = stride; call.occluded = occluded; call.pack = dev->packRays != 0;
   call.recBytes = recBytes; call.recList = occluded ? 4 : 48; call.T = (unsigned)dev->hostPool().size();
@@ -734,10 +695,8 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
   unsigned issued = 0;
   auto finish = [&] {                                           // every issued chunk done and no closure of this call left
     std::unique_lock<std::mutex> lk(call.m);
-    call.closing = true;
     call.cv.wait(lk, [&] { return call.chunksDone == issued && call.pending == 0; });
   };
-  call.submit([&call] { call.progressLoop(); });
   try {
     unsigned done = 0;
     for (unsigned i = 0; i < numChunks; i++) {
@@ -781,7 +740,6 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
         c->packed = call.pack && (dev->packRays >= 2 || call.packing < dev->packDepth);
         if (c->packed) call.packing++;
         call.slotBusy[r] = true;
-        call.outstanding++;
       }
       c->packParts = c->packed ? std::max(1u, std::min(2 * call.T, (n + 16383u) / 16384u)) : 1u;
       c->packLeft = c->packParts;
