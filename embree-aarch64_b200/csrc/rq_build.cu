@@ -96,6 +96,19 @@ k_setup_prims(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t N,
         t.pad = RQ_PAD_INSTANCE | G.instIndex;
         for (int k = 0; k < 3; k++) { lo[k] = G.lo[k]; hi[k] = G.hi[k]; clo[k] = chi[k] = 0.5f * lo[k] + 0.5f * hi[k]; }
       }
+    } else if (G.type == 2u) {
+      // quad q = two triangles (v0,v1,v3) and (v2,v3,v1); the quad is dropped as a whole unless all four vertices are valid
+      // (scene_quad_mesh.h:131-154)
+      const uint32_t* ip = (const uint32_t*)(G.indices + (size_t)(local >> 1) * G.indexStride);
+      const uint32_t q0 = ip[0], q1 = ip[1], q2 = ip[2], q3 = ip[3];
+      t.primID = local >> 1;
+      if (q0 < G.numVerts && q1 < G.numVerts && q2 < G.numVerts && q3 < G.numVerts) {
+        const uint32_t other = (local & 1u) ? q0 : q2;         // the vertex this half does not use must be valid too
+        const float* po = (const float*)(G.vertices + (size_t)other * G.vertexStride);
+        bool ov = true;
+        for (int k = 0; k < 3; k++) ov &= (po[k] > -RQ_FLT_LARGE) & (po[k] < RQ_FLT_LARGE);
+        if (ov) { if (local & 1u) { i0 = q2; i1 = q3; i2 = q1; } else { i0 = q0; i1 = q1; i2 = q3; } }
+      }
     } else {
       const uint32_t* ip = (const uint32_t*)(G.indices + (size_t)local * G.indexStride);
       i0 = ip[0]; i1 = ip[1]; i2 = ip[2];
@@ -112,7 +125,7 @@ k_setup_prims(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t N,
         valid &= (t.v2[k] > -RQ_FLT_LARGE) & (t.v2[k] < RQ_FLT_LARGE);
       }
       if (valid) {
-        t.pad = 0;
+        t.pad = (G.type == 2u && (local & 1u)) ? RQ_PAD_FLIPUV : 0u;
         for (int k = 0; k < 3; k++) {
           lo[k] = fminf(fminf(t.v0[k], t.v1[k]), t.v2[k]);
           hi[k] = fmaxf(fmaxf(t.v0[k], t.v1[k]), t.v2[k]);
@@ -1014,12 +1027,28 @@ k_refit_tris(const RQGeomDesc* __restrict__ geomsByID, uint32_t numSlots, RQTri*
   const uint32_t odd = i & 1u;                                  // odd records: last 16 bytes first (rq_types.h)
   const float4 c = rec[odd ? 0 : 2];
   const uint32_t primID = __float_as_uint(c.y), geomID = __float_as_uint(c.z);
-  if (__float_as_uint(c.w) != 0u) return;                       // instance records keep their box (a moved instance forces a rebuild)
+  const uint32_t pad = __float_as_uint(c.w);
+  if (pad & RQ_PAD_INSTANCE) return;                            // instance records keep their box (a moved instance forces a rebuild)
   if (geomID >= numSlots) return;
   const RQGeomDesc G = geomsByID[geomID];
-  if (primID >= G.numTris || G.indices == nullptr || G.vertices == nullptr) return;
-  const uint32_t* ip = (const uint32_t*)(G.indices + (size_t)primID * G.indexStride);
-  const uint32_t i0 = ip[0], i1 = ip[1], i2 = ip[2];
+  if (G.indices == nullptr || G.vertices == nullptr) return;
+  uint32_t i0 = RQ_INVALID, i1 = RQ_INVALID, i2 = RQ_INVALID;
+  if (G.type == 2u) {
+    if (2u * primID >= G.numTris) return;
+    const uint32_t* ip = (const uint32_t*)(G.indices + (size_t)primID * G.indexStride);
+    const uint32_t q0 = ip[0], q1 = ip[1], q2 = ip[2], q3 = ip[3];
+    if (q0 < G.numVerts && q1 < G.numVerts && q2 < G.numVerts && q3 < G.numVerts) {
+      const uint32_t other = (pad & RQ_PAD_FLIPUV) ? q0 : q2;
+      const float* po = (const float*)(G.vertices + (size_t)other * G.vertexStride);
+      bool ov = true;
+      for (int k = 0; k < 3; k++) ov &= (po[k] > -RQ_FLT_LARGE) & (po[k] < RQ_FLT_LARGE);
+      if (ov) { if (pad & RQ_PAD_FLIPUV) { i0 = q2; i1 = q3; i2 = q1; } else { i0 = q0; i1 = q1; i2 = q3; } }
+    }
+  } else {
+    if (primID >= G.numTris) return;
+    const uint32_t* ip = (const uint32_t*)(G.indices + (size_t)primID * G.indexStride);
+    i0 = ip[0]; i1 = ip[1]; i2 = ip[2];
+  }
   const float qnan = __uint_as_float(0x7FC00000u);
   float v[9] = {qnan, qnan, qnan, qnan, qnan, qnan, qnan, qnan, qnan};
   if (i0 < G.numVerts && i1 < G.numVerts && i2 < G.numVerts) {

@@ -277,6 +277,9 @@ k_trace(const TraceParams P) {
             if (OCCLUDED) { tmask = 0u; ng.y = 0u; sp = 0; if (INST) curInst = RQ_INVALID; }    // any hit ends the ray (finishes in the N phase)
             else {
               tfar = h.t; hu = h.u; hv = h.v; hNg = h.Ng;
+              if (__float_as_uint(t2.w) & RQ_PAD_FLIPUV) {       // second triangle of a quad (quad_intersector_moeller.h:28-37)
+                hu = 1.0f - fminf(hu, 1.0f); hv = 1.0f - fminf(hv, 1.0f);
+              }
               hPrim = __float_as_uint(t2.y); hGeom = __float_as_uint(t2.z);
               if (INST) hInst = (curInst != RQ_INVALID) ? curInst : P.instID0;
             }

@@ -63,6 +63,9 @@ static_assert(sizeof(RQTri) == 48, "RQTri must be 48 bytes");
 // RQ_PAD_INSTANCE | i stands for instances[i]; its v0 / v1 hold the world-space bounds.
 #define RQ_PAD_INVALID  1u
 #define RQ_PAD_INSTANCE 0x80000000u
+// second triangle (v2, v3, v1) of a quad (RTC_GEOMETRY_TYPE_QUAD): a hit reports u = 1 - u, v = 1 - v and the quad's primID
+// (kernels/geometry/quad_intersector_moeller.h:122-144, quad_intersector_pluecker.h:179-180)
+#define RQ_PAD_FLIPUV   0x40000000u
 struct alignas(16) RQInstance {
   float    w2l[12];         // world -> instance space, column major: vx, vy, vz, p (AffineSpace3fa)
   uint64_t nodes;           // device address of the instanced scene's RQNode array
@@ -83,7 +86,8 @@ struct RQGeomDesc {
   uint32_t numVerts;
   uint32_t primBase;         // first global primitive number of this mesh
   uint32_t geomID;
-  uint32_t type;             // 0 = triangle mesh; 1 = instance: one primitive with the bounds below (numTris = 1)
+  uint32_t type;             // 0 = triangle mesh; 1 = instance: one primitive with the bounds below (numTris = 1);
+                             // 2 = quad mesh: RTC_FORMAT_UINT4 index records, numTris = 2 x quads (triangle 2q = (v0,v1,v3), 2q+1 = (v2,v3,v1))
   uint32_t instIndex;        // index into the scene's RQInstance table
   float    lo[3], hi[3];     // instance only: world-space bounds = xfmBounds(local2world, bounds of the instanced scene)
 };

@@ -458,12 +458,14 @@ void commitScene(Scene* sc) {
       if (!g->enabled || g->indices.count == 0) continue;
       RQGeomDesc d; memset(&d, 0, sizeof(d));
       const char* ip = g->indices.data(); const char* vp = g->vertices.data();
-      const size_t ibytes = (size_t)(g->indices.count - 1) * g->indices.stride + 12;
+      const bool quad = g->type == RTC_GEOMETRY_TYPE_QUAD;   // two triangles per quad: (v0,v1,v3), (v2,v3,v1)
+      const size_t ibytes = (size_t)(g->indices.count - 1) * g->indices.stride + (quad ? 16 : 12);
       const size_t vbytes = g->vertices.count ? (size_t)(g->vertices.count - 1) * g->vertices.stride + 12 : 0;
       d.indices = isDevicePointer(ip) ? (const uint8_t*)ip : tmp.upload(ip, ibytes, s);
       d.vertices = (vp && isDevicePointer(vp)) ? (const uint8_t*)vp : tmp.upload(vp, vbytes, s);
       d.indexStride = (uint32_t)g->indices.stride; d.vertexStride = (uint32_t)g->vertices.stride;
-      d.numTris = g->indices.count; d.numVerts = g->vertices.count; d.geomID = (uint32_t)i;
+      d.numTris = quad ? 2u * g->indices.count : g->indices.count; d.numVerts = g->vertices.count; d.geomID = (uint32_t)i;
+      d.type = quad ? 2u : 0u;
       descs.push_back(d);
     }
   }
@@ -1052,8 +1054,8 @@ RTC_API RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
   Device* d = (Device*)h;
   RTC_TRY
     VERIFY_HANDLE(h);
-    if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_INSTANCE)
-      fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE and RTC_GEOMETRY_TYPE_INSTANCE are supported by the B200 ray-query device");
+    if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE)
+      fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD and _INSTANCE are supported by the B200 ray-query device");
     return (RTCGeometry) new Geometry(d, type);
   RTC_CATCH(d)
   return nullptr;
@@ -1082,7 +1084,7 @@ RTC_API void rtcSetGeometryBuildQuality(RTCGeometry h, enum RTCBuildQuality q) {
 
 namespace {
 void setBuffer(Geometry* g, RTCBufferType type, unsigned slot, RTCFormat format, Buffer* buf, size_t offset, size_t stride, unsigned num) {
-  if (g->type != RTC_GEOMETRY_TYPE_TRIANGLE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
+  if (g->type != RTC_GEOMETRY_TYPE_TRIANGLE && g->type != RTC_GEOMETRY_TYPE_QUAD) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
   if ((((size_t)buf->ptr + offset) & 3) || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
   if (type == RTC_BUFFER_TYPE_VERTEX) {
     if (format != RTC_FORMAT_FLOAT3) fail(RTC_ERROR_INVALID_OPERATION, "invalid vertex buffer format");
@@ -1091,7 +1093,8 @@ void setBuffer(Geometry* g, RTCBufferType type, unsigned slot, RTCFormat format,
     g->vertices.set(buf, offset, stride, num, format);
   } else if (type == RTC_BUFFER_TYPE_INDEX) {
     if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot");
-    if (format != RTC_FORMAT_UINT3) fail(RTC_ERROR_INVALID_OPERATION, "invalid index buffer format");
+    if (format != (g->type == RTC_GEOMETRY_TYPE_QUAD ? RTC_FORMAT_UINT4 : RTC_FORMAT_UINT3))
+      fail(RTC_ERROR_INVALID_OPERATION, "invalid index buffer format");   // scene_triangle_mesh.cpp:62, scene_quad_mesh.cpp:62
     g->indices.set(buf, offset, stride, num, format);
   } else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) {
     fail(RTC_ERROR_INVALID_OPERATION, "vertex attributes are not supported by the B200 ray-query device");

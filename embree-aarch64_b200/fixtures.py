@@ -34,6 +34,15 @@ def triangle_plane(p0, dx, dy, width, height):
     return v, t
 
 
+def quad_plane(p0, dx, dy, width, height):
+    """Same grid as triangle_plane, one RTC_GEOMETRY_TYPE_QUAD per cell (v0..v3 counter-clockwise: p00, p01, p11, p10)."""
+    v, _ = triangle_plane(p0, dx, dy, width, height)
+    y, x = np.meshgrid(np.arange(height, dtype=np.int64), np.arange(width, dtype=np.int64), indexing="ij")
+    p00 = (y * (width + 1) + x).ravel()
+    q = np.stack([p00, p00 + 1, p00 + (width + 1) + 1, p00 + (width + 1)], axis=1).astype(np.uint32)
+    return v, q
+
+
 def triangle_sphere(center, radius, num_phi):
     num_theta = 2 * num_phi
     phi = np.arange(num_phi + 1, dtype=np.float32) * np.float32(np.pi) * np.float32(1.0 / num_phi)
@@ -154,7 +163,8 @@ def random_soup(n, seed=7):
 
 
 def num_tris(meshes):
-    return int(sum(len(t) for _, t in meshes))
+    """Triangles the builder sees: a quad (4-index record) counts as two."""
+    return int(sum(len(t) * (2 if (np.ndim(t) == 2 and np.shape(t)[1] == 4) else 1) for _, t in meshes))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@ PRODUCT_LIB = os.path.join(HERE, "lib", "libembree3.so")
 
 RTC_INVALID_GEOMETRY_ID = 0xFFFFFFFF
 RTC_FORMAT_UINT3 = 0x5003
+RTC_FORMAT_UINT4 = 0x5004
 RTC_FORMAT_FLOAT3 = 0x9003
 RTC_BUFFER_TYPE_INDEX = 0
 RTC_BUFFER_TYPE_VERTEX = 1
@@ -178,15 +179,17 @@ class RTCore:
         return c
 
     def add_mesh(self, device, scene, vertices, triangles, keep=None):
-        """Attach a triangle mesh through shared buffers.  vertices (n,3) float32 (a 16-byte tail pad
-        is added as the API demands), triangles (m,3) uint32.  Returns (geomID, geometry handle)."""
+        """Attach a triangle mesh -- or, for an (m,4) index array, a quad mesh -- through shared buffers.  vertices (n,3)
+        float32 (a 16-byte tail pad is added as the API demands), triangles (m,3) uint32.  Returns (geomID, geometry handle)."""
         v = np.ascontiguousarray(vertices, dtype=np.float32)
         t = np.ascontiguousarray(triangles, dtype=np.uint32)
         vpad = np.zeros(v.size + 4, dtype=np.float32)
         vpad[:v.size] = v.ravel()
-        g = self.lib.rtcNewGeometry(device, RTC_GEOMETRY_TYPE_TRIANGLE)
+        quads = t.ndim == 2 and t.shape[1] == 4
+        g = self.lib.rtcNewGeometry(device, RTC_GEOMETRY_TYPE_QUAD if quads else RTC_GEOMETRY_TYPE_TRIANGLE)
         self.lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, vpad.ctypes.data, 0, 12, len(v))
-        self.lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT3, t.ctypes.data, 0, 12, len(t))
+        self.lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT4 if quads else RTC_FORMAT_UINT3, t.ctypes.data, 0,
+                                            16 if quads else 12, len(t))
         self.lib.rtcCommitGeometry(g)
         gid = self.lib.rtcAttachGeometry(scene, g)
         if keep is not None:

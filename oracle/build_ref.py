@@ -9,7 +9,7 @@ This is our own recipe, not the reference's build system: the reference's CMake 
 run.  The sources are compiled where they lie under /root/reference with plain g++; the three
 small configuration headers CMake would have generated from `kernels/config.h.in`,
 `kernels/rtcore_config.h.in` and `kernels/hash.h.in` are written by this script into
-oracle/_ref/gen/ (only #define lines: triangle and instance geometry only, ray packets on, filter functions
+oracle/_ref/gen/ (only #define lines: triangle, quad and instance geometry only, ray packets on, filter functions
 on, ray masks off, backface culling off -- the reference's defaults, CMakeLists.txt:155-179).
 All outputs go to oracle/_ref/ (git-ignored, but shipped to the GPU box by gpurun).
 
@@ -118,12 +118,13 @@ bvh/bvh_builder_twolevel""".split()
 CONFIG_H = """// written by oracle/build_ref.py (stands in for the CMake-configured kernels/config.h)
 #define EMBREE_FILTER_FUNCTION
 #define EMBREE_GEOMETRY_TRIANGLE
+#define EMBREE_GEOMETRY_QUAD
 #define EMBREE_GEOMETRY_INSTANCE
 #define EMBREE_RAY_PACKETS
 {stat}
 #define EMBREE_CURVE_SELF_INTERSECTION_AVOIDANCE_FACTOR 2.0
 #define IF_ENABLED_TRIS(x) x
-#define IF_ENABLED_QUADS(x)
+#define IF_ENABLED_QUADS(x) x
 #define IF_ENABLED_CURVES_OR_POINTS(x)
 #define IF_ENABLED_CURVES(x)
 #define IF_ENABLED_POINTS(x)

@@ -54,7 +54,7 @@ static inline float box_half_area(const box3* b) { return half_area(vsub(b->hi, 
 static inline float comp(v3 a, int d) { return d == 0 ? a.x : d == 1 ? a.y : a.z; }
 
 /* ------------------------------------------------------------------------------------------ */
-typedef struct { v3 v0, v1, v2; uint32_t primID, geomID; } tri_t;
+typedef struct { v3 v0, v1, v2; uint32_t primID, geomID, flip; } tri_t;   /* flip: second triangle (v2,v3,v1) of a quad */
 typedef struct { box3 b; uint32_t tri; } primref_t;                 /* kernels/common/primref.h:11-105 */
 
 typedef struct node_s {
@@ -225,25 +225,46 @@ static void stat_rec(scene_t* sc, const node_t* nd, const box3* b) {
 }
 static void free_rec(node_t* nd) { if (!nd) return; for (int i = 0; i < nd->nchild; i++) free_rec(nd->child[i]); free(nd); }
 
-typedef struct { const void* indices; const void* vertices; uint32_t indexStride, vertexStride, numTris, numVerts, geomID; } rqo_mesh;
+/* quads != 0: RTC_GEOMETRY_TYPE_QUAD, `indices` holds numTris records of FOUR vertex indices; a quad is intersected as the
+ * triangles (v0,v1,v3) and (v2,v3,v1), the second reporting u = 1 - u, v = 1 - v (kernels/geometry/quad_intersector_moeller.h:122-144,
+ * quad_intersector_pluecker.h:179-180; hit finalisation :28-37 / :34-43), and is dropped as a whole unless all four vertices are
+ * valid (kernels/common/scene_quad_mesh.h:131-154) */
+typedef struct { const void* indices; const void* vertices; uint32_t indexStride, vertexStride, numTris, numVerts, geomID, quads; } rqo_mesh;
 
 RQO_API void* rqo_build(const rqo_mesh* meshes, int nmeshes, int robust) {
   scene_t* sc = (scene_t*)calloc(1, sizeof(scene_t));
   sc->robust = robust; sc->bounds = box_empty();
   uint64_t total = 0;
-  for (int m = 0; m < nmeshes; m++) total += meshes[m].numTris;
+  for (int m = 0; m < nmeshes; m++) total += (uint64_t)meshes[m].numTris * (meshes[m].quads ? 2 : 1);
   tri_t* src = (tri_t*)malloc(sizeof(tri_t) * (total ? total : 1));
   primref_t* pr = (primref_t*)malloc(sizeof(primref_t) * (total ? total : 1));
   uint32_t n = 0;
   for (int m = 0; m < nmeshes; m++) {                            /* builders/primrefgen.cpp:35-57 */
     const rqo_mesh* M = &meshes[m];
-    for (uint32_t i = 0; i < M->numTris; i++) {
+    for (uint32_t i = 0; i < M->numTris && M->quads; i++) {
+      const uint32_t* ix = (const uint32_t*)((const char*)M->indices + (size_t)i * M->indexStride);
+      if (ix[0] >= M->numVerts || ix[1] >= M->numVerts || ix[2] >= M->numVerts || ix[3] >= M->numVerts) continue;
+      v3 q[4]; int okq = 1;
+      for (int k = 0; k < 4; k++) {
+        const float* p = (const float*)((const char*)M->vertices + (size_t)ix[k] * M->vertexStride);
+        q[k] = V(p[0], p[1], p[2]); okq &= vertex_valid(q[k]);
+      }
+      if (!okq) continue;
+      for (int half = 0; half < 2; half++) {
+        tri_t t; t.primID = i; t.geomID = M->geomID; t.flip = (uint32_t)half;
+        if (half == 0) { t.v0 = q[0]; t.v1 = q[1]; t.v2 = q[3]; } else { t.v0 = q[2]; t.v1 = q[3]; t.v2 = q[1]; }
+        box3 bx; bx.lo = V(fminf(fminf(t.v0.x, t.v1.x), t.v2.x), fminf(fminf(t.v0.y, t.v1.y), t.v2.y), fminf(fminf(t.v0.z, t.v1.z), t.v2.z));
+        bx.hi = V(fmaxf(fmaxf(t.v0.x, t.v1.x), t.v2.x), fmaxf(fmaxf(t.v0.y, t.v1.y), t.v2.y), fmaxf(fmaxf(t.v0.z, t.v1.z), t.v2.z));
+        src[n] = t; pr[n].b = bx; pr[n].tri = n; n++;
+      }
+    }
+    for (uint32_t i = 0; i < M->numTris && !M->quads; i++) {
       const uint32_t* ix = (const uint32_t*)((const char*)M->indices + (size_t)i * M->indexStride);
       if (ix[0] >= M->numVerts || ix[1] >= M->numVerts || ix[2] >= M->numVerts) continue;
       const float* a = (const float*)((const char*)M->vertices + (size_t)ix[0] * M->vertexStride);
       const float* b = (const float*)((const char*)M->vertices + (size_t)ix[1] * M->vertexStride);
       const float* c = (const float*)((const char*)M->vertices + (size_t)ix[2] * M->vertexStride);
-      tri_t t; t.v0 = V(a[0], a[1], a[2]); t.v1 = V(b[0], b[1], b[2]); t.v2 = V(c[0], c[1], c[2]); t.primID = i; t.geomID = M->geomID;
+      tri_t t; t.v0 = V(a[0], a[1], a[2]); t.v1 = V(b[0], b[1], b[2]); t.v2 = V(c[0], c[1], c[2]); t.primID = i; t.geomID = M->geomID; t.flip = 0;
       if (!vertex_valid(t.v0) || !vertex_valid(t.v1) || !vertex_valid(t.v2)) continue;
       box3 bx; bx.lo = V(fminf(fminf(t.v0.x, t.v1.x), t.v2.x), fminf(fminf(t.v0.y, t.v1.y), t.v2.y), fminf(fminf(t.v0.z, t.v1.z), t.v2.z));
       bx.hi = V(fmaxf(fmaxf(t.v0.x, t.v1.x), t.v2.x), fmaxf(fmaxf(t.v0.y, t.v1.y), t.v2.y), fmaxf(fmaxf(t.v0.z, t.v1.z), t.v2.z));
@@ -362,6 +383,7 @@ static int trace_one(const scene_t* sc, ray_t* ray, rhit_t* hit, int occluded, u
         if (occluded) return 1;
         /* epilog, kernels/geometry/intersector_epilog.h:280-290 */
         ray->tfar = o[0]; hit->u = o[1]; hit->v = o[2]; hit->Ng_x = o[3]; hit->Ng_y = o[4]; hit->Ng_z = o[5];
+        if (t->flip) { hit->u = 1.0f - fminf(hit->u, 1.0f); hit->v = 1.0f - fminf(hit->v, 1.0f); }   /* quad_intersector_moeller.h:28-37 */
         hit->primID = t->primID; hit->geomID = t->geomID; hit->instID = instID;
       }
       continue;

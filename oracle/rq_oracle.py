@@ -13,7 +13,7 @@ REF_LIB = os.path.join(HERE, "_ref", "libembree3_ref.so")
 
 class _Mesh(C.Structure):
     _fields_ = [("indices", C.c_void_p), ("vertices", C.c_void_p), ("indexStride", C.c_uint), ("vertexStride", C.c_uint),
-                ("numTris", C.c_uint), ("numVerts", C.c_uint), ("geomID", C.c_uint)]
+                ("numTris", C.c_uint), ("numVerts", C.c_uint), ("geomID", C.c_uint), ("quads", C.c_uint)]
 
 
 class _Instance(C.Structure):
@@ -52,14 +52,15 @@ class Oracle:
             f.argtypes = [fp, fp, C.c_float, C.c_float, fp, fp, fp, fp]
 
     def build(self, meshes, robust=False, geom_ids=None):
-        """meshes: list of (vertices (n,3) f32, triangles (m,3) u32)."""
+        """meshes: list of (vertices (n,3) f32, triangles (m,3) u32) -- or quads (m,4) u32: RTC_GEOMETRY_TYPE_QUAD."""
         arr = (_Mesh * max(len(meshes), 1))()
         keep = []
         for i, (v, t) in enumerate(meshes):
             v = np.ascontiguousarray(v, dtype=np.float32)
             t = np.ascontiguousarray(t, dtype=np.uint32)
             keep += [v, t]
-            arr[i] = _Mesh(t.ctypes.data, v.ctypes.data, 12, 12, len(t), len(v), geom_ids[i] if geom_ids else i)
+            quads = 1 if (t.ndim == 2 and t.shape[1] == 4) else 0
+            arr[i] = _Mesh(t.ctypes.data, v.ctypes.data, 16 if quads else 12, 12, len(t), len(v), geom_ids[i] if geom_ids else i, quads)
         h = self.lib.rqo_build(arr, len(meshes), 1 if robust else 0)
         return h
 

@@ -100,7 +100,7 @@ def test_error_slot_first_error_wins_and_callback(product, hostdev):
     cb = CB(lambda p, code, msg: seen.append((code, msg.decode())))
     L.rtcSetDeviceErrorFunction.argtypes = [C.c_void_p, CB, C.c_void_p]
     L.rtcSetDeviceErrorFunction(hostdev, cb, None)
-    assert not L.rtcNewGeometry(hostdev, rt.RTC_GEOMETRY_TYPE_QUAD)           # unsupported type -> INVALID_OPERATION
+    assert not L.rtcNewGeometry(hostdev, 2)                                   # RTC_GEOMETRY_TYPE_GRID: unsupported type -> INVALID_OPERATION
     L.rtcCommitGeometry(None)                                                 # NULL handle -> INVALID_ARGUMENT, thread slot
     g = L.rtcNewGeometry(hostdev, rt.RTC_GEOMETRY_TYPE_TRIANGLE)
     L.rtcSetGeometryTimeStepCount(g, 2)                                       # second error on the device: not recorded

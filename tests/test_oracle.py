@@ -157,3 +157,25 @@ def test_instancing_restatement_matches_reference_golden(oracle, name):
     oracle.free_top(top)
     for h in handles:
         oracle.free(h)
+
+
+@pytest.mark.parametrize("name", ["quads_mixed", "quads_mixed_robust"])
+def test_quad_restatement_matches_reference_golden(oracle, name):
+    """RTC_GEOMETRY_TYPE_QUAD as two triangles (quad_intersector_moeller.h:122-144): restatement vs vectors of the real library,
+    including a quad with an out-of-range index and quads around a NaN vertex (dropped as a whole)."""
+    import quads
+    c = quads.CASES[name]()
+    g = quads.load_golden(name)
+    assert np.array_equal(c["rays"].view(np.uint8), g["rays"].view(np.uint8))
+    h = oracle.build(c["meshes"], robust=bool(c["flags"] & rt.RTC_SCENE_FLAG_ROBUST))
+    assert np.array_equal(oracle.bounds(h), g["bounds"])
+    r = g["rays"].copy()
+    oracle.intersect(h, r)
+    res = parity.compare_closest(r, g["closest"])
+    assert res["pass"] and res["hits_ours"] > 5000, str(res)
+    on_quads = r["geomID"] != 1
+    assert (r["u"][(r["geomID"] != 0xFFFFFFFF) & on_quads] <= 1.0).all()
+    s = g["shadow_in"].copy()
+    oracle.occluded(h, s)
+    assert parity.compare_occluded(s, g["shadow_out"])["pass"]
+    oracle.free(h)
