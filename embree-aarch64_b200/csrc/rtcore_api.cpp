@@ -575,19 +575,22 @@ inline void packRay32(const char* s, char* d) {
 struct CompactCall;
 struct CompactChunk {
   CompactCall* call; int slot; char* h; unsigned n; unsigned count; unsigned packLeft; unsigned scatterLeft; unsigned packParts; bool packed;
+  double tIssue = 0, tEnq = 0, tCount = 0, tList = 0, tDone = 0; // host clock, ms since the call started (printed at verbose >= 3)
 };
 struct CompactCall {
   Device* dev; RQTraceArgs a; size_t stride; bool occluded, pack; size_t recBytes, recList; unsigned T;
   std::mutex m; std::condition_variable cv;                     // guards everything below and the chunks' counters
   bool slotBusy[Device::kRing] = {false, false, false, false};
   int pending = 0; unsigned chunksDone = 0; int error = 0;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double now() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
   int packing = 0;                                              // chunks whose pack slices are still queued or running
   void submit(std::function<void()> fn) {
     { std::lock_guard<std::mutex> lk(m); pending++; }
     dev->hostPool().submit([this, fn] { fn(); std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv.notify_all(); });
   }
   void fail(int e) { std::lock_guard<std::mutex> lk(m); if (!error) error = e ? e : (int)cudaErrorUnknown; cudaGetLastError(); }
-  void chunkDone(CompactChunk* c) { std::lock_guard<std::mutex> lk(m); slotBusy[c->slot] = false; chunksDone++; cv.notify_all(); }
+  void chunkDone(CompactChunk* c) { c->tDone = now(); std::lock_guard<std::mutex> lk(m); slotBusy[c->slot] = false; chunksDone++; cv.notify_all(); }
 
   void packSlice(CompactChunk* c, unsigned p) {
     const size_t b0 = (size_t)c->n * p / c->packParts, e0 = (size_t)c->n * (p + 1) / c->packParts;
@@ -600,8 +603,8 @@ struct CompactCall {
     { std::lock_guard<std::mutex> lk(m); last = (--c->packLeft == 0); if (last) { packing--; cv.notify_all(); } }
     if (last) enqueue(c);
   }
-  static void CUDART_CB onCount(void* p) { CompactChunk* c = (CompactChunk*)p; c->call->submit([c] { c->call->fetchList(c); }); }
-  static void CUDART_CB onList(void* p) { CompactChunk* c = (CompactChunk*)p; c->call->startScatter(c); }
+  static void CUDART_CB onCount(void* p) { CompactChunk* c = (CompactChunk*)p; c->tCount = c->call->now(); c->call->submit([c] { c->call->fetchList(c); }); }
+  static void CUDART_CB onList(void* p) { CompactChunk* c = (CompactChunk*)p; c->tList = c->call->now(); c->call->startScatter(c); }
 
   void enqueue(CompactChunk* c) {                               // any thread
     cudaSetDevice(dev->ordinal);
@@ -625,6 +628,7 @@ struct CompactCall {
     if (!e) e = occluded ? rqLaunchOccluded(&x, (rqStream)s) : rqLaunchIntersect(&x, (rqStream)s);
     if (!e) e = cudaMemcpyAsync(&dev->countHost[r], x.hitCount, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
     if (!e) e = cudaLaunchHostFunc(s, onCount, c);
+    c->tEnq = now();
     if (e) { fail(e); chunkDone(c); }
   }
   void fetchList(CompactChunk* c) {                             // pool thread, the kernel of this chunk has finished
@@ -745,6 +749,7 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
       }
       c->packParts = c->packed ? std::max(1u, std::min(2 * call.T, (n + 16383u) / 16384u)) : 1u;
       c->packLeft = c->packParts;
+      c->tIssue = call.now();
       issued++;
       if (c->packed) { for (unsigned p = 0; p < c->packParts; p++) call.submit([&call, c, p] { call.packSlice(c, p); }); }
       else call.submit([&call, c] { call.enqueue(c); });
@@ -761,6 +766,10 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
     fprintf(stderr, "b200-rayquery staged %s stream: %u rays in %u chunks, %.2f ms total, caller waited %.2f ms for ring slots; pool %u threads, pack %d\n",
             occluded ? "occlusion" : "closest-hit", M, numChunks, std::chrono::duration<double, std::milli>(clk::now() - tCall).count(), tSlot,
             call.T, (int)call.pack);
+  if (dev->verbose >= 3)
+    for (unsigned i = 0; i < issued; i++)
+      fprintf(stderr, "  chunk %2u slot %d rays %7u hits %7u: issued %.3f, enqueued %.3f, count back %.3f, list back %.3f, scattered %.3f ms\n", i, chunks[i].slot,
+              chunks[i].n, chunks[i].count, chunks[i].tIssue, chunks[i].tEnq, chunks[i].tCount, chunks[i].tList, chunks[i].tDone);
   if (call.error) cudaCheck(call.error, "staged trace");
 }
 
