@@ -37,6 +37,7 @@ for cfg in sys.argv[1:] or ["-"]:
     for k in range(4):
         w_d.copy_(h_d); w_s.copy_(h_s)
         torch.cuda.synchronize()
+        time.sleep(float(os.environ.get("PROBE_SETTLE", "0")))          # optional settle time after the host-side reset copy (PROBE_SETTLE seconds): measured, no consistent effect
         t0 = time.perf_counter()
         lib.intersect_ptr(sc, w_d.data_ptr(), nd, 80)
         t1 = time.perf_counter()

@@ -19,6 +19,7 @@ for cfg in sys.argv[1:] or ["-"]:
     ts = []
     for r in range(8):
         hw.copy_(host); torch.cuda.synchronize()
+        time.sleep(float(os.environ.get("PROBE_SETTLE", "0")))          # optional settle time after the host-side reset copy (PROBE_SETTLE seconds): measured, no consistent effect
         t0 = time.perf_counter(); lib.intersect_ptr(sc, hw.data_ptr(), n, coherent=True); ts.append(time.perf_counter() - t0)
     if first is None:
         first = hw.numpy().copy()
