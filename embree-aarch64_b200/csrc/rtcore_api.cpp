@@ -103,7 +103,6 @@ struct Device : RefCounted {
   size_t listCap[kRing] = {0, 0, 0, 0};
   unsigned int* countHost = nullptr;      // kRing page-locked words
   unsigned int* countDev = nullptr;       // kRing device words, 32 bytes apart
-  cudaEvent_t evCount[kRing] = {nullptr, nullptr, nullptr, nullptr}, evList[kRing] = {nullptr, nullptr, nullptr, nullptr};
   RQTraceCounters* dCounters = nullptr;
   unsigned int* dWork = nullptr;          // ray cursors of the persistent kernels: one per ring stream + one for the device stream
   std::mutex launchMutex;                 // (cursor reset + launch) pairs on the device stream are enqueued atomically
@@ -181,8 +180,6 @@ struct Device : RefCounted {
         if (listDev[i]) cudaFree(listDev[i]);
         if (listHost[i]) cudaFreeHost(listHost[i]);
         if (packHost[i]) cudaFreeHost(packHost[i]);
-        if (evCount[i]) cudaEventDestroy(evCount[i]);
-        if (evList[i]) cudaEventDestroy(evList[i]);
       }
       for (SmallStage* s : smallAll) { if (s->buf) cudaFree(s->buf); if (s->work) cudaFree(s->work); if (s->stream) cudaStreamDestroy(s->stream); delete s; }
       if (countHost) cudaFreeHost(countHost);
