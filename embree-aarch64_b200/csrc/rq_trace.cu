@@ -48,7 +48,7 @@ struct TraceParams {
 
 __device__ __forceinline__ float rcpSafe(float d) {           // common/math/vec3fa.h:172-177
   const float a = fabsf(d) < 1e-18f ? copysignf(1e-18f, d) : d;
-  return 1.0f / a;
+  return __frcp_rn(a);                                          // = 1.0f / a (both correctly rounded), shorter instruction sequence
 }
 
 // Byte j of w as the float 1 + q*2^-16 (bits 0x3F800000 + q*128) with ONE integer dot product:
