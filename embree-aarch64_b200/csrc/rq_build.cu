@@ -503,7 +503,10 @@ k_ploc_nn(B2 t, const uint32_t* __restrict__ cid, const uint32_t* __restrict__ m
 // merge mutual pairs (the lower position keeps the new cluster), flag survivors, count them per block
 __global__ void __launch_bounds__(PLOC_THREADS)
 k_ploc_merge(B2 t, uint32_t* __restrict__ cid, const uint32_t* __restrict__ mPtr, const uint32_t* __restrict__ nn, uint32_t* __restrict__ keep,
-             uint32_t* __restrict__ blockCount, uint32_t* nextInner, float costNode, float costTri, int maxLeafTris) {
+             uint32_t* blockCount, uint32_t* nextInner, float costNode, float costTri, int maxLeafTris,
+             uint32_t* mNext, uint32_t* iterations, uint32_t* blocksDone) {
+  __shared__ uint32_t part[PLOC_THREADS];
+  __shared__ bool isLast;
   const uint32_t m = *mPtr;
   if (blockIdx.x * PLOC_THREADS >= m) return;                   // block-uniform: nobody reaches the barrier below
   const uint32_t i = blockIdx.x * PLOC_THREADS + threadIdx.x;
@@ -522,36 +525,36 @@ k_ploc_merge(B2 t, uint32_t* __restrict__ cid, const uint32_t* __restrict__ mPtr
     keep[i] = alive ? 1u : 0u;
   }
   const unsigned cnt = __syncthreads_count(alive);
-  if (threadIdx.x == 0) blockCount[blockIdx.x] = cnt;
-}
-
-// exclusive scan of the per-block survivor counts (one block), total to *total
-__global__ void __launch_bounds__(1024)
-k_ploc_scan(uint32_t* __restrict__ blockCount, const uint32_t* __restrict__ mPtr, uint32_t* total, uint32_t* iterations) {
-  __shared__ uint32_t part[1024];
-  __shared__ uint32_t carry;
-  const uint32_t m = *mPtr;
+  // The block that finishes last turns the per-block survivor counts into exclusive offsets and publishes the next cluster count
+  // (threadfence reduction): no separate one-block scan launch per iteration.
   const uint32_t numBlocks = (m + PLOC_THREADS - 1) / PLOC_THREADS;
-  if (threadIdx.x == 0 && m > 1) atomicAdd(iterations, 1u);     // iterations that still had something to merge
-  if (threadIdx.x == 0) carry = 0;
+  if (threadIdx.x == 0) {
+    blockCount[blockIdx.x] = cnt;
+    __threadfence();
+    isLast = (atomicAdd(blocksDone, 1u) == numBlocks - 1u);
+  }
   __syncthreads();
-  for (uint32_t base = 0; base < numBlocks; base += 1024) {
-    const uint32_t idx = base + threadIdx.x;
-    const uint32_t v = idx < numBlocks ? blockCount[idx] : 0u;
-    part[threadIdx.x] = v;
+  if (!isLast) return;
+  __threadfence();
+  const uint32_t chunk = (numBlocks + PLOC_THREADS - 1) / PLOC_THREADS;
+  const uint32_t b0 = threadIdx.x * chunk, e0 = min(b0 + chunk, numBlocks);
+  uint32_t sum = 0;
+  for (uint32_t k = b0; k < e0; k++) sum += __ldcg(blockCount + k);
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < PLOC_THREADS; o <<= 1) {                  // Hillis-Steele inclusive scan of the 256 partial sums
+    const uint32_t v = (int)threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const uint32_t a = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
-      __syncthreads();
-      part[threadIdx.x] += a;
-      __syncthreads();
-    }
-    if (idx < numBlocks) blockCount[idx] = carry + part[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += part[1023];
+    part[threadIdx.x] += v;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry;
+  uint32_t run = part[threadIdx.x] - sum;
+  for (uint32_t k = b0; k < e0; k++) { const uint32_t v = __ldcg(blockCount + k); blockCount[k] = run; run += v; }
+  if (threadIdx.x == PLOC_THREADS - 1) {
+    *mNext = part[PLOC_THREADS - 1];
+    if (m > 1) atomicAdd(iterations, 1u);
+    *blocksDone = 0u;                                           // ready for the next iteration (stream ordered)
+  }
 }
 
 __global__ void __launch_bounds__(PLOC_THREADS)
@@ -887,11 +890,11 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       if (P.builder == 1 && n > 1) {
         // ---- PLOC: iterate nearest-neighbour search / merge / compaction until one cluster is left ----
         const int radius = P.plocRadius < 1 ? 1 : (P.plocRadius > PLOC_MAX_RADIUS ? PLOC_MAX_RADIUS : P.plocRadius);
-        CK(cid0.alloc(n)); CK(cid1.alloc(n)); CK(nnBuf.alloc(n)); CK(blockCount.alloc(blocksFor(n, PLOC_THREADS) + 1)); CK(plocCtr.alloc(4));
+        CK(cid0.alloc(n)); CK(cid1.alloc(n)); CK(nnBuf.alloc(n)); CK(blockCount.alloc(blocksFor(n, PLOC_THREADS) + 1)); CK(plocCtr.alloc(5));
         // counters on the device: [0] next inner node id, [1]/[2] cluster count of the current / next iteration (ping-pong),
-        // [3] iterations that merged something.  The host reads the count back only every few iterations (to shrink the
+        // [3] iterations that merged something, [4] blocks of the running merge kernel that are done.  The host reads the count back only every few iterations (to shrink the
         // grids and to detect the end); in between the kernels are launched for the last known upper bound.
-        const uint32_t initCtr[4] = {n - 2u, n, n, 0u};
+        const uint32_t initCtr[5] = {n - 2u, n, n, 0u, 0u};
         CK(cudaMemcpyAsync(plocCtr.p, initCtr, sizeof(initCtr), cudaMemcpyHostToDevice, stream));
         k_ploc_init<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costTri, cid0.p);
         rqCountLaunch(1);
@@ -905,10 +908,10 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
             uint32_t* mCur = plocCtr.p + 1 + (it & 1u);
             uint32_t* mNext = plocCtr.p + 1 + ((it + 1u) & 1u);
             k_ploc_nn<<<nb, PLOC_THREADS, 0, stream>>>(t, cin, mCur, radius, nnBuf.p);
-            k_ploc_merge<<<nb, PLOC_THREADS, 0, stream>>>(t, cin, mCur, nnBuf.p, flag.p, blockCount.p, plocCtr.p, P.costNode, P.costTri, P.maxLeafTris);
-            k_ploc_scan<<<1, 1024, 0, stream>>>(blockCount.p, mCur, mNext, plocCtr.p + 3);
+            k_ploc_merge<<<nb, PLOC_THREADS, 0, stream>>>(t, cin, mCur, nnBuf.p, flag.p, blockCount.p, plocCtr.p, P.costNode, P.costTri, P.maxLeafTris,
+                                                          mNext, plocCtr.p + 3, plocCtr.p + 4);
             k_ploc_compact<<<nb, PLOC_THREADS, 0, stream>>>(cin, mCur, flag.p, blockCount.p, cout);
-            rqCountLaunch(4);
+            rqCountLaunch(3);
             std::swap(cin, cout);
           }
           uint32_t next = 0;
