@@ -269,7 +269,7 @@ def run_ours(args):
     ms_step = t_close + t_occ
 
     # ---- end to end through the C ABI with pinned host buffers (H2D + kernels + D2H timed) ----
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     hw_d, hw_s = torch.empty_like(h_d).pin_memory(), torch.empty_like(h_s).pin_memory()
     t_e2e = 0.0
     xfer0 = (0, 0)
