@@ -7,10 +7,11 @@
 //   intersectNode<8,8> (slab test)      kernels/bvh/node_intersector1.h:527-578, robust :621-636
 //   Intersect1EpilogM / Occluded1EpilogM kernels/geometry/intersector_epilog.h:215-294,378-444
 //   RayStreamAOS get/setHitByOffset     kernels/common/ray.h:1098-1185
-// with one design for the GPU: one ray per thread, a while-while loop over 128-byte quantised
-// 8-wide nodes (five 16-byte ld.global.nc per node, three per triangle), child ordering by ray
-// octant instead of a distance sort, a node-group stack (one 8-byte entry per visited level) and
-// the reference's FP32 triangle tests (rq_math.cuh).
+// with one design for the GPU: one ray per thread, a persistent while-while loop over 128-byte
+// quantised 8-wide nodes (three 32-byte ld.global.nc per node, 32 + 16 bytes per triangle), child
+// ordering by ray octant instead of a distance sort, a node-group stack (one 8-byte entry per
+// visited level, shared memory first) and the reference's FP32 triangle tests (rq_math.cuh).
+// Variants: INST (single-level instancing), LIST (compact hit output for host-staged streams).
 //
 // Ray semantics preserved: a ray is inactive unless tnear <= tfar (NaN = inactive)
 // and is then left untouched; box culling uses max(tnear,0) / max(tfar,0) (bvh_intersector1.cpp:64)
