@@ -436,6 +436,27 @@ k_trace(const TraceParams P) {
           tvalid = masks & 0x00FFFFFFu;
           tmask = s_exp3[hit8] & tvalid;
           triBase = n1.y;
+#ifdef RQ_PREFETCH
+          // Experiment (off): the record this lane will need in its next iteration is known now -- ask for it.  The first use of a
+          // node / triangle record is where 10.7 % / 10.4 % of the stall samples sit (profiles/r01final_ncu_source.txt), but the
+          // kernel is issue-bound: the extra address arithmetic + CCTL.E.PF1 cost 3-6 % closest-hit and 4-29 % occlusion
+          // throughput on configs[1] / configs[2] (profiles/r01pf_sweep_prefetch.log).
+          if (tmask == 0u) {
+            if (ng.y & 0xFF000000u) {
+              const uint32_t nbit = 31u - (uint32_t)__clz((int)ng.y);
+              const uint32_t nslot = (nbit - 24u) ^ octinv;
+              const uint32_t nrel = __popc(ng.y & 0xFFu & ((1u << nslot) - 1u));
+              asm volatile("prefetch.global.L1 [%0];" :: "l"((INST ? cnodes : P.nodes) + (size_t)(ng.x + nrel) * 128));
+            }
+          }
+#if RQ_PREFETCH >= 2
+          else {
+            const uint32_t pb = 31u - (uint32_t)__clz((int)tmask);
+            const uint32_t pti = triBase + __popc(tvalid & ((1u << pb) - 1u));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"((INST ? ctris : P.tris) + (size_t)pti * 48));
+          }
+#endif
+#endif
         }
       }
       const unsigned act = __ballot_sync(FULL, active);
