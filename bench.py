@@ -330,7 +330,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_trace<closest>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "bytes_per_ray": alg_close / nd, "achieved_if_nodes_count_128B": (alg_close + c_close["nodes"] * 48) / (t_close * 1e-3) / 1e9,
-                         "traffic": ncu.get("dram_bytes_per_launch_closest")},
+                         "traffic": ncu.get("dram_bytes_per_launch_closest") if args.workload == "c2" else None},   # the ncu capture is of the configs[1] streams
             "e2e": {"value": total_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d_step),
                     "d2h_bytes_per_step": int(d2h_step), "host_record_bytes_per_step": world * (nd * 80 + ns * 48),
                     "path": "rtcIntersect1M + rtcOccluded1M on page-locked host streams: H2D of the ray records, kernels, compact "
