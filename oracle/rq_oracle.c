@@ -9,6 +9,8 @@
  * known-answer tests (TriangleHitTest analytic expectations, tutorials/verify/verify.cpp:2339-2426),
  * (b) golden vectors produced by the real reference library (tests/golden/, generator
  * tests/golden/make_golden.py, library built by oracle/build_ref.py), (c) oracle/_ref live when present.
+ * The quad-mesh and single-level-instancing restatements further down are pinned the same way
+ * (tests/golden/quads_*.npz, inst_*.npz; generators make_golden_quads.py, make_golden_instances.py).
  *
  * Each function cites the reference source it restates (paths relative to /root/reference).
  * Differences that are deliberate and inside the stated tolerances:
