@@ -1001,8 +1001,8 @@ RTC_API ssize_t rtcGetDeviceProperty(RTCDevice h, enum RTCDeviceProperty prop) {
       case RTC_DEVICE_PROPERTY_FILTER_FUNCTION_SUPPORTED: return 0;
       case RTC_DEVICE_PROPERTY_IGNORE_INVALID_RAYS_ENABLED: return 0;
       case RTC_DEVICE_PROPERTY_COMPACT_POLYS_ENABLED: return 0;
-      case RTC_DEVICE_PROPERTY_TRIANGLE_GEOMETRY_SUPPORTED: return 1;
-      case RTC_DEVICE_PROPERTY_QUAD_GEOMETRY_SUPPORTED: case RTC_DEVICE_PROPERTY_SUBDIVISION_GEOMETRY_SUPPORTED:
+      case RTC_DEVICE_PROPERTY_TRIANGLE_GEOMETRY_SUPPORTED: case RTC_DEVICE_PROPERTY_QUAD_GEOMETRY_SUPPORTED: return 1;
+      case RTC_DEVICE_PROPERTY_SUBDIVISION_GEOMETRY_SUPPORTED:
       case RTC_DEVICE_PROPERTY_CURVE_GEOMETRY_SUPPORTED: case RTC_DEVICE_PROPERTY_USER_GEOMETRY_SUPPORTED:
       case RTC_DEVICE_PROPERTY_POINT_GEOMETRY_SUPPORTED: return 0;
       case RTC_DEVICE_PROPERTY_TASKING_SYSTEM: return 0;

@@ -194,6 +194,7 @@ def test_commit_state_machine_without_gpu(product, hostdev):
     assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
     assert L.rtcGetDeviceProperty(hostdev, 0) == 31201 and L.rtcGetDeviceProperty(hostdev, 96) == 1
     assert L.rtcGetDeviceProperty(hostdev, 66) == 0 and L.rtcGetDeviceProperty(hostdev, 35) == 1
+    assert L.rtcGetDeviceProperty(hostdev, 97) == 1 and L.rtcGetDeviceProperty(hostdev, 98) == 0   # quads yes, subdivision no
     L.rtcReleaseGeometry(g)
     L.rtcReleaseScene(sc)
 
