@@ -215,6 +215,17 @@ def test_oracle_is_not_on_the_product_path():
 
 def test_instance_geometry_host_logic(product, hostdev):
     """rtcSetGeometryTransform / rtcGetGeometryTransform formats (rtcore.cpp:1008-1069) and instance-only calls."""
+    _instance_host_logic(product, hostdev)
+
+
+def test_instance_geometry_host_logic_is_the_references(reflib):
+    """The same call sequence against the real reference library: the expectations above are its behaviour, not ours."""
+    d = reflib.new_device("")
+    _instance_host_logic(reflib, d)
+    reflib.lib.rtcReleaseDevice(d)
+
+
+def _instance_host_logic(product, hostdev):
     L = product.lib
     g = L.rtcNewGeometry(hostdev, rt.RTC_GEOMETRY_TYPE_INSTANCE)
     assert g and err(product, hostdev) == 0
@@ -249,3 +260,39 @@ def test_instance_geometry_host_logic(product, hostdev):
     L.rtcReleaseScene(sc)                                                         # the geometry still holds the instanced scene
     L.rtcReleaseGeometry(g)
     L.rtcReleaseGeometry(t)
+
+
+def _buffer_format_rules(lib, dev):
+    """scene_triangle_mesh.cpp:35-80 / scene_quad_mesh.cpp:35-80: index format per geometry type, vertex format, alignment."""
+    L = lib.lib
+    v = np.zeros(64, dtype=np.float32)
+    i = np.zeros(64, dtype=np.uint32)
+    tri = L.rtcNewGeometry(dev, rt.RTC_GEOMETRY_TYPE_TRIANGLE)
+    quad = L.rtcNewGeometry(dev, rt.RTC_GEOMETRY_TYPE_QUAD)
+    assert tri and quad and L.rtcGetDeviceError(dev) == 0
+    L.rtcSetSharedGeometryBuffer(tri, rt.RTC_BUFFER_TYPE_INDEX, 0, rt.RTC_FORMAT_UINT3, i.ctypes.data, 0, 12, 4)
+    L.rtcSetSharedGeometryBuffer(quad, rt.RTC_BUFFER_TYPE_INDEX, 0, rt.RTC_FORMAT_UINT4, i.ctypes.data, 0, 16, 4)
+    L.rtcSetSharedGeometryBuffer(quad, rt.RTC_BUFFER_TYPE_VERTEX, 0, rt.RTC_FORMAT_FLOAT3, v.ctypes.data, 0, 12, 4)
+    assert L.rtcGetDeviceError(dev) == 0
+    L.rtcSetSharedGeometryBuffer(tri, rt.RTC_BUFFER_TYPE_INDEX, 0, rt.RTC_FORMAT_UINT4, i.ctypes.data, 0, 16, 4)
+    assert L.rtcGetDeviceError(dev) == rt.RTC_ERROR_INVALID_OPERATION
+    L.rtcSetSharedGeometryBuffer(quad, rt.RTC_BUFFER_TYPE_INDEX, 0, rt.RTC_FORMAT_UINT3, i.ctypes.data, 0, 12, 4)
+    assert L.rtcGetDeviceError(dev) == rt.RTC_ERROR_INVALID_OPERATION
+    L.rtcSetSharedGeometryBuffer(quad, rt.RTC_BUFFER_TYPE_VERTEX, 0, 0x9002, v.ctypes.data, 0, 8, 4)          # RTC_FORMAT_FLOAT2
+    assert L.rtcGetDeviceError(dev) == rt.RTC_ERROR_INVALID_OPERATION
+    L.rtcSetSharedGeometryBuffer(tri, rt.RTC_BUFFER_TYPE_VERTEX, 0, rt.RTC_FORMAT_FLOAT3, v.ctypes.data, 0, 14, 4)   # stride not a multiple of 4
+    assert L.rtcGetDeviceError(dev) == rt.RTC_ERROR_INVALID_OPERATION
+    L.rtcSetSharedGeometryBuffer(tri, rt.RTC_BUFFER_TYPE_VERTEX, 1, rt.RTC_FORMAT_FLOAT3, v.ctypes.data, 0, 12, 4)   # slot 1 without time steps
+    assert L.rtcGetDeviceError(dev) != 0
+    L.rtcReleaseGeometry(tri)
+    L.rtcReleaseGeometry(quad)
+
+
+def test_buffer_format_rules(product, hostdev):
+    _buffer_format_rules(product, hostdev)
+
+
+def test_buffer_format_rules_are_the_references(reflib):
+    d = reflib.new_device("")
+    _buffer_format_rules(reflib, d)
+    reflib.lib.rtcReleaseDevice(d)
