@@ -1074,8 +1074,8 @@ RTC_API void rtcDisableGeometry(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC
 RTC_API void rtcSetGeometryTimeStepCount(RTCGeometry h, unsigned int n) {
   Geometry* g = (Geometry*)h;
   RTC_TRY VERIFY_HANDLE(h);
-    if (n == 0 || n > RTC_MAX_TIME_STEP_COUNT) fail(RTC_ERROR_INVALID_OPERATION, "number of time steps is out of range");
-    if (n != 1) fail(RTC_ERROR_INVALID_OPERATION, "motion blur is not supported by the B200 ray-query device");
+    if (n > RTC_MAX_TIME_STEP_COUNT) fail(RTC_ERROR_INVALID_ARGUMENT, "number of time steps is out of range");   // rtcore.cpp:1335-1336
+    if (n > 1) fail(RTC_ERROR_INVALID_OPERATION, "motion blur is not supported by the B200 ray-query device");
   RTC_CATCH(devOf(g))
 }
 RTC_API void rtcSetGeometryMask(RTCGeometry h, unsigned int mask) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); g->mask = mask; RTC_CATCH(devOf(g)) }
@@ -1083,7 +1083,7 @@ RTC_API void rtcSetGeometryBuildQuality(RTCGeometry h, enum RTCBuildQuality q) {
   Geometry* g = (Geometry*)h;
   RTC_TRY VERIFY_HANDLE(h);
     if (q != RTC_BUILD_QUALITY_LOW && q != RTC_BUILD_QUALITY_MEDIUM && q != RTC_BUILD_QUALITY_HIGH && q != RTC_BUILD_QUALITY_REFIT)
-      fail(RTC_ERROR_INVALID_OPERATION, "invalid build quality");
+      throw std::runtime_error("invalid build quality");   // the reference throws a plain runtime_error here: RTC_ERROR_UNKNOWN (rtcore.cpp:233,1386)
     g->quality = q; g->update();
   RTC_CATCH(devOf(g))
 }
@@ -1325,7 +1325,7 @@ RTC_API void rtcSetSceneBuildQuality(RTCScene hs, enum RTCBuildQuality q) {
   Scene* s = (Scene*)hs;
   RTC_TRY VERIFY_HANDLE(hs);
     if (q != RTC_BUILD_QUALITY_LOW && q != RTC_BUILD_QUALITY_MEDIUM && q != RTC_BUILD_QUALITY_HIGH)
-      fail(RTC_ERROR_INVALID_OPERATION, "invalid build quality");
+      throw std::runtime_error("invalid build quality");   // the reference throws a plain runtime_error here: RTC_ERROR_UNKNOWN (rtcore.cpp:233,1386)
     if (q != s->quality) { s->quality = q; s->modified = true; }
   RTC_CATCH(devOf(s))
 }

@@ -188,7 +188,7 @@ def test_commit_state_machine_without_gpu(product, hostdev):
     L.rtcSetSceneFlags(sc, rt.RTC_SCENE_FLAG_ROBUST)
     assert L.rtcGetSceneFlags(sc) == rt.RTC_SCENE_FLAG_ROBUST
     L.rtcSetSceneBuildQuality(sc, 7)
-    assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
+    assert err(product, hostdev) == rt.RTC_ERROR_UNKNOWN                      # the reference throws a plain runtime_error (rtcore.cpp:233)
     L.rtcSetGeometryTessellationRate.argtypes = [C.c_void_p, C.c_float]
     L.rtcSetGeometryTessellationRate(g, 4.0)                                 # out-of-scope entry point
     assert err(product, hostdev) == rt.RTC_ERROR_INVALID_OPERATION
@@ -296,3 +296,51 @@ def test_buffer_format_rules_are_the_references(reflib):
     d = reflib.new_device("")
     _buffer_format_rules(reflib, d)
     reflib.lib.rtcReleaseDevice(d)
+
+
+def _scene_state_rules(lib, dev):
+    """Geometry-ID allocation (lowest free first, scene.cpp:595-623), attach / detach / get errors, quality and time-step
+    arguments, queries on an uncommitted scene, NULL handles -- one call sequence, the observations returned as a list."""
+    L = lib.lib
+    out = []
+
+    def e():
+        return L.rtcGetDeviceError(dev)
+    sc = L.rtcNewScene(dev)
+    gs = [L.rtcNewGeometry(dev, rt.RTC_GEOMETRY_TYPE_TRIANGLE) for _ in range(5)]
+    out.append(("attach0", L.rtcAttachGeometry(sc, gs[0]), e()))
+    out.append(("attach1", L.rtcAttachGeometry(sc, gs[1]), e()))
+    L.rtcDetachGeometry(sc, 0); out.append(("detach0", e()))
+    out.append(("attach2 takes the lowest free id", L.rtcAttachGeometry(sc, gs[2]), e()))
+    L.rtcAttachGeometryByID(sc, gs[3], 5); out.append(("by id 5", e()))
+    out.append(("attach4", L.rtcAttachGeometry(sc, gs[4]), e()))
+    L.rtcAttachGeometryByID(sc, gs[0], 5); out.append(("by id 5 again", e()))
+    L.rtcDetachGeometry(sc, 3); out.append(("detach unused id", e()))
+    L.rtcDetachGeometry(sc, 77); out.append(("detach out of range", e()))
+    out.append(("get 1", bool(L.rtcGetGeometry(sc, 1)), e()))
+    out.append(("get unused id", bool(L.rtcGetGeometry(sc, 3)), e()))
+    L.rtcSetSceneBuildQuality(sc, 3); out.append(("scene quality REFIT is invalid", e()))
+    L.rtcSetGeometryBuildQuality(gs[1], 3); out.append(("geometry quality REFIT", e()))
+    L.rtcSetGeometryBuildQuality(gs[1], 9); out.append(("geometry quality 9", e()))
+    L.rtcSetGeometryTimeStepCount(gs[1], 0); out.append(("time steps 0", e()))
+    L.rtcSetGeometryTimeStepCount(gs[1], 1); out.append(("time steps 1", e()))
+    L.rtcSetGeometryTimeStepCount(gs[1], 1000); out.append(("time steps 1000", e()))
+    r = rt.new_rays(4)
+    ctx = lib.context()
+    L.rtcIntersect1M(sc, C.byref(ctx), r.ctypes.data, 4, 80); out.append(("query on an uncommitted scene", e()))
+    b = rt.Bounds()
+    L.rtcGetSceneBounds(sc, C.byref(b)); out.append(("bounds of an uncommitted scene", e()))
+    L.rtcCommitScene(None); out.append(("commit NULL", e(), L.rtcGetDeviceError(None)))
+    for g in gs:
+        L.rtcReleaseGeometry(g)
+    L.rtcReleaseScene(sc)
+    return out
+
+
+def test_scene_state_rules_equal_the_references(product, hostdev, reflib):
+    d = reflib.new_device("")
+    want = _scene_state_rules(reflib, d)
+    reflib.lib.rtcReleaseDevice(d)
+    got = _scene_state_rules(product, hostdev)
+    assert got == want, [(a, b) for a, b in zip(got, want) if a != b]
+    assert ("attach2 takes the lowest free id", 0, 0) in got and ("by id 5 again", rt.RTC_ERROR_INVALID_OPERATION) in got
