@@ -1042,7 +1042,7 @@ RTC_API RTCBuffer rtcNewBuffer(RTCDevice h, size_t bytes) {
 }
 RTC_API RTCBuffer rtcNewSharedBuffer(RTCDevice h, void* ptr, size_t bytes) {
   Device* d = (Device*)h;
-  RTC_TRY VERIFY_HANDLE(h); VERIFY_HANDLE(ptr); return (RTCBuffer) new Buffer(d, bytes, ptr); RTC_CATCH(d)
+  RTC_TRY VERIFY_HANDLE(h); return (RTCBuffer) new Buffer(d, bytes, ptr); RTC_CATCH(d)   // a NULL pointer is not rejected by the reference either (rtcore.cpp:128-141); it then owns its memory here
   return nullptr;
 }
 RTC_API void* rtcGetBufferData(RTCBuffer h) {
@@ -1158,9 +1158,16 @@ RTC_API void* rtcGetGeometryBufferData(RTCGeometry h, enum RTCBufferType type, u
   RTC_CATCH(devOf(g))
   return nullptr;
 }
-RTC_API void rtcUpdateGeometryBuffer(RTCGeometry h, enum RTCBufferType type, unsigned int) {
+RTC_API void rtcUpdateGeometryBuffer(RTCGeometry h, enum RTCBufferType type, unsigned int slot) {
   Geometry* g = (Geometry*)h;
-  RTC_TRY VERIFY_HANDLE(h); if (type == RTC_BUFFER_TYPE_VERTEX) g->updateVertices(); else g->update(); RTC_CATCH(devOf(g))
+  RTC_TRY
+    VERIFY_HANDLE(h);
+    // scene_triangle_mesh.cpp:109-135: index slot 0, vertex slot < number of time steps (1 here), anything else is an invalid argument
+    if (type == RTC_BUFFER_TYPE_INDEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); g->update(); }
+    else if (type == RTC_BUFFER_TYPE_VERTEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); g->updateVertices(); }
+    else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot");   // no attribute buffers can be bound
+    else fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
+  RTC_CATCH(devOf(g))
 }
 RTC_API void rtcSetGeometryUserData(RTCGeometry h, void* p) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); g->userPtr = p; RTC_CATCH(devOf(g)) }
 RTC_API void* rtcGetGeometryUserData(RTCGeometry h) { Geometry* g = (Geometry*)h; RTC_TRY VERIFY_HANDLE(h); return g->userPtr; RTC_CATCH(devOf(g)) return nullptr; }

@@ -344,3 +344,54 @@ def test_scene_state_rules_equal_the_references(product, hostdev, reflib):
     got = _scene_state_rules(product, hostdev)
     assert got == want, [(a, b) for a, b in zip(got, want) if a != b]
     assert ("attach2 takes the lowest free id", 0, 0) in got and ("by id 5 again", rt.RTC_ERROR_INVALID_OPERATION) in got
+
+
+def _buffer_and_property_rules(lib, dev):
+    """Buffers, geometry buffers (alignment, slots, unknown types), user data, masks, device properties, scene flags, NULL handles:
+    one call sequence, the observations returned as a list."""
+    L = lib.lib
+    out = []
+    def e(): return L.rtcGetDeviceError(dev)
+    L.rtcGetGeometryUserData.restype = C.c_void_p; L.rtcGetGeometryUserData.argtypes=[C.c_void_p]
+    L.rtcSetGeometryUserData.argtypes=[C.c_void_p, C.c_void_p]
+    L.rtcSetGeometryMask.argtypes=[C.c_void_p, C.c_uint]
+    L.rtcSetDeviceProperty.argtypes=[C.c_void_p, C.c_int, C.c_ssize_t]
+    g = L.rtcNewGeometry(dev, rt.RTC_GEOMETRY_TYPE_TRIANGLE)
+    out.append(("new shared buffer NULL", bool(L.rtcNewSharedBuffer(dev, None, 64)), e()))
+    b = L.rtcNewBuffer(dev, 256); out.append(("new buffer", bool(b), e()))
+    out.append(("buffer data", bool(L.rtcGetBufferData(b)), e()))
+    L.rtcSetGeometryBuffer(g, rt.RTC_BUFFER_TYPE_VERTEX, 0, rt.RTC_FORMAT_FLOAT3, b, 2, 12, 4); out.append(("unaligned offset", e()))
+    L.rtcSetGeometryBuffer(g, rt.RTC_BUFFER_TYPE_VERTEX, 0, rt.RTC_FORMAT_FLOAT3, b, 0, 12, 4); out.append(("vertex buffer ok", e()))
+    L.rtcSetGeometryBuffer(g, rt.RTC_BUFFER_TYPE_VERTEX, 0, rt.RTC_FORMAT_FLOAT3, None, 0, 12, 4); out.append(("NULL buffer", e()))
+    L.rtcSetGeometryBuffer(g, 77, 0, rt.RTC_FORMAT_FLOAT3, b, 0, 12, 4); out.append(("buffer type 77", e()))
+    L.rtcSetGeometryBuffer(g, rt.RTC_BUFFER_TYPE_INDEX, 1, rt.RTC_FORMAT_UINT3, b, 0, 12, 4); out.append(("index slot 1", e()))
+    out.append(("get vertex data", bool(L.rtcGetGeometryBufferData(g, rt.RTC_BUFFER_TYPE_VERTEX, 0)), e()))
+    out.append(("get index data unset", bool(L.rtcGetGeometryBufferData(g, rt.RTC_BUFFER_TYPE_INDEX, 0)), e()))
+    out.append(("get data type 77", bool(L.rtcGetGeometryBufferData(g, 77, 0)), e()))
+    p = L.rtcSetNewGeometryBuffer(g, rt.RTC_BUFFER_TYPE_INDEX, 0, rt.RTC_FORMAT_UINT3, 12, 10); out.append(("set new index buffer", bool(p), e()))
+    L.rtcUpdateGeometryBuffer(g, rt.RTC_BUFFER_TYPE_VERTEX, 0); out.append(("update vertex", e()))
+    L.rtcUpdateGeometryBuffer(g, 77, 0); out.append(("update type 77", e()))
+    L.rtcSetGeometryMask(g, 0xF0); out.append(("mask", e()))
+    L.rtcSetGeometryUserData(g, 0x1234); out.append(("userdata", L.rtcGetGeometryUserData(g), e()))
+    L.rtcEnableGeometry(g); L.rtcDisableGeometry(g); L.rtcDisableGeometry(g); out.append(("enable/disable", e()))
+    L.rtcCommitGeometry(g); out.append(("commit geometry", e()))
+    out.append(("prop 999", L.rtcGetDeviceProperty(dev, 999), e()))
+    L.rtcSetDeviceProperty(dev, 999, 1); out.append(("set prop 999", e()))
+    L.rtcSetDeviceProperty(dev, 0, 1); out.append(("set prop version", e()))
+    sc = L.rtcNewScene(dev)
+    out.append(("flags default", L.rtcGetSceneFlags(sc), e()))
+    L.rtcSetSceneFlags(sc, 7); out.append(("flags 7", L.rtcGetSceneFlags(sc), e()))
+    d2 = L.rtcGetSceneDevice(sc); out.append(("scene device", d2 == dev, e())); L.rtcReleaseDevice(d2)
+    L.rtcAttachGeometry(None, g); out.append(("attach NULL scene", e(), L.rtcGetDeviceError(None)))
+    L.rtcAttachGeometry(sc, None); out.append(("attach NULL geom", e(), L.rtcGetDeviceError(None)))
+    L.rtcAttachGeometryByID(sc, g, 0xFFFFFFFF); out.append(("by id INVALID", e()))
+    L.rtcReleaseBuffer(b); L.rtcReleaseGeometry(g); L.rtcReleaseScene(sc)
+    return out
+
+
+def test_buffer_and_property_rules_equal_the_references(product, hostdev, reflib):
+    d = reflib.new_device("")
+    want = _buffer_and_property_rules(reflib, d)
+    reflib.lib.rtcReleaseDevice(d)
+    got = _buffer_and_property_rules(product, hostdev)
+    assert got == want, [(a, b) for a, b in zip(got, want) if a != b]
