@@ -584,6 +584,7 @@ struct EmitCounters {
   uint32_t leafSlots;
   double sahInnerQ, sahLeafQ;  // reference SAH terms on de-quantised boxes
   double sahInnerX, sahLeafX;  // same on exact boxes
+  double sahLeafTrisQ;         // leaf term weighted by triangles instead of blocks: sum A(leaf) * numTris (de-quantised boxes)
 };
 
 __device__ __forceinline__ uint8_t expForExtent(float ext) {
@@ -600,7 +601,7 @@ __device__ __forceinline__ void
 emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2* __restrict__ nextQueue,
          EmitCounters* ctr, RQNode* __restrict__ nodes, RQTri* __restrict__ trisOut,
          const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals, uint32_t level,
-         const uint32_t* __restrict__ parentOf, uint32_t* __restrict__ nextParentOf, double sahOut[4]) {
+         const uint32_t* __restrict__ parentOf, uint32_t* __restrict__ nextParentOf, double sahOut[5]) {
   const uint32_t b = queue[q].x, w = queue[q].y;
   const uint32_t firstLeaf = (uint32_t)(n - 1);
 
@@ -681,7 +682,7 @@ emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2*
     for (int a = 0; a < 3; a++) { N.qlo[a][s] = 255; N.qhi[a][s] = 0; }
   }
   uint32_t innerRank = 0, triOff = 0;
-  double sahInnerQ = 0, sahLeafQ = 0, sahInnerX = 0, sahLeafX = 0;
+  double sahInnerQ = 0, sahLeafQ = 0, sahInnerX = 0, sahLeafX = 0, sahLeafTrisQ = 0;
   for (int s = 0; s < 8; s++) {
     const int c = childAt[s];
     if (c < 0) continue;
@@ -720,7 +721,7 @@ emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2*
         } else if (wsp < 3) { walk[wsp++] = t.right[x]; walk[wsp++] = t.left[x]; }
       }
       triOff += nt;
-      sahLeafQ += Aq * (double)((nt + 3) / 4); sahLeafX += Ax * (double)((nt + 3) / 4);
+      sahLeafQ += Aq * (double)((nt + 3) / 4); sahLeafX += Ax * (double)((nt + 3) / 4); sahLeafTrisQ += Aq * (double)nt;
     }
   }
   N.lo[0] = nlo.x; N.lo[1] = nlo.y; N.lo[2] = nlo.z; N.hi[0] = nhi.x; N.hi[1] = nhi.y; N.hi[2] = nhi.z;
@@ -732,7 +733,7 @@ emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2*
     for (int i = 0; i < 8; i++) d4[i] = s4[i];
   }
   if (level == 0) { sahInnerQ += (double)nlo.w; sahInnerX += (double)nlo.w; }   // the root's own box
-  sahOut[0] = sahInnerQ; sahOut[1] = sahLeafQ; sahOut[2] = sahInnerX; sahOut[3] = sahLeafX;
+  sahOut[0] = sahInnerQ; sahOut[1] = sahLeafQ; sahOut[2] = sahInnerX; sahOut[3] = sahLeafX; sahOut[4] = sahLeafTrisQ;
 }
 
 __global__ void __launch_bounds__(128)
@@ -741,15 +742,15 @@ k_emit(B2 t, int n, const uint2* __restrict__ queue, uint32_t count, uint2* __re
        const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals, uint32_t level,
        const uint32_t* __restrict__ parentOf /* wide parent per queue entry */, uint32_t* __restrict__ nextParentOf) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (q < count)
     emit_one(t, n, q, queue, nextQueue, ctr, nodes, trisOut, trisIn, vals, level, parentOf, nextParentOf, s);
   #pragma unroll
-  for (int k = 0; k < 4; k++)
+  for (int k = 0; k < 5; k++)
     for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
   if ((threadIdx.x & 31) == 0) {
     atomicAdd(&ctr->sahInnerQ, s[0]); atomicAdd(&ctr->sahLeafQ, s[1]);
-    atomicAdd(&ctr->sahInnerX, s[2]); atomicAdd(&ctr->sahLeafX, s[3]);
+    atomicAdd(&ctr->sahInnerX, s[2]); atomicAdd(&ctr->sahLeafX, s[3]); atomicAdd(&ctr->sahLeafTrisQ, s[4]);
   }
 }
 
@@ -985,6 +986,8 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       stats->numPrimsIn = N; stats->numPrimsValid = n; stats->numNodes = numNodes; stats->numTris = numTris;
       stats->depth = depth; stats->numLeaves = hc.leafSlots; stats->sah = H.sah;
       stats->sahExact = rootA > 0 ? (hc.sahInnerX + hc.sahLeafX) / rootA : 0.0;
+      stats->sahInner = rootA > 0 ? hc.sahInnerQ / rootA : 0.0;
+      stats->sahLeafTris = rootA > 0 ? hc.sahLeafTrisQ / rootA : 0.0;
       stats->bytes = H.totalBytes;
       stats->builderIterations = plocIters;
       cudaEventElapsedTime(&stats->msTotal, ev[0], ev[6]);
@@ -1070,12 +1073,12 @@ k_refit_tris(const RQGeomDesc* __restrict__ geomsByID, uint32_t numSlots, RQTri*
   if (odd) { rec[0] = c2; rec[1] = a; rec[2] = b; } else { rec[0] = a; rec[1] = b; rec[2] = c2; }
 }
 
-struct RefitSums { double sahInnerQ, sahLeafQ, sahInnerX, sahLeafX; };
+struct RefitSums { double sahInnerQ, sahLeafQ, sahInnerX, sahLeafX, sahLeafTrisQ; };
 
 __global__ void __launch_bounds__(128)
 k_refit_nodes(RQNode* __restrict__ nodes, const RQTri* __restrict__ tris, uint32_t first, uint32_t count, RefitSums* sums) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (q < count) {
     RQNode N;
     {
@@ -1140,7 +1143,7 @@ k_refit_nodes(RQNode* __restrict__ nodes, const RQTri* __restrict__ tris, uint32
       }
       const double Aq = (double)halfArea(dq[0], dq[1], dq[2]);
       const double Ax = (double)halfArea(chi[k][0] - clo[k][0], chi[k][1] - clo[k][1], chi[k][2] - clo[k][2]);
-      if (imask & (1u << k)) { s[0] += Aq; s[2] += Ax; } else { s[1] += Aq; s[3] += Ax; }
+      if (imask & (1u << k)) { s[0] += Aq; s[2] += Ax; } else { s[1] += Aq; s[3] += Ax; s[4] += Aq * (double)__popc((tvalid >> (3 * k)) & 7u); }
     }
     // an empty node keeps an inverted exact box, so its parent skips it as well
     for (int a = 0; a < 3; a++) { N.lo[a] = nodeEmpty ? FLT_MAX : nlo[a]; N.hi[a] = nodeEmpty ? -FLT_MAX : nhi[a]; }
@@ -1155,11 +1158,11 @@ k_refit_nodes(RQNode* __restrict__ nodes, const RQTri* __restrict__ tris, uint32
     }
   }
   #pragma unroll
-  for (int k = 0; k < 4; k++)
+  for (int k = 0; k < 5; k++)
     for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
   if ((threadIdx.x & 31) == 0 && (s[0] != 0.0 || s[1] != 0.0)) {
     atomicAdd(&sums->sahInnerQ, s[0]); atomicAdd(&sums->sahLeafQ, s[1]);
-    atomicAdd(&sums->sahInnerX, s[2]); atomicAdd(&sums->sahLeafX, s[3]);
+    atomicAdd(&sums->sahInnerX, s[2]); atomicAdd(&sums->sahLeafX, s[3]); atomicAdd(&sums->sahLeafTrisQ, s[4]);
   }
 }
 
@@ -1211,6 +1214,8 @@ int rqRefitBVH(const RQGeomDesc* geomsByID, int numSlots, RQDeviceImage* img, rq
     if (stats) {
       stats->sah = H.sah;
       stats->sahExact = rootA > 0 ? (hs.sahInnerX + hs.sahLeafX) / rootA : 0.0;
+      stats->sahInner = rootA > 0 ? hs.sahInnerQ / rootA : 0.0;
+      stats->sahLeafTris = rootA > 0 ? hs.sahLeafTrisQ / rootA : 0.0;
       stats->msSort = stats->msHierarchy = stats->msEmit = 0.f;
       cudaEventElapsedTime(&stats->msTotal, ev[0], ev[2]);
       cudaEventElapsedTime(&stats->msPrims, ev[0], ev[1]);
@@ -1226,4 +1231,58 @@ fail:
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   cudaGetLastError();
   return err ? err : (int)cudaErrorUnknown;
+}
+
+// ================================================================================================
+// Validation of an adopted image (rtcxSetSceneImage / rtcxLoadSceneImage): see rq_device.h.
+// ================================================================================================
+namespace {
+__global__ void __launch_bounds__(256)
+k_validate_image(const RQNode* __restrict__ nodes, const RQTri* __restrict__ tris, uint32_t numNodes, uint32_t numTris, uint32_t depth,
+                 unsigned int* violations) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool bad = false;
+  if (i < numNodes) {
+    const RQNode* N = nodes + i;
+    const uint32_t imask = N->masks >> 24, tvalid = N->masks & 0x00FFFFFFu;
+    const uint32_t ni = __popc(imask), nt = __popc(tvalid);
+    if (N->level >= depth) bad = true;
+    if (ni) {
+      // children live behind their parent (the builder emits level by level) and one level deeper
+      if (N->childBase <= i || (uint64_t)N->childBase + ni > numNodes) bad = true;
+      else for (uint32_t k = 0; k < ni; k++) if (nodes[N->childBase + k].level != N->level + 1u) bad = true;
+    }
+    if (nt && (uint64_t)N->triBase + nt > numTris) bad = true;
+    for (uint32_t k = 0; k < 8; k++) {                          // a slot is inner or leaf, never both; leaf bits are contiguous from bit 0 of the slot
+      const uint32_t tb = (tvalid >> (3 * k)) & 7u;
+      if (((imask >> k) & 1u) && tb) bad = true;
+      if (tb != 0u && tb != 1u && tb != 3u && tb != 7u) bad = true;
+    }
+  }
+  if (i < numTris) {
+    const uint4* rec = (const uint4*)(tris + i);
+    const uint32_t pad = (i & 1u) ? rec[0].w : rec[2].w;        // odd records are stored rotated (rq_types.h)
+    if (pad & RQ_PAD_INSTANCE) bad = true;                      // instance records refer to other scenes' device memory
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAdd(violations, 1u);
+}
+}  // namespace
+
+int rqValidateImage(const void* image, const RQImageHeader* H, rqStream stream_, unsigned int* violations) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  unsigned int* d = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&d, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(d, 0, sizeof(unsigned int), stream);
+  const uint32_t n = H->numNodes > H->numTris ? H->numNodes : H->numTris;
+  if (e == cudaSuccess && n) {
+    k_validate_image<<<blocksFor(n, 256), 256, 0, stream>>>((const RQNode*)((const char*)image + H->nodesOffset),
+                                                            (const RQTri*)((const char*)image + H->trisOffset), H->numNodes, H->numTris, H->depth, d);
+    rqCountLaunch(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(violations, d, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFreeAsync(d, stream);
+  return (int)e;
 }

@@ -71,16 +71,27 @@ struct RQTraceArgs {
 int rqLaunchIntersect(const RQTraceArgs* a, rqStream stream);
 int rqLaunchOccluded(const RQTraceArgs* a, rqStream stream);
 
-// Layout adapters for the non-AoS entry points (SoA packets / pointer streams): gather into a
-// dense AoS scratch buffer, trace, scatter results back.
-struct RQSoAView {              // device-readable field pointers, element i at ptr[i]
+// Layout adapters for the non-AoS entry points (reference: RayStreamFilter::filterAOP / filterSOA / filterSOP,
+// kernels/bvh/bvh_intersector_stream_filters.cpp:155-592): gather every ray of the call into a dense AoS scratch buffer of
+// 80-byte RTCRayHit records, trace that with the stream kernels, scatter the results back.  All pointers are device readable.
+struct RQSoAView {              // ray i = lane (i % N) of packet (i / N); its field lives at field + (i / N) * packetStride bytes + (i % N) * 4
   float *org_x, *org_y, *org_z, *tnear, *dir_x, *dir_y, *dir_z, *time, *tfar;
   unsigned int *mask, *id, *flags;
   float *Ng_x, *Ng_y, *Ng_z, *u, *v;
   unsigned int *primID, *geomID, *instID0;
+  uint32_t N;                   // packet width (RTCRayHitNp / one packet: N = number of rays, packetStride = 0)
+  size_t   packetStride;        // bytes between consecutive packets (rtcIntersectNM byteStride)
 };
 int rqGatherSoA(const RQSoAView* v, const int* valid, uint32_t n, void* aosRayHit, rqStream stream);
 int rqScatterSoA(const RQSoAView* v, uint32_t n, const void* aosRayHit, int occluded, rqStream stream);
+// array-of-pointers streams (rtcIntersect1Mp / rtcOccluded1Mp): ptrs[i] addresses an RTCRayHit (80 B) or an RTCRay (48 B)
+int rqGatherAoP(const void* const* ptrs, uint32_t n, int recBytes, void* aosRayHit, rqStream stream);
+int rqScatterAoP(void* const* ptrs, uint32_t n, const void* aosRayHit, int occluded, rqStream stream);
+
+// Consistency check of an image that did not come out of rqBuildBVH (rtcxSetSceneImage / rtcxLoadSceneImage): every child and
+// triangle reference in range, child levels = parent level + 1, deepest level < header depth, no instance records.  *violations
+// receives the number of offending records (0 = usable).
+int rqValidateImage(const void* image, const RQImageHeader* header, rqStream stream, unsigned int* violations);
 
 // Number of kernel launches issued by this library since load (bench.py's gpu_launches claim).
 unsigned long long rqLaunchCount(void);

@@ -570,19 +570,25 @@ int rqLaunchIntersect(const RQTraceArgs* a, rqStream stream) { return launchTrac
 int rqLaunchOccluded(const RQTraceArgs* a, rqStream stream) { return launchTrace(true, a, (cudaStream_t)stream); }
 
 // ------------------------------------------------------------------------------------------------
-// layout adapters: SoA / pointer-SoA  <->  dense AoS RTCRayHit scratch (80-byte records)
+// layout adapters: SoA packets / pointer-SoA / array-of-pointers  <->  dense AoS RTCRayHit scratch (80-byte records)
+// (reference: filterSOA / filterSOP / filterAOP, kernels/bvh/bvh_intersector_stream_filters.cpp:155-592)
 // ------------------------------------------------------------------------------------------------
 namespace {
+template <typename T>
+__device__ __forceinline__ T* soaAt(T* field, const RQSoAView& v, uint32_t i) {
+  const uint32_t m = i / v.N, j = i - m * v.N;
+  return (T*)((char*)field + (size_t)m * v.packetStride) + j;
+}
 __global__ void __launch_bounds__(256)
 k_gather_soa(const RQSoAView v, const int* __restrict__ valid, uint32_t n, float* __restrict__ aos) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float* r = aos + (size_t)i * 20;
   const bool ok = valid ? valid[i] != 0 : true;
-  r[0] = v.org_x[i]; r[1] = v.org_y[i]; r[2] = v.org_z[i];
-  r[3] = ok ? v.tnear[i] : INFINITY;                            // invalid lane = inactive ray
-  r[4] = v.dir_x[i]; r[5] = v.dir_y[i]; r[6] = v.dir_z[i]; r[7] = 0.f;
-  r[8] = ok ? v.tfar[i] : -INFINITY;
+  r[0] = *soaAt(v.org_x, v, i); r[1] = *soaAt(v.org_y, v, i); r[2] = *soaAt(v.org_z, v, i);
+  r[3] = ok ? *soaAt(v.tnear, v, i) : INFINITY;                 // invalid lane = inactive ray
+  r[4] = *soaAt(v.dir_x, v, i); r[5] = *soaAt(v.dir_y, v, i); r[6] = *soaAt(v.dir_z, v, i); r[7] = 0.f;
+  r[8] = ok ? *soaAt(v.tfar, v, i) : -INFINITY;
   ((uint32_t*)r)[9] = 0; ((uint32_t*)r)[10] = 0; ((uint32_t*)r)[11] = 0;
   ((uint32_t*)r)[18] = RQ_INVALID;                              // geomID marks "hit written"
 }
@@ -592,14 +598,38 @@ k_scatter_soa(const RQSoAView v, uint32_t n, const float* __restrict__ aos, int 
   if (i >= n) return;
   const float* r = aos + (size_t)i * 20;
   if (occluded) {
-    if (r[8] == -INFINITY && r[3] != INFINITY) v.tfar[i] = -INFINITY;   // only newly occluded, valid lanes
+    if (r[8] == -INFINITY && r[3] != INFINITY) *soaAt(v.tfar, v, i) = -INFINITY;   // only newly occluded, valid lanes
     return;
   }
   if (((const uint32_t*)r)[18] == RQ_INVALID) return;           // miss or inactive: nothing is written
-  v.tfar[i] = r[8];
-  v.Ng_x[i] = r[12]; v.Ng_y[i] = r[13]; v.Ng_z[i] = r[14]; v.u[i] = r[15]; v.v[i] = r[16];
-  v.primID[i] = ((const uint32_t*)r)[17]; v.geomID[i] = ((const uint32_t*)r)[18];
-  if (v.instID0) v.instID0[i] = ((const uint32_t*)r)[19];
+  *soaAt(v.tfar, v, i) = r[8];
+  *soaAt(v.Ng_x, v, i) = r[12]; *soaAt(v.Ng_y, v, i) = r[13]; *soaAt(v.Ng_z, v, i) = r[14];
+  *soaAt(v.u, v, i) = r[15]; *soaAt(v.v, v, i) = r[16];
+  *soaAt(v.primID, v, i) = ((const uint32_t*)r)[17]; *soaAt(v.geomID, v, i) = ((const uint32_t*)r)[18];
+  if (v.instID0) *soaAt(v.instID0, v, i) = ((const uint32_t*)r)[19];
+}
+// one thread per record, 4-byte words (the caller's records are only guaranteed 4-byte aligned)
+__global__ void __launch_bounds__(256)
+k_gather_aop(const void* const* __restrict__ ptrs, uint32_t n, int recBytes, uint32_t* __restrict__ aos) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* s = (const uint32_t*)ptrs[i];
+  uint32_t* d = aos + (size_t)i * 20;
+  const int words = recBytes / 4;
+  for (int k = 0; k < words; k++) d[k] = s[k];
+  for (int k = words; k < 20; k++) d[k] = 0u;
+  d[18] = RQ_INVALID;                                           // geomID marks "hit written" (the caller's own value is never read back)
+}
+__global__ void __launch_bounds__(256)
+k_scatter_aop(void* const* __restrict__ ptrs, uint32_t n, const uint32_t* __restrict__ aos, int occluded) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* r = aos + (size_t)i * 20;
+  uint32_t* d = (uint32_t*)ptrs[i];
+  if (occluded) { if (r[8] == 0xFF800000u) d[8] = 0xFF800000u; return; }   // tfar = -inf
+  if (r[18] == RQ_INVALID) return;
+  d[8] = r[8];
+  for (int k = 12; k < 20; k++) d[k] = r[k];
 }
 }  // namespace
 
@@ -612,6 +642,18 @@ int rqGatherSoA(const RQSoAView* v, const int* valid, uint32_t n, void* aos, rqS
 int rqScatterSoA(const RQSoAView* v, uint32_t n, const void* aos, int occluded, rqStream stream) {
   if (!n) return 0;
   k_scatter_soa<<<(n + 255u) / 256u, 256, 0, (cudaStream_t)stream>>>(*v, n, (const float*)aos, occluded);
+  rqCountLaunch(1);
+  return (int)cudaGetLastError();
+}
+int rqGatherAoP(const void* const* ptrs, uint32_t n, int recBytes, void* aos, rqStream stream) {
+  if (!n) return 0;
+  k_gather_aop<<<(n + 255u) / 256u, 256, 0, (cudaStream_t)stream>>>(ptrs, n, recBytes, (uint32_t*)aos);
+  rqCountLaunch(1);
+  return (int)cudaGetLastError();
+}
+int rqScatterAoP(void* const* ptrs, uint32_t n, const void* aos, int occluded, rqStream stream) {
+  if (!n) return 0;
+  k_scatter_aop<<<(n + 255u) / 256u, 256, 0, (cudaStream_t)stream>>>(ptrs, n, (const uint32_t*)aos, occluded);
   rqCountLaunch(1);
   return (int)cudaGetLastError();
 }

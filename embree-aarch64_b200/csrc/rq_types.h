@@ -124,6 +124,8 @@ struct RQBuildStats {
   uint64_t bytes;
   uint32_t builderIterations; // PLOC merge iterations (0 for the radix tree)
   uint32_t refitCount;        // refits applied to this BVH since its last full build (0 = freshly built)
+  double   sahInner;          // inner-node term of `sah` alone (sah - sahInner = leaf term, one block per leaf slot)
+  double   sahLeafTris;       // leaf term weighted by triangles: sum A(leaf slot) * numTris / A(root)
 };
 
 // Per-call traversal counters (instrumented kernel variant only).

@@ -388,12 +388,16 @@ void commitScene(Scene* sc) {
   std::vector<RQInstance> insts;
   unsigned instDepth = 0;
   TempDev tmp;
+  // the counters this commit is about to absorb: written back to the scene only after the build / refit has succeeded, so a
+  // failed commit (out of memory, cancelled, invalid instance) is retried by the next rtcCommitScene instead of being skipped
+  std::vector<unsigned> newMod, newTopo;
   {
     std::lock_guard<std::mutex> gl(sc->geomMutex);
+    newMod = sc->seenMod; newTopo = sc->seenTopo;
     for (size_t i = 0; i < sc->geoms.size(); i++) {
       Geometry* g = sc->geoms[i];
       if (!g) continue;
-      sc->seenMod[i] = g->modCounter; sc->seenTopo[i] = g->topoCounter;
+      newMod[i] = g->modCounter; newTopo[i] = g->topoCounter;
       if (g->enabled && g->type == RTC_GEOMETRY_TYPE_INSTANCE) {
         // one primitive whose box is xfmBounds(local2world, bounds of the instanced scene) (scene_instance.h:61-66);
         // the instanced scene must be committed first, as in the reference
@@ -504,6 +508,10 @@ void commitScene(Scene* sc) {
       cudaCheck(cudaStreamSynchronize(s), "instance table");
       sc->traceDepth = img.header.depth + 3 + instDepth;       // the lane parks 3 entries of top-level state while inside an instance
     }
+  }
+  {
+    std::lock_guard<std::mutex> gl(sc->geomMutex);
+    for (size_t i = 0; i < newMod.size() && i < sc->seenMod.size(); i++) { sc->seenMod[i] = newMod[i]; sc->seenTopo[i] = newTopo[i]; }
   }
   sc->modified = false; sc->everCommitted = true; sc->epoch++;
   if (sc->progress) sc->progress(sc->progressPtr, 1.0);
@@ -626,7 +634,7 @@ struct CompactCall {
     if (!e) e = cudaMemcpyAsync(&dev->countHost[r], x.hitCount, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
     if (!e) e = cudaLaunchHostFunc(s, onCount, c);
     c->tEnq = now();
-    if (e) { fail(e); chunkDone(c); }
+    if (e) { fail(e); cudaStreamSynchronize(s); cudaGetLastError(); chunkDone(c); }   // whatever was queued on the slot is finished before it is reused
   }
   void fetchList(CompactChunk* c) {                             // pool thread, the kernel of this chunk has finished
     cudaSetDevice(dev->ordinal);
@@ -640,7 +648,7 @@ struct CompactCall {
     }
     dev->d2hBytes += sizeof(unsigned);
     if (!e) e = cudaLaunchHostFunc(s, onList, c);
-    if (e) { fail(e); chunkDone(c); }
+    if (e) { fail(e); cudaStreamSynchronize(s); cudaGetLastError(); chunkDone(c); }
   }
   void startScatter(CompactChunk* c) {                          // CUDA callback thread: only queues work
     const unsigned per = std::max(8192u, (c->count + T - 1) / T);
@@ -767,19 +775,29 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
     for (unsigned i = 0; i < issued; i++)
       fprintf(stderr, "  chunk %2u slot %d rays %7u hits %7u: issued %.3f, enqueued %.3f, count back %.3f, list back %.3f, scattered %.3f ms\n", i, chunks[i].slot,
               chunks[i].n, chunks[i].count, chunks[i].tIssue, chunks[i].tEnq, chunks[i].tCount, chunks[i].tList, chunks[i].tDone);
-  if (call.error) cudaCheck(call.error, "staged trace");
+  if (call.error) {
+    for (int r = 0; r < Device::kRing; r++) if (dev->ringStream[r]) cudaStreamSynchronize(dev->ringStream[r]);
+    cudaGetLastError();
+    cudaCheck(call.error, "staged trace");
+  }
 }
 
 // Trace M records of `stride` bytes at `rays`; occluded selects the any-hit kernel; recBytes is
 // 80 (RTCRayHit) or 48 (RTCRay).  Device-resident memory is traced in place; host memory is staged
 // through a ring of device buffers so copies of one chunk overlap the kernel of another.
+// streamRule: entry rules of occlusion rays -- 1 = stream filter (AoS / AoP streams with M > 1: rays with tnear < 0 are skipped,
+// bvh_intersector_stream.cpp:303-305), 0 = single ray / packet (tnear is clamped to 0 instead, bvh_intersector1.cpp:132,
+// bvh_intersector_hybrid.cpp:153,403), -1 = decide by M like rtcOccluded1M does.
 void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, size_t stride, bool occluded,
-                 size_t recBytes, RQTraceCounters* countersOut) {
+                 size_t recBytes, RQTraceCounters* countersOut, int streamRule = -1) {
   if (M == 0) return;
   Device* dev = sc->dev;
   if (!dev->hasGpu) fail(RTC_ERROR_UNKNOWN, "no CUDA device");
+  // the kernels read records through 4-byte (16-byte when possible) words: a misaligned address would fault and poison the context
+  if (((uintptr_t)rays & 3u) || (stride & 3u)) fail(RTC_ERROR_INVALID_ARGUMENT, "ray not aligned to 4 bytes");
+  if (M > 1 && stride < recBytes) fail(RTC_ERROR_INVALID_OPERATION, "byteStride too small");   // overlapping records: hit writes would race with ray reads
   dev->bind();
-  RQTraceArgs a; fillArgs(sc, ctx, a, M > 1);
+  RQTraceArgs a; fillArgs(sc, ctx, a, streamRule < 0 ? M > 1 : streamRule != 0);
   RQTraceCounters* dC = nullptr;
   if (countersOut) {
     std::lock_guard<std::mutex> l(dev->stageMutex);
@@ -842,6 +860,7 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
     size_t chunk = dev->chunkRays;
     if ((size_t)M < 8 * chunk) chunk = std::min(chunk, std::max<size_t>(65536, (((size_t)M + 7) / 8 + 32767) & ~(size_t)32767));
     unsigned done = 0; int slot = 0;
+    try {
     while (done < M) {
       const unsigned n = (unsigned)std::min<size_t>(chunk, M - done);
       const size_t span = (size_t)(n - 1) * stride + recBytes;
@@ -876,6 +895,12 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
       }
       done += n;
     }
+    } catch (...) {
+      // earlier pieces may still be copying into the caller's buffer or reading the ring slots: drain them before the error leaves the call
+      for (int r = 0; r < Device::kRing; r++) if (dev->ringStream[r]) cudaStreamSynchronize(dev->ringStream[r]);
+      cudaGetLastError();
+      throw;
+    }
     for (int r = 0; r < Device::kRing; r++) if (dev->ringStream[r]) cudaCheck(cudaStreamSynchronize(dev->ringStream[r]), "trace");
   }
   if (countersOut) {
@@ -884,52 +909,120 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
   }
 }
 
-// host-side packing for the packet / pointer layouts (rtcore_ray.h:52-251): N lanes -> AoS records
-struct Lane { float *org_x, *org_y, *org_z, *tnear, *dir_x, *dir_y, *dir_z, *time, *tfar; unsigned *mask, *id, *flags;
-              float *Ng_x, *Ng_y, *Ng_z, *u, *v; unsigned *primID, *geomID, *instID; };
+// ------------------------------------------------------------------------------------------------------------------
+// Adapters for the non-AoS entry points (rtcore_ray.h:52-251; reference: RayStreamFilter::filterAOP / filterSOA / filterSOP,
+// bvh_intersector_stream_filters.cpp:155-592).  Every flavour becomes ONE gather of all its rays into a dense AoS scratch
+// stream, ONE trace of that stream, ONE scatter of the hits:
+//   * layouts living in device memory: gather / scatter kernels (rq_trace.cu), scratch from the stream-ordered pool, the
+//     trace runs in place on the scratch -- nothing crosses PCIe;
+//   * layouts living in host memory: the caller thread gathers into a host scratch stream that goes through the staged
+//     host path of traceStream like any rtcIntersect1M stream.
+// ------------------------------------------------------------------------------------------------------------------
+RQSoAView viewOfNp(const RTCRayNp* r, const RTCHitNp* h, unsigned N) {
+  RQSoAView v; memset(&v, 0, sizeof(v));
+  v.org_x = r->org_x; v.org_y = r->org_y; v.org_z = r->org_z; v.tnear = r->tnear; v.dir_x = r->dir_x; v.dir_y = r->dir_y; v.dir_z = r->dir_z;
+  v.time = r->time; v.tfar = r->tfar; v.mask = r->mask; v.id = r->id; v.flags = r->flags;
+  if (h) { v.Ng_x = h->Ng_x; v.Ng_y = h->Ng_y; v.Ng_z = h->Ng_z; v.u = h->u; v.v = h->v; v.primID = h->primID; v.geomID = h->geomID; v.instID0 = h->instID[0]; }
+  v.N = N ? N : 1u; v.packetStride = 0;
+  return v;
+}
+// SoA block(s) of runtime width N (RTCRayN / RTCRayHitN, also RTCRay4/8/16): field k of a packet starts at word k*N
+RQSoAView viewOfN(void* base, unsigned N, size_t packetStride, bool withHit) {
+  RQSoAView v; memset(&v, 0, sizeof(v));
+  float* f = (float*)base; unsigned* u = (unsigned*)base;
+  v.org_x = f; v.org_y = f + N; v.org_z = f + 2 * N; v.tnear = f + 3 * N; v.dir_x = f + 4 * N; v.dir_y = f + 5 * N; v.dir_z = f + 6 * N;
+  v.time = f + 7 * N; v.tfar = f + 8 * N; v.mask = u + 9 * N; v.id = u + 10 * N; v.flags = u + 11 * N;
+  if (withHit) {
+    float* h = f + 12 * N; unsigned* uh = (unsigned*)h;
+    v.Ng_x = h; v.Ng_y = h + N; v.Ng_z = h + 2 * N; v.u = h + 3 * N; v.v = h + 4 * N; v.primID = uh + 5 * N; v.geomID = uh + 6 * N; v.instID0 = uh + 7 * N;
+  }
+  v.N = N ? N : 1u; v.packetStride = packetStride;
+  return v;
+}
+template <typename T> inline T* soaAtHost(T* field, const RQSoAView& v, unsigned i) {
+  const unsigned m = i / v.N, j = i - m * v.N;
+  return (T*)((char*)field + (size_t)m * v.packetStride) + j;
+}
 
-void tracePacked(Scene* sc, RTCIntersectContext* ctx, const Lane& L, const int* valid, unsigned N, bool occluded) {
-  std::vector<RTCRayHit> tmp(N);
-  for (unsigned i = 0; i < N; i++) {
+struct PoolScratch {                                     // device scratch from the stream-ordered pool, released in stream order
+  void* p = nullptr; cudaStream_t s = nullptr;
+  void alloc(size_t bytes, cudaStream_t st) { s = st; cudaCheck(cudaMallocAsync(&p, bytes ? bytes : 16, st), "scratch alloc"); }
+  ~PoolScratch() { if (p) cudaFreeAsync(p, s); }
+};
+
+void traceSoA(Scene* sc, RTCIntersectContext* ctx, const RQSoAView& v, const int* valid, unsigned total, bool occluded, int streamRule) {
+  if (total == 0) return;
+  Device* dev = sc->dev;
+  if (!dev->hasGpu) fail(RTC_ERROR_UNKNOWN, "no CUDA device");
+  dev->bind();
+  const size_t rec = occluded ? sizeof(RTCRay) : sizeof(RTCRayHit);
+  if (isDevicePointer(v.org_x)) {
+    cudaStream_t s = dev->stream();
+    PoolScratch aos, dvalid;
+    aos.alloc((size_t)total * sizeof(RTCRayHit), s);
+    const int* dv = valid;
+    if (valid && !isDevicePointer(valid)) {              // packet entry points: the (short) valid mask usually lives with the caller
+      dvalid.alloc((size_t)total * sizeof(int), s);
+      cudaCheck(cudaMemcpyAsync(dvalid.p, valid, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, s), "valid mask upload");
+      dv = (const int*)dvalid.p;
+    }
+    cudaCheck(rqGatherSoA(&v, dv, total, aos.p, (rqStream)s), "SoA gather");
+    traceStream(sc, ctx, aos.p, total, sizeof(RTCRayHit), occluded, rec, nullptr, streamRule);
+    cudaCheck(rqScatterSoA(&v, total, aos.p, occluded ? 1 : 0, (rqStream)s), "SoA scatter");
+    if (!dev->async) cudaCheck(cudaStreamSynchronize(s), "trace");
+    return;
+  }
+  std::vector<RTCRayHit> tmp(total);
+  for (unsigned i = 0; i < total; i++) {
     RTCRayHit& r = tmp[i];
     const bool ok = valid ? valid[i] != 0 : true;
-    r.ray.org_x = L.org_x[i]; r.ray.org_y = L.org_y[i]; r.ray.org_z = L.org_z[i];
-    r.ray.dir_x = L.dir_x[i]; r.ray.dir_y = L.dir_y[i]; r.ray.dir_z = L.dir_z[i];
-    r.ray.tnear = ok ? L.tnear[i] : INFINITY; r.ray.tfar = ok ? L.tfar[i] : -INFINITY;   // inactive lane
+    r.ray.org_x = *soaAtHost(v.org_x, v, i); r.ray.org_y = *soaAtHost(v.org_y, v, i); r.ray.org_z = *soaAtHost(v.org_z, v, i);
+    r.ray.dir_x = *soaAtHost(v.dir_x, v, i); r.ray.dir_y = *soaAtHost(v.dir_y, v, i); r.ray.dir_z = *soaAtHost(v.dir_z, v, i);
+    r.ray.tnear = ok ? *soaAtHost(v.tnear, v, i) : INFINITY; r.ray.tfar = ok ? *soaAtHost(v.tfar, v, i) : -INFINITY;   // inactive lane
     r.ray.time = 0.f; r.ray.mask = r.ray.id = r.ray.flags = 0;
     r.hit.geomID = RTC_INVALID_GEOMETRY_ID;
   }
-  // packets follow the single-ray entry rules of their lanes
-  Device* dev = sc->dev; (void)dev;
-  traceStream(sc, ctx, tmp.data(), N, sizeof(RTCRayHit), occluded, occluded ? sizeof(RTCRay) : sizeof(RTCRayHit), nullptr);
-  for (unsigned i = 0; i < N; i++) {
+  traceStream(sc, ctx, tmp.data(), total, sizeof(RTCRayHit), occluded, rec, nullptr, streamRule);
+  for (unsigned i = 0; i < total; i++) {
     const RTCRayHit& r = tmp[i];
     const bool ok = valid ? valid[i] != 0 : true;
     if (!ok) continue;
-    if (occluded) { if (r.ray.tfar == -INFINITY) L.tfar[i] = -INFINITY; continue; }
+    if (occluded) { if (r.ray.tfar == -INFINITY) *soaAtHost(v.tfar, v, i) = -INFINITY; continue; }
     if (r.hit.geomID == RTC_INVALID_GEOMETRY_ID) continue;
-    L.tfar[i] = r.ray.tfar; L.Ng_x[i] = r.hit.Ng_x; L.Ng_y[i] = r.hit.Ng_y; L.Ng_z[i] = r.hit.Ng_z;
-    L.u[i] = r.hit.u; L.v[i] = r.hit.v; L.primID[i] = r.hit.primID; L.geomID[i] = r.hit.geomID; L.instID[i] = r.hit.instID[0];
+    *soaAtHost(v.tfar, v, i) = r.ray.tfar;
+    *soaAtHost(v.Ng_x, v, i) = r.hit.Ng_x; *soaAtHost(v.Ng_y, v, i) = r.hit.Ng_y; *soaAtHost(v.Ng_z, v, i) = r.hit.Ng_z;
+    *soaAtHost(v.u, v, i) = r.hit.u; *soaAtHost(v.v, v, i) = r.hit.v;
+    *soaAtHost(v.primID, v, i) = r.hit.primID; *soaAtHost(v.geomID, v, i) = r.hit.geomID;
+    if (v.instID0) *soaAtHost(v.instID0, v, i) = r.hit.instID[0];
   }
 }
 
-template <typename RayT, typename HitT>
-Lane laneOf(RayT* r, HitT* h) {
-  Lane L;
-  L.org_x = r->org_x; L.org_y = r->org_y; L.org_z = r->org_z; L.tnear = r->tnear; L.dir_x = r->dir_x; L.dir_y = r->dir_y;
-  L.dir_z = r->dir_z; L.time = r->time; L.tfar = r->tfar; L.mask = r->mask; L.id = r->id; L.flags = r->flags;
-  if (h) { L.Ng_x = h->Ng_x; L.Ng_y = h->Ng_y; L.Ng_z = h->Ng_z; L.u = h->u; L.v = h->v; L.primID = h->primID; L.geomID = h->geomID; L.instID = h->instID[0]; }
-  else { L.Ng_x = L.Ng_y = L.Ng_z = L.u = L.v = nullptr; L.primID = L.geomID = L.instID = nullptr; }
-  return L;
-}
-Lane laneOfN(float* base, unsigned N, bool withHit) {     // runtime-N SoA block: field k at word k*N
-  Lane L; unsigned* ub = (unsigned*)base;
-  L.org_x = base; L.org_y = base + N; L.org_z = base + 2 * N; L.tnear = base + 3 * N; L.dir_x = base + 4 * N; L.dir_y = base + 5 * N;
-  L.dir_z = base + 6 * N; L.time = base + 7 * N; L.tfar = base + 8 * N; L.mask = ub + 9 * N; L.id = ub + 10 * N; L.flags = ub + 11 * N;
-  if (withHit) { float* h = base + 12 * N; unsigned* uh = (unsigned*)h;
-    L.Ng_x = h; L.Ng_y = h + N; L.Ng_z = h + 2 * N; L.u = h + 3 * N; L.v = h + 4 * N; L.primID = uh + 5 * N; L.geomID = uh + 6 * N; L.instID = uh + 7 * N; }
-  else { L.Ng_x = L.Ng_y = L.Ng_z = L.u = L.v = nullptr; L.primID = L.geomID = L.instID = nullptr; }
-  return L;
+// array-of-pointers streams (rtcIntersect1Mp / rtcOccluded1Mp)
+void traceAoP(Scene* sc, RTCIntersectContext* ctx, void** ptrs, unsigned M, bool occluded) {
+  if (M == 0) return;
+  Device* dev = sc->dev;
+  if (!dev->hasGpu) fail(RTC_ERROR_UNKNOWN, "no CUDA device");
+  dev->bind();
+  const size_t rec = occluded ? sizeof(RTCRay) : sizeof(RTCRayHit);
+  if (isDevicePointer(ptrs)) {                           // a device array of device pointers
+    cudaStream_t s = dev->stream();
+    PoolScratch aos;
+    aos.alloc((size_t)M * sizeof(RTCRayHit), s);
+    cudaCheck(rqGatherAoP((const void* const*)ptrs, M, (int)rec, aos.p, (rqStream)s), "AoP gather");
+    traceStream(sc, ctx, aos.p, M, sizeof(RTCRayHit), occluded, rec, nullptr, -1);
+    cudaCheck(rqScatterAoP((void* const*)ptrs, M, aos.p, occluded ? 1 : 0, (rqStream)s), "AoP scatter");
+    if (!dev->async) cudaCheck(cudaStreamSynchronize(s), "trace");
+    return;
+  }
+  std::vector<RTCRayHit> tmp(M);
+  for (unsigned i = 0; i < M; i++) { memcpy(&tmp[i], ptrs[i], sizeof(RTCRay)); tmp[i].hit.geomID = RTC_INVALID_GEOMETRY_ID; }
+  traceStream(sc, ctx, tmp.data(), M, sizeof(RTCRayHit), occluded, rec, nullptr, -1);
+  for (unsigned i = 0; i < M; i++) {
+    if (occluded) { if (tmp[i].ray.tfar == -INFINITY) ((RTCRay*)ptrs[i])->tfar = -INFINITY; continue; }
+    if (tmp[i].hit.geomID == RTC_INVALID_GEOMETRY_ID) continue;
+    RTCRayHit* d = (RTCRayHit*)ptrs[i];
+    d->ray.tfar = tmp[i].ray.tfar; d->hit = tmp[i].hit;
+  }
 }
 
 inline Device* devOf(Scene* s) { return s ? s->dev : nullptr; }
@@ -1382,76 +1475,57 @@ RTC_API void rtcOccluded1(RTCScene hs, struct RTCIntersectContext* ctx, struct R
   Scene* s = (Scene*)hs;
   RTC_TRY checkQuery(s, ctx); traceStream(s, ctx, ray, 1, sizeof(RTCRay), true, sizeof(RTCRay), nullptr); RTC_CATCH(devOf(s))
 }
+// Packets of 4 / 8 / 16 rays: the lanes follow the packet kernels' entry rules (tnear clamped to 0, not rejected:
+// bvh_intersector_hybrid.cpp:153,403), so the stream rule is off.
 #define B200RQ_PACKET_ENTRY(W)                                                                                              \
   RTC_API void rtcIntersect##W(const int* valid, RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHit##W* rh) {    \
     Scene* s = (Scene*)hs;                                                                                                  \
-    RTC_TRY checkQuery(s, ctx); tracePacked(s, ctx, laneOf(&rh->ray, &rh->hit), valid, W, false); RTC_CATCH(devOf(s))        \
+    RTC_TRY checkQuery(s, ctx); traceSoA(s, ctx, viewOfN(rh, W, 0, true), valid, W, false, 0); RTC_CATCH(devOf(s))           \
   }                                                                                                                         \
   RTC_API void rtcOccluded##W(const int* valid, RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRay##W* r) {         \
     Scene* s = (Scene*)hs;                                                                                                  \
-    RTC_TRY checkQuery(s, ctx); tracePacked(s, ctx, laneOf(r, (RTCHit##W*)nullptr), valid, W, true); RTC_CATCH(devOf(s))     \
+    RTC_TRY checkQuery(s, ctx); traceSoA(s, ctx, viewOfN(r, W, 0, false), valid, W, true, 0); RTC_CATCH(devOf(s))            \
   }
 B200RQ_PACKET_ENTRY(4)
 B200RQ_PACKET_ENTRY(8)
 B200RQ_PACKET_ENTRY(16)
 
+// rtcore.cpp:626-731,877-905: M == 1 is the single-ray path, otherwise filterAOP (stream rules)
 RTC_API void rtcIntersect1Mp(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHit** rh, unsigned int M) {
   Scene* s = (Scene*)hs;
-  RTC_TRY
-    checkQuery(s, ctx);
-    std::vector<RTCRayHit> tmp(M);
-    for (unsigned i = 0; i < M; i++) tmp[i] = *rh[i];
-    for (unsigned i = 0; i < M; i++) tmp[i].hit.geomID = RTC_INVALID_GEOMETRY_ID;
-    traceStream(s, ctx, tmp.data(), M, sizeof(RTCRayHit), false, sizeof(RTCRayHit), nullptr);
-    for (unsigned i = 0; i < M; i++)
-      if (tmp[i].hit.geomID != RTC_INVALID_GEOMETRY_ID) { rh[i]->ray.tfar = tmp[i].ray.tfar; rh[i]->hit = tmp[i].hit; }
-  RTC_CATCH(devOf(s))
+  RTC_TRY checkQuery(s, ctx); traceAoP(s, ctx, (void**)rh, M, false); RTC_CATCH(devOf(s))
 }
 RTC_API void rtcOccluded1Mp(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRay** r, unsigned int M) {
   Scene* s = (Scene*)hs;
-  RTC_TRY
-    checkQuery(s, ctx);
-    std::vector<RTCRay> tmp(M);
-    for (unsigned i = 0; i < M; i++) tmp[i] = *r[i];
-    traceStream(s, ctx, tmp.data(), M, sizeof(RTCRay), true, sizeof(RTCRay), nullptr);
-    for (unsigned i = 0; i < M; i++) if (tmp[i].tfar == -INFINITY) r[i]->tfar = -INFINITY;
-  RTC_CATCH(devOf(s))
+  RTC_TRY checkQuery(s, ctx); traceAoP(s, ctx, (void**)r, M, true); RTC_CATCH(devOf(s))
 }
+// rtcore.cpp:733-790,906-945: N == 1 is an AoS stream of M records, otherwise filterSOA: M packets of N lanes, packet rules
 RTC_API void rtcIntersectNM(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHitN* rh, unsigned int N, unsigned int M, size_t byteStride) {
   Scene* s = (Scene*)hs;
   RTC_TRY
     checkQuery(s, ctx);
-    for (unsigned m = 0; m < M; m++) tracePacked(s, ctx, laneOfN((float*)((char*)rh + m * byteStride), N, true), nullptr, N, false);
+    if (N == 1) traceStream(s, ctx, rh, M, byteStride, false, sizeof(RTCRayHit), nullptr);
+    else if ((unsigned long long)N * M > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_ARGUMENT, "too many rays in one call");
+    else traceSoA(s, ctx, viewOfN(rh, N, byteStride, true), nullptr, N * M, false, 0);
   RTC_CATCH(devOf(s))
 }
 RTC_API void rtcOccludedNM(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayN* r, unsigned int N, unsigned int M, size_t byteStride) {
   Scene* s = (Scene*)hs;
   RTC_TRY
     checkQuery(s, ctx);
-    for (unsigned m = 0; m < M; m++) tracePacked(s, ctx, laneOfN((float*)((char*)r + m * byteStride), N, false), nullptr, N, true);
+    if (N == 1) traceStream(s, ctx, r, M, byteStride, true, sizeof(RTCRay), nullptr);
+    else if ((unsigned long long)N * M > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_ARGUMENT, "too many rays in one call");
+    else traceSoA(s, ctx, viewOfN(r, N, byteStride, false), nullptr, N * M, true, 0);
   RTC_CATCH(devOf(s))
 }
+// rtcore.cpp:792-846,947-974: filterSOP
 RTC_API void rtcIntersectNp(RTCScene hs, struct RTCIntersectContext* ctx, const struct RTCRayHitNp* rh, unsigned int N) {
   Scene* s = (Scene*)hs;
-  RTC_TRY
-    checkQuery(s, ctx);
-    Lane L;
-    L.org_x = rh->ray.org_x; L.org_y = rh->ray.org_y; L.org_z = rh->ray.org_z; L.tnear = rh->ray.tnear; L.dir_x = rh->ray.dir_x;
-    L.dir_y = rh->ray.dir_y; L.dir_z = rh->ray.dir_z; L.time = rh->ray.time; L.tfar = rh->ray.tfar; L.mask = rh->ray.mask; L.id = rh->ray.id;
-    L.flags = rh->ray.flags; L.Ng_x = rh->hit.Ng_x; L.Ng_y = rh->hit.Ng_y; L.Ng_z = rh->hit.Ng_z; L.u = rh->hit.u; L.v = rh->hit.v;
-    L.primID = rh->hit.primID; L.geomID = rh->hit.geomID; L.instID = rh->hit.instID[0];
-    tracePacked(s, ctx, L, nullptr, N, false);
-  RTC_CATCH(devOf(s))
+  RTC_TRY checkQuery(s, ctx); VERIFY_HANDLE(rh); traceSoA(s, ctx, viewOfNp(&rh->ray, &rh->hit, N), nullptr, N, false, 0); RTC_CATCH(devOf(s))
 }
 RTC_API void rtcOccludedNp(RTCScene hs, struct RTCIntersectContext* ctx, const struct RTCRayNp* r, unsigned int N) {
   Scene* s = (Scene*)hs;
-  RTC_TRY
-    checkQuery(s, ctx);
-    Lane L; memset(&L, 0, sizeof(L));
-    L.org_x = r->org_x; L.org_y = r->org_y; L.org_z = r->org_z; L.tnear = r->tnear; L.dir_x = r->dir_x; L.dir_y = r->dir_y;
-    L.dir_z = r->dir_z; L.time = r->time; L.tfar = r->tfar; L.mask = r->mask; L.id = r->id; L.flags = r->flags;
-    tracePacked(s, ctx, L, nullptr, N, true);
-  RTC_CATCH(devOf(s))
+  RTC_TRY checkQuery(s, ctx); VERIFY_HANDLE(r); traceSoA(s, ctx, viewOfNp(r, nullptr, N), nullptr, N, true, 0); RTC_CATCH(devOf(s))
 }
 
 // ================================================================================================
@@ -1511,11 +1585,20 @@ void adoptImage(Scene* s, const void* src, size_t bytes) {
       H.trisOffset != H.nodesOffset + (uint64_t)H.numNodes * sizeof(RQNode) ||
       H.trisOffset + (uint64_t)H.numTris * sizeof(RQTri) > H.totalBytes)
     fail(RTC_ERROR_INVALID_ARGUMENT, "not a BVH image");
+  if (H.depth == 0 || H.depth > RQ_MAX_LEVELS || H.numNodes == 0) fail(RTC_ERROR_INVALID_ARGUMENT, "not a BVH image (depth / node count out of range)");
   void* p = nullptr;
   cudaCheck(rqAllocImage(&p, bytes, (rqStream)dev->stream()), "image alloc");
   int e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyDefault, dev->stream());
+  // a truncated or corrupt file with a plausible header must not reach the traversal kernels: out-of-range child / triangle
+  // references would be context-fatal illegal addresses, a too small depth silently wrong answers
+  unsigned int violations = 0;
+  if (!e) e = rqValidateImage(p, &H, (rqStream)dev->stream(), &violations);
   if (!e) e = cudaStreamSynchronize(dev->stream());
-  if (e) { RQDeviceImage tmpImg; memset(&tmpImg, 0, sizeof(tmpImg)); tmpImg.base = p; rqFreeImage(&tmpImg); cudaCheck(e, "image copy"); }
+  if (e || violations) {
+    RQDeviceImage tmpImg; memset(&tmpImg, 0, sizeof(tmpImg)); tmpImg.base = p; rqFreeImage(&tmpImg);
+    cudaCheck(e, "image copy");
+    fail(RTC_ERROR_INVALID_ARGUMENT, "corrupt BVH image (references out of range)");
+  }
   if (s->image.base) rqFreeImage(&s->image);
   if (s->dInstances) { cudaFree(s->dInstances); s->dInstances = nullptr; }
   s->numInstances = 0; s->clearInstanced(); s->epoch++;
@@ -1632,3 +1715,4 @@ B200RQ_STUB(void*, rtcBuildBVH, (const void*), B200RQ_NODEV, nullptr)
 B200RQ_STUB(void*, rtcThreadLocalAlloc, (void*, size_t, size_t), B200RQ_NODEV, nullptr)
 B200RQ_STUB(void, rtcRetainBVH, (void*), B200RQ_NODEV, )
 B200RQ_STUB(void, rtcReleaseBVH, (void*), B200RQ_NODEV, )
+B200RQ_STUB(void, rtcMakeStaticBVH, (void*), B200RQ_NODEV, )   /* kernels/common/rtcore_builder.cpp:409 (exported, not in the public header) */

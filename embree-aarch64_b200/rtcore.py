@@ -64,7 +64,8 @@ class BuildStats(C.Structure):
                 ("sah", C.c_double), ("sahExact", C.c_double),
                 ("msTotal", C.c_float), ("msPrims", C.c_float), ("msSort", C.c_float),
                 ("msHierarchy", C.c_float), ("msRefit", C.c_float), ("msEmit", C.c_float),
-                ("bytes", C.c_ulonglong), ("builderIterations", C.c_uint), ("refitCount", C.c_uint)]
+                ("bytes", C.c_ulonglong), ("builderIterations", C.c_uint), ("refitCount", C.c_uint),
+                ("sahInner", C.c_double), ("sahLeafTris", C.c_double)]
 
 
 class TraceCounters(C.Structure):

@@ -26,6 +26,10 @@ struct RTCXBuildStats {
   unsigned long long bytes;     /* size of the device image                                       */
   unsigned int builderIterations; /* PLOC merge iterations (0 for the radix-tree front end)       */
   unsigned int refitCount;      /* refits since the last full build (RTC_BUILD_QUALITY_REFIT path) */
+  double sahInner;              /* inner-node term of `sah`; sah - sahInner = leaf term with one block per leaf slot,
+                                   the weighting of BVHNStatistics (a reference leaf block holds <= 4 triangles, a slot <= 3) */
+  double sahLeafTris;           /* leaf term weighted by triangles instead of blocks: sum A(slot) * numTris / A(root);
+                                   sahInner + sahLeafTris / 4 is the figure to hold against the reference's blocks of four */
 };
 
 struct RTCXTraceCounters {

@@ -1,0 +1,121 @@
+"""GPU tests at the north-star scale and of the builder's output as a data structure:
+  * the 10 M-triangle scene of BASELINE configs[2]-[3] (depth > 10, 0.6 GB image, not L2 resident) against the LIVE reference
+    library on > 1 M diffuse + shadow rays (oracle/_ref travels to the GPU box);
+  * the SAH statistic (SURVEY a-14): RTCXBuildStats.sah against an independent evaluation of the reference's formula
+    (oracle/rq_image.py restating kernels/bvh/bvh_statistics.cpp:41-160) on the exported image of the same tree;
+  * structural invariants of the exported image (every primitive exactly once, references in range, conservative
+    quantisation, level / depth bookkeeping) for every builder front end and build quality."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+
+parity = cases.importlib.import_module("embree-aarch64_b200.parity")
+rt, fx = cases.rt, cases.fx
+pytestmark = pytest.mark.gpu
+INV = 0xFFFFFFFF
+
+
+def _prim_keys(meshes):
+    keys = []
+    for g, (v, t) in enumerate(meshes):
+        t = np.asarray(t)
+        if t.ndim == 2 and t.shape[1] == 4:                              # quads: two halves, the second flagged
+            p = np.repeat(np.arange(len(t), dtype=np.uint64), 2)
+            half = np.tile(np.array([0, 1], dtype=np.uint64), len(t))
+            keys.append((np.uint64(g) << np.uint64(33)) | (p << np.uint64(1)) | half)
+        else:
+            keys.append((np.uint64(g) << np.uint64(33)) | (np.arange(len(t), dtype=np.uint64) << np.uint64(1)))
+    return np.concatenate(keys)
+
+
+@pytest.mark.parametrize("quality", [rt.RTC_BUILD_QUALITY_LOW, rt.RTC_BUILD_QUALITY_MEDIUM, rt.RTC_BUILD_QUALITY_HIGH])
+def test_sah_statistic_and_image_structure(product, gpu_device, quality):
+    from oracle import rq_image
+    for meshes in (fx.scene_c2(0.12), [fx.triangle_sphere((0, 0, 0), 1.0, 9)], [fx.quad_plane((-1, 0, -1), (2, 0, 0), (0, 0, 2), 17, 13)]):
+        L = product.lib
+        sc = L.rtcNewScene(gpu_device)
+        L.rtcSetSceneBuildQuality(sc, quality)
+        keep = []
+        for v, t in meshes:
+            _, g = product.add_mesh(gpu_device, sc, v, t, keep)
+            L.rtcReleaseGeometry(g)
+        L.rtcCommitScene(sc)
+        assert L.rtcGetDeviceError(gpu_device) == 0
+        st = product.build_stats(sc)
+        img = rq_image.fetch(product, sc)
+        assert img.check_structure(_prim_keys(meshes))
+        sah, inner, leaf, leaf_tris = img.sah()
+        assert abs(sah - st["sah"]) <= 1e-6 * sah, (sah, st["sah"])       # a-14: the reported figure IS the reference formula on this tree
+        assert abs(inner - st["sahInner"]) <= 1e-6 * sah and abs(leaf_tris - st["sahLeafTris"]) <= 1e-6 * sah
+        assert float(img.header["sah"]) == st["sah"] and int(img.header["depth"]) == st["depth"]
+        assert st["sahExact"] <= st["sah"] * (1 + 1e-9)                    # quantisation only ever grows boxes
+        L.rtcReleaseScene(sc)
+
+
+def test_sah_close_to_the_reference_builder(product, reflib):
+    """Tree quality against the reference's binned-SAH BVH8 builder on the same input (BENCHMARK_BUILD figure):
+    the blocks-of-4-equivalent SAH of our tree must stay within 15 % of it."""
+    import re
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(cases.ROOT, "tools"))
+    from bench_build import capture_stdout
+    meshes = fx.scene_c3(0.32)                                             # ~1.0 M triangles of the configs[2] scene shape
+    rdev = reflib.new_device("benchmark=1,threads=4")
+    (rsc, rkeep), out = capture_stdout(lambda: reflib.build_scene(rdev, meshes))
+    m = re.search(r"BENCHMARK_BUILD\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)", out)
+    assert m, out
+    ref_sah = float(m.group(3))
+    dev = product.new_device("")
+    sc, keep = product.build_scene(dev, meshes)
+    st = product.build_stats(sc)
+    ours4 = st["sahInner"] + st["sahLeafTris"] / 4.0
+    print(f"SAH reference {ref_sah:.3f}, ours (slot = block) {st['sah']:.3f}, ours blocks-of-4 equivalent {ours4:.3f}")
+    assert ours4 <= 1.15 * ref_sah, (ours4, ref_sah)
+    reflib.lib.rtcReleaseScene(rsc); reflib.lib.rtcReleaseDevice(rdev)
+    product.lib.rtcReleaseScene(sc); product.lib.rtcReleaseDevice(dev)
+
+
+def test_c3_scale_parity_against_live_reference(product, reflib):
+    """BASELINE configs[2]-[3] scene at full size (10.0 M triangles): 1.05 M incoherent diffuse rays and the matching shadow
+    rays, product (CUDA, through the C ABI) against the reference library running on the host cores of the same box."""
+    import sys
+    import os
+    sys.path.insert(0, cases.ROOT)
+    import bench
+    meshes = fx.scene_c3(1.0)
+    ntris = fx.num_tris(meshes)
+    assert 9.9e6 < ntris < 10.1e6
+    dev = product.new_device("")
+    sc, keep = product.build_scene(dev, meshes)
+    st = product.build_stats(sc)
+    assert st["numTris"] == ntris and st["depth"] >= 8 and st["bytes"] > 400e6
+    rdev = reflib.new_device(f"threads={os.cpu_count() or 4}")
+    rsc, rkeep = reflib.build_scene(rdev, meshes)
+    drv = bench.CpuDriver(reflib)
+    prim = fx.primary_rays(4096, 4096, rows=(1900, 2156), **fx.C2_CAMERA)  # 256 rows through the middle of the frame: 1 048 576 rays
+    drv.trace(rsc, prim, coherent=True)
+    mine = fx.primary_rays(4096, 4096, rows=(1900, 2156), **fx.C2_CAMERA)
+    product.intersect(sc, mine, coherent=True)
+    res = parity.compare_closest(mine, prim)
+    assert res["pass"], res
+    for seed in (0, 1):
+        d = fx.diffuse_rays(prim, sample_id=seed)
+        a, b = d.copy(), d.copy()
+        product.intersect(sc, a)
+        drv.trace(rsc, b)
+        res = parity.compare_closest(a, b)
+        print("c3 diffuse seed", seed, {k: res[k] for k in ("rays", "hits_ours", "agreement", "hitmiss_disagree", "id_disagree", "max_t_rel", "max_uv_abs")})
+        assert res["pass"] and len(d) > 1000000, res
+    s = fx.shadow_rays(prim)
+    a, b = s.copy(), s.copy()
+    product.occluded(sc, a)
+    drv.trace(rsc, b, occluded=True)
+    res = parity.compare_occluded(a, b)
+    assert res["pass"] and res["disagree"] <= 1e-4 * len(s), res
+    assert product.lib.rtcGetDeviceError(dev) == 0
+    reflib.lib.rtcReleaseScene(rsc); reflib.lib.rtcReleaseDevice(rdev)
+    product.lib.rtcReleaseScene(sc); product.lib.rtcReleaseDevice(dev)

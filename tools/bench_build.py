@@ -49,6 +49,7 @@ def ours(lib, meshes, cfg, rays):
     out = w.cpu().numpy().reshape(-1).view(rt.RAYHIT_DTYPE)
     res = {"device_ms": st["msTotal"], "mtris_per_s_device": st["numPrimsValid"] / st["msTotal"] / 1e3, "commit_wall_ms": min(walls),
            "mtris_per_s_wall": st["numPrimsValid"] / min(walls) / 1e3, "sah": st["sah"], "sahExact": st["sahExact"], "nodes": st["numNodes"],
+           "sahInner": st["sahInner"], "sahLeafTris": st["sahLeafTris"], "sah_blocks_of_4_equivalent": st["sahInner"] + st["sahLeafTris"] / 4.0,
            "depth": st["depth"], "image_gb": st["bytes"] / 1e9, "phases_ms": {k: st[k] for k in ("msPrims", "msSort", "msHierarchy", "msRefit", "msEmit")},
            "probe_mrays_per_s": len(rays) / best / 1e6, "probe_hits": int((out["geomID"] != 0xFFFFFFFF).sum())}
     lib.lib.rtcReleaseScene(sc); lib.lib.rtcReleaseDevice(dev)
@@ -68,7 +69,7 @@ def capture_stdout(fn):
         return r, tmp.read().decode()
 
 
-def reference(ref, meshes, rays):
+def reference_build(ref, meshes, rays):
     dev = ref.new_device("benchmark=1")
     t0 = time.perf_counter()
     (sc, keep), out = capture_stdout(lambda: ref.build_scene(dev, meshes))
@@ -93,19 +94,19 @@ def reference(ref, meshes, rays):
     return res, r
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--sizes", default="10,20,50")
-    ap.add_argument("--kinds", default="scene,soup")
-    ap.add_argument("--no-reference", action="store_true")
-    ap.add_argument("--ref-max", type=float, default=20)
-    a = ap.parse_args()
+LAUNCHES = [0]
+BUILDERS = (("ours", ""), ("ploc", "gpu_builder=ploc"), ("lbvh", "gpu_builder=lbvh"))
+
+
+def run(sizes=(10.0, 20.0, 50.0), kinds=("scene", "soup"), reference=True, ref_max=20.0, builders=BUILDERS, emit=None):
+    """One row per (kind, size): every builder front end ('ours' = the device default), the reference's builder beside it."""
     parity = importlib.import_module("embree-aarch64_b200.parity")
     lib = rt.RTCore()
     from oracle.rq_oracle import REF_LIB
-    ref = rt.RTCore(REF_LIB) if (not a.no_reference and os.path.exists(REF_LIB)) else None
-    for kind in a.kinds.split(","):
-        for m in [float(x) for x in a.sizes.split(",")]:
+    ref = rt.RTCore(REF_LIB) if (reference and os.path.exists(REF_LIB)) else None
+    rows = []
+    for kind in kinds:
+        for m in sizes:
             if kind == "scene":
                 meshes = fx.scene_c3(float(np.sqrt(m / 10.0)))
                 lo, hi = (-9.0, 0.5, -9.0), (9.0, 4.0, 9.0)
@@ -116,14 +117,28 @@ def main():
             rays = probe_rays(1 << 22, lo, hi)
             line = {"kind": kind, "triangles": n}
             outs = {}
-            for name, cfg in (("ploc", "gpu_builder=ploc"), ("lbvh", "gpu_builder=lbvh")):
+            for name, cfg in builders:
                 line[name], outs[name] = ours(lib, meshes, cfg, rays)
-            if ref is not None and m <= a.ref_max:
-                line["reference"], rr = reference(ref, meshes, rays)
-                c = parity.compare_closest(outs["ploc"][:len(rr)], rr)
+            if ref is not None and m <= ref_max:
+                line["reference"], rr = reference_build(ref, meshes, rays)
+                c = parity.compare_closest(outs[builders[0][0]][:len(rr)], rr)
                 line["parity_vs_reference_1M_rays"] = {k: c[k] for k in ("pass", "agreement", "hitmiss_disagree", "id_disagree_unexplained", "max_t_rel", "max_uv_abs")}
-            print(json.dumps(line), flush=True)
+            rows.append(line)
+            if emit:
+                emit(line)
             del meshes, rays, outs
+    LAUNCHES[0] = int(lib.lib.rtcxGetLaunchCount())
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="10,20,50")
+    ap.add_argument("--kinds", default="scene,soup")
+    ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--ref-max", type=float, default=20)
+    a = ap.parse_args()
+    run([float(x) for x in a.sizes.split(",")], a.kinds.split(","), not a.no_reference, a.ref_max, emit=lambda l: print(json.dumps(l), flush=True))
 
 
 if __name__ == "__main__":
