@@ -139,19 +139,33 @@ k_setup_prims(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t N,
     dst[1] = make_float4(t.v1[1], t.v1[2], t.v2[0], t.v2[1]);
     dst[2] = make_float4(t.v2[2], __uint_as_float(t.primID), __uint_as_float(t.geomID), __uint_as_float(t.pad));
   }
-  // block reduction: warp shuffles, then one atomic per warp and slot
+  // block reduction: warp shuffles, shared memory across the 8 warps, then one atomic per block and slot
+  // (one atomic set per WARP meant 312 K x 12 same-address L2 atomics for 10 M triangles: 0.6 ms of the phase)
+  __shared__ float red[8][12];
+  __shared__ unsigned redInvalid[8];
   const unsigned nInvalid = __popc(__ballot_sync(0xffffffffu, (g < N) && !valid));
   for (int k = 0; k < 3; k++) {
     lo[k] = warpMin(lo[k]); hi[k] = warpMax(hi[k]); clo[k] = warpMin(clo[k]); chi[k] = warpMax(chi[k]);
   }
+  const int warp = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
-    if (lo[0] <= hi[0]) {
-      for (int k = 0; k < 3; k++) {
-        atomicMin(&bounds->sceneLo[k], f2ord(lo[k])); atomicMax(&bounds->sceneHi[k], f2ord(hi[k]));
-        atomicMin(&bounds->centLo[k], f2ord(clo[k])); atomicMax(&bounds->centHi[k], f2ord(chi[k]));
-      }
-    }
-    if (nInvalid) atomicAdd(invalidCount, nInvalid);
+    for (int k = 0; k < 3; k++) { red[warp][k] = lo[k]; red[warp][3 + k] = hi[k]; red[warp][6 + k] = clo[k]; red[warp][9 + k] = chi[k]; }
+    redInvalid[warp] = nInvalid;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    const bool isMin = threadIdx.x < 3 || (threadIdx.x >= 6 && threadIdx.x < 9);
+    float v = red[0][threadIdx.x];
+    for (int w = 1; w < 8; w++) v = isMin ? fminf(v, red[w][threadIdx.x]) : fmaxf(v, red[w][threadIdx.x]);
+    uint32_t* dst = threadIdx.x < 3 ? &bounds->sceneLo[threadIdx.x] : threadIdx.x < 6 ? &bounds->sceneHi[threadIdx.x - 3]
+                  : threadIdx.x < 9 ? &bounds->centLo[threadIdx.x - 6] : &bounds->centHi[threadIdx.x - 9];
+    // an all-invalid block holds +/-FLT_MAX sentinels: they never win against a real bound
+    if (isMin) { if (v < FLT_MAX) atomicMin(dst, f2ord(v)); } else { if (v > -FLT_MAX) atomicMax(dst, f2ord(v)); }
+  }
+  if (threadIdx.x == 12) {
+    unsigned tot = 0;
+    for (int w = 0; w < 8; w++) tot += redInvalid[w];
+    if (tot) atomicAdd(invalidCount, tot);
   }
 }
 
@@ -170,7 +184,7 @@ __device__ __forceinline__ uint64_t expand21(uint32_t v) {    // spread 21 bits 
 
 __global__ void __launch_bounds__(256)
 k_morton(const RQTri* __restrict__ trisIn, uint32_t N, const Bounds12* __restrict__ bounds,
-         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int cubic) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= N) return;
   const float4* src = (const float4*)(trisIn + g);
@@ -179,11 +193,16 @@ k_morton(const RQTri* __restrict__ trisIn, uint32_t N, const Bounds12* __restric
   if (__float_as_uint(c.w) != RQ_PAD_INVALID) {
     const float v0[3] = {a.x, a.y, a.z}, v1[3] = {a.w, b.x, b.y}, v2[3] = {b.z, b.w, c.x};
     uint32_t q[3];
+    // cubic: one scale for all axes (the largest centroid extent), so a Morton cell is a cube.  With per-axis scales a flat
+    // scene gets cells that are as flat as the scene, and the bits of the short axis split neighbouring triangles by height
+    // before the long axes have separated them (noisy terrain: 10 M-triangle scene, SAH 28.9 per-axis vs cubic).
+    float extMax = 0.f;
+    for (int k = 0; k < 3; k++) extMax = fmaxf(extMax, ord2f(bounds->centHi[k]) - ord2f(bounds->centLo[k]));
     for (int k = 0; k < 3; k++) {
       const float lo = fminf(fminf(v0[k], v1[k]), v2[k]), hi = fmaxf(fmaxf(v0[k], v1[k]), v2[k]);
       const float cen = 0.5f * lo + 0.5f * hi;
       const float cl = ord2f(bounds->centLo[k]), ch = ord2f(bounds->centHi[k]);
-      const float ext = ch - cl;
+      const float ext = cubic ? extMax : ch - cl;
       float x = ext > 0.f ? (cen - cl) / ext : 0.f;
       x = fminf(fmaxf(x, 0.f), 1.f);
       q[k] = min(2097151u, (uint32_t)(x * 2097152.0f));
@@ -319,7 +338,7 @@ __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, i
 
 __global__ void __launch_bounds__(256)
 k_hierarchy(const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ left, uint32_t* __restrict__ right,
-            uint32_t* __restrict__ parent, uint32_t* __restrict__ rangeFirst) {
+            uint32_t* __restrict__ parent, uint32_t* __restrict__ rangeFirst, uint32_t* __restrict__ rangeLast = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -341,6 +360,7 @@ k_hierarchy(const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ lef
   const uint32_t L = (lo == gamma) ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
   const uint32_t R = (hi == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
   left[i] = L; right[i] = R; rangeFirst[i] = (uint32_t)lo;
+  if (rangeLast) rangeLast[i] = (uint32_t)hi;
   parent[L] = (uint32_t)i; parent[R] = (uint32_t)i;
   if (i == 0) parent[0] = RQ_INVALID;
 }
@@ -430,11 +450,11 @@ __device__ __forceinline__ void combineNode(const B2& t, uint32_t cur, uint32_t 
 
 __global__ void __launch_bounds__(256)
 k_refit_dp(B2 t, int n, const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals,
-           float costNode, float costTri, int maxLeafTris) {
+           float costNode, float costTri, int maxLeafTris, int initLeaves = 1) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   uint32_t node = (uint32_t)(n - 1 + k);
-  initLeaf(t, node, trisIn, vals[k], costTri);
+  if (initLeaves) initLeaf(t, node, trisIn, vals[k], costTri);
   __threadfence();
   uint32_t cur = t.parent[node];
   while (cur != RQ_INVALID) {
@@ -572,6 +592,354 @@ k_ploc_compact(const uint32_t* __restrict__ cidIn, const uint32_t* __restrict__ 
   uint32_t off = blockOffset[blockIdx.x];
   for (int w = 0; w < warp; w++) off += warpSum[w];
   if (alive) cidOut[off + __popc(bal & ((1u << lane) - 1u))] = cidIn[i];
+}
+
+// ----------------------------------------------------------------------------------------------
+// 5c. Binned-SAH treelets (builder 2): the stage that replaces the reference's top-down binned-SAH recursion
+//     (kernels/builders/bvh_builder_sah.h:222-319, heuristic_binning.h:210-256 bin, :336-392 best,
+//     heuristic_binning_array_aligned.h:60-123 find / split) on the GPU.
+//
+//     The Morton order only decides which triangles are built TOGETHER: the radix tree over the sorted codes is cut into
+//     "treelets" -- maximal subtrees of at most K triangles, i.e. the triangles of one Morton cell, contiguous in the
+//     sorted array.  Inside a treelet the binary hierarchy is rebuilt top-down by the surface-area heuristic, by ONE WARP
+//     working in shared memory:
+//       * nodes of more than TL_SMALL triangles: 16 centroid bins on each of the 3 axes (shared-memory atomics on
+//         order-preserving uint keys), prefix / suffix box scans over the bins with width-16 shuffles (lanes 0..15 scan
+//         left to right, lanes 16..31 the mirrored bins, so one scan yields both sides), SAH = A_L n_L + A_R n_R for all
+//         45 candidate planes at once, warp arg-min, stable partition of the treelet's index permutation;
+//       * subtrees of at most TL_SMALL triangles: one THREAD each, exact sweep SAH -- the indices are insertion-sorted along
+//         each axis and every one of the m-1 split positions is evaluated (suffix areas in shared scratch), as a full-sweep
+//         builder does; 32 such subtrees are built at once by the lanes of the warp.
+//     Above the treelets the existing PLOC stage clusters the treelet roots (a few ten thousand boxes) and the SAH dynamic
+//     programme then cuts the binary tree into 8-wide nodes as before.
+//     Node ids: the T-1 nodes above the treelets take ids [0, T-1) (PLOC hands them out downwards, the root ends up as 0);
+//     treelet t, which starts at sorted position a_t and holds n_t triangles, owns ids T-1 + a_t - t + [0, n_t - 1), and the
+//     subtree over a range of m triangles rooted at local index j uses [j, j+m-1): left child j+1, right child j+m_left.
+// ----------------------------------------------------------------------------------------------
+constexpr int TL_BINS = 16;
+constexpr int TL_SMALL = 16;
+constexpr uint32_t TL_ORD_PINF = 0xFF800000u;                 // f2ord(+inf)
+constexpr uint32_t TL_ORD_NINF = 0x007FFFFFu;                 // f2ord(-inf)
+
+// which sorted positions start a treelet, and how large it is (0 = not a start)
+__global__ void __launch_bounds__(256)
+k_treelet_mark(int n, const uint32_t* __restrict__ rparent, const uint32_t* __restrict__ rfirst, const uint32_t* __restrict__ rlast,
+               uint32_t K, uint32_t* __restrict__ sizeAt) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= 2 * n - 1) return;
+  const uint32_t par = rparent[x];
+  const uint32_t psize = (par == RQ_INVALID) ? 0xFFFFFFFFu : rlast[par] - rfirst[par] + 1u;
+  if (x < n - 1) {
+    const uint32_t size = rlast[x] - rfirst[x] + 1u;
+    if (size <= K && psize > K) sizeAt[rfirst[x]] = size;
+  } else if (psize > K) {
+    sizeAt[x - (n - 1)] = 1u;                                   // a single triangle directly below a large node
+  }
+}
+
+constexpr int TLS_THREADS = 256, TLS_ITEMS = 4, TLS_TILE = TLS_THREADS * TLS_ITEMS;
+__global__ void __launch_bounds__(TLS_THREADS)
+k_treelet_count(const uint32_t* __restrict__ sizeAt, uint32_t n, uint32_t* __restrict__ blockCount) {
+  const uint32_t base = blockIdx.x * TLS_TILE + threadIdx.x * TLS_ITEMS;
+  int c = 0;
+  #pragma unroll
+  for (int i = 0; i < TLS_ITEMS; i++) if (base + i < n && sizeAt[base + i] != 0u) c++;
+  __shared__ uint32_t wsum[TLS_THREADS / 32];
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = (uint32_t)c;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < TLS_THREADS / 32; w++) t += wsum[w]; blockCount[blockIdx.x] = t; }
+}
+// one block: per-block counts -> exclusive offsets (in place), total -> *total
+__global__ void __launch_bounds__(1024)
+k_treelet_scan(uint32_t* __restrict__ blockCount, uint32_t numBlocks, uint32_t* __restrict__ total) {
+  __shared__ uint32_t part[1024];
+  const uint32_t chunk = (numBlocks + 1023u) / 1024u;
+  const uint32_t b0 = min(threadIdx.x * chunk, numBlocks), e0 = min(b0 + chunk, numBlocks);
+  uint32_t sum = 0;
+  for (uint32_t k = b0; k < e0; k++) sum += blockCount[k];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const uint32_t v = (int)threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - sum;
+  for (uint32_t k = b0; k < e0; k++) { const uint32_t v = blockCount[k]; blockCount[k] = run; run += v; }
+  if (threadIdx.x == 1023) *total = part[1023];
+}
+__global__ void __launch_bounds__(TLS_THREADS)
+k_treelet_write(const uint32_t* __restrict__ sizeAt, uint32_t n, const uint32_t* __restrict__ blockOffset, uint32_t* __restrict__ treeletStart) {
+  __shared__ uint32_t wsum[TLS_THREADS / 32];
+  const uint32_t base = blockIdx.x * TLS_TILE + threadIdx.x * TLS_ITEMS;
+  bool f[TLS_ITEMS]; uint32_t c = 0;
+  #pragma unroll
+  for (int i = 0; i < TLS_ITEMS; i++) { f[i] = base + i < n && sizeAt[base + i] != 0u; c += f[i] ? 1u : 0u; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = c;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  uint32_t off = blockOffset[blockIdx.x] + incl - c;
+  for (int w = 0; w < warp; w++) off += wsum[w];
+  #pragma unroll
+  for (int i = 0; i < TLS_ITEMS; i++) if (f[i]) treeletStart[off++] = base + i;
+}
+// the clusters PLOC starts from: the root of every treelet, in Morton order
+__global__ void __launch_bounds__(256)
+k_treelet_roots(int n, const uint32_t* __restrict__ treeletStart, const uint32_t* __restrict__ sizeAt, uint32_t T, uint32_t* __restrict__ cid) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const uint32_t a = treeletStart[t];
+  cid[t] = sizeAt[a] == 1u ? (uint32_t)(n - 1) + a : (T - 1u) + (a - t);
+}
+
+template <int K>
+struct TreeletSmem {                                           // one per warp
+  float    box[6][K];                                          // lo.xyz, hi.xyz of the treelet's triangles (SoA: lane-strided access is conflict free)
+  uint16_t perm[K], perm2[K];                                  // the treelet's triangles, partitioned in place node by node
+  uint32_t bins[3][TL_BINS][7];                                // per axis and bin: ordered-uint lo.xyz, hi.xyz, count
+  uint32_t stack[16][2];                                       // pending large nodes: begin | end << 16, local node index
+  uint32_t small[K / 2][2];                                    // subtrees left to the thread phase, same encoding
+  float    keys[TL_SMALL][32];                                 // thread phase: sort keys of the lane's current node
+  float    suffix[TL_SMALL][32];                               // thread phase: right-side areas of the lane's current node
+};
+
+__device__ __forceinline__ float boxArea6(const float lo[3], const float hi[3]) {
+  return halfArea(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
+}
+
+// one lane builds the subtree over perm[b0, e0) (2 <= e0 - b0 <= TL_SMALL) rooted at local node index j0
+template <int K>
+__device__ void treeletSmallSubtree(TreeletSmem<K>& S, const B2& t, uint32_t b0, uint32_t e0, uint32_t j0, uint32_t base, uint32_t leaf0, int lane) {
+  uint32_t st[TL_SMALL]; int sp = 0;
+  st[sp++] = b0 | (e0 << 10) | (j0 << 20);
+  while (sp > 0) {
+    const uint32_t w = st[--sp];
+    const uint32_t b = w & 1023u, e = (w >> 10) & 1023u, j = w >> 20;
+    const int m = (int)(e - b);
+    int split = 1;
+    if (m > 2) {
+      float best = INFINITY; int bestAxis = -1;
+      for (int a = 0; a < 3; a++) {
+        // insertion sort of the index slice along axis a (key = 2 x centroid; ties keep the lower index first)
+        for (int i = 0; i < m; i++) { const uint32_t p = S.perm[b + i]; S.keys[i][lane] = S.box[a][p] + S.box[3 + a][p]; }
+        for (int i = 1; i < m; i++) {
+          const float k = S.keys[i][lane]; const uint16_t p = S.perm[b + i];
+          int q = i - 1;
+          while (q >= 0 && (S.keys[q][lane] > k || (S.keys[q][lane] == k && S.perm[b + q] > p))) {
+            S.keys[q + 1][lane] = S.keys[q][lane]; S.perm[b + q + 1] = S.perm[b + q]; q--;
+          }
+          S.keys[q + 1][lane] = k; S.perm[b + q + 1] = p;
+        }
+        // right to left: area of the box of prims [i, m)
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = m - 1; i >= 1; i--) {
+          const uint32_t p = S.perm[b + i];
+          for (int c = 0; c < 3; c++) { lo[c] = fminf(lo[c], S.box[c][p]); hi[c] = fmaxf(hi[c], S.box[3 + c][p]); }
+          S.suffix[i][lane] = boxArea6(lo, hi);
+        }
+        // left to right: SAH of every split position
+        for (int c = 0; c < 3; c++) { lo[c] = INFINITY; hi[c] = -INFINITY; }
+        for (int i = 1; i < m; i++) {
+          const uint32_t p = S.perm[b + i - 1];
+          for (int c = 0; c < 3; c++) { lo[c] = fminf(lo[c], S.box[c][p]); hi[c] = fmaxf(hi[c], S.box[3 + c][p]); }
+          const float cost = boxArea6(lo, hi) * (float)i + S.suffix[i][lane] * (float)(m - i);
+          if (cost < best) { best = cost; bestAxis = a; split = i; }
+        }
+      }
+      if (bestAxis < 0) split = m >> 1;                         // non-finite areas: object median in the current order
+      else if (bestAxis != 2) {                                 // the slice is sorted along z now: restore the winning order
+        const int a = bestAxis;
+        for (int i = 0; i < m; i++) { const uint32_t p = S.perm[b + i]; S.keys[i][lane] = S.box[a][p] + S.box[3 + a][p]; }
+        for (int i = 1; i < m; i++) {
+          const float k = S.keys[i][lane]; const uint16_t p = S.perm[b + i];
+          int q = i - 1;
+          while (q >= 0 && (S.keys[q][lane] > k || (S.keys[q][lane] == k && S.perm[b + q] > p))) {
+            S.keys[q + 1][lane] = S.keys[q][lane]; S.perm[b + q + 1] = S.perm[b + q]; q--;
+          }
+          S.keys[q + 1][lane] = k; S.perm[b + q + 1] = p;
+        }
+      }
+    }
+    const uint32_t mL = (uint32_t)split, mR = (uint32_t)m - mL;
+    const uint32_t jL = j + 1u, jR = j + mL;
+    const uint32_t g = base + j;
+    const uint32_t refL = mL == 1u ? leaf0 + S.perm[b] : base + jL;
+    const uint32_t refR = mR == 1u ? leaf0 + S.perm[b + mL] : base + jR;
+    t.left[g] = refL; t.right[g] = refR; t.parent[refL] = g; t.parent[refR] = g;
+    if (mR >= 2u) st[sp++] = (b + mL) | (e << 10) | (jR << 20);
+    if (mL >= 2u) st[sp++] = b | ((b + mL) << 10) | (jL << 20);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128)
+k_treelet_build(B2 t, int n, const uint32_t* __restrict__ treeletStart, const uint32_t* __restrict__ sizeAt, uint32_t T) {
+  extern __shared__ __align__(16) unsigned char tlSmemRaw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  TreeletSmem<K>& S = reinterpret_cast<TreeletSmem<K>*>(tlSmemRaw)[warp];
+  const uint32_t tIdx = blockIdx.x * 4u + (uint32_t)warp;
+  if (tIdx >= T) return;                                        // warps are independent: no block-wide barrier below
+  const uint32_t a0 = treeletStart[tIdx], m0 = sizeAt[a0];
+  if (m0 < 2u || m0 > (uint32_t)K) return;                      // a single triangle is its own cluster
+  const uint32_t base = (T - 1u) + (a0 - tIdx);                 // global id of this treelet's local node 0 (its root)
+  const uint32_t leaf0 = (uint32_t)(n - 1) + a0;                // global id of this treelet's first triangle (binary-tree leaf)
+  for (uint32_t i = lane; i < m0; i += 32u) {
+    const float4 lo = t.lo[leaf0 + i], hi = t.hi[leaf0 + i];
+    S.box[0][i] = lo.x; S.box[1][i] = lo.y; S.box[2][i] = lo.z; S.box[3][i] = hi.x; S.box[4][i] = hi.y; S.box[5][i] = hi.z;
+    S.perm[i] = (uint16_t)i;
+  }
+  int sp = 0, nsmall = 0;                                       // warp-uniform
+  if (m0 > (uint32_t)TL_SMALL) { if (lane == 0) { S.stack[0][0] = m0 << 16; S.stack[0][1] = 0u; } sp = 1; }
+  else { if (lane == 0) { S.small[0][0] = m0 << 16; S.small[0][1] = 0u; } nsmall = 1; }
+  __syncwarp();
+
+  // ---------------- warp-cooperative phase: nodes of more than TL_SMALL triangles ----------------
+  while (sp > 0) {
+    --sp;
+    const uint32_t be = S.stack[sp][0], j = S.stack[sp][1];
+    const uint32_t b = be & 0xFFFFu, e = be >> 16, m = e - b;
+    // centroid bounds (of lo + hi = twice the centroid, like the reference's PrimRef::center2)
+    float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = b + lane; i < e; i += 32u) {
+      const uint32_t p = S.perm[i];
+      #pragma unroll
+      for (int a = 0; a < 3; a++) { const float c = S.box[a][p] + S.box[3 + a][p]; cmin[a] = fminf(cmin[a], c); cmax[a] = fmaxf(cmax[a], c); }
+    }
+    #pragma unroll
+    for (int a = 0; a < 3; a++) { cmin[a] = warpMin(cmin[a]); cmax[a] = warpMax(cmax[a]); }
+    float scale[3];
+    #pragma unroll
+    for (int a = 0; a < 3; a++) scale[a] = cmax[a] > cmin[a] ? ((float)TL_BINS * 0.999f) / (cmax[a] - cmin[a]) : 0.f;
+    // ---- bin (heuristic_binning.h:210-256) ----
+    for (int w = lane; w < 3 * TL_BINS * 7; w += 32) {
+      const int f = w % 7;
+      (&S.bins[0][0][0])[w] = f < 3 ? TL_ORD_PINF : (f < 6 ? TL_ORD_NINF : 0u);
+    }
+    __syncwarp();
+    for (uint32_t i = b + lane; i < e; i += 32u) {
+      const uint32_t p = S.perm[i];
+      const float lx = S.box[0][p], ly = S.box[1][p], lz = S.box[2][p], hx = S.box[3][p], hy = S.box[4][p], hz = S.box[5][p];
+      const uint32_t olx = f2ord(lx), oly = f2ord(ly), olz = f2ord(lz), ohx = f2ord(hx), ohy = f2ord(hy), ohz = f2ord(hz);
+      const float c[3] = {lx + hx, ly + hy, lz + hz};
+      #pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const int bin = min(TL_BINS - 1, (int)((c[a] - cmin[a]) * scale[a]));
+        uint32_t* B = S.bins[a][bin];
+        atomicMin(&B[0], olx); atomicMin(&B[1], oly); atomicMin(&B[2], olz);
+        atomicMax(&B[3], ohx); atomicMax(&B[4], ohy); atomicMax(&B[5], ohz);
+        atomicAdd(&B[6], 1u);
+      }
+    }
+    __syncwarp();
+    // ---- best (heuristic_binning.h:336-392): lanes 0..15 accumulate bins 0..idx, lanes 16..31 bins 15..15-idx ----
+    const int half = lane >> 4, idx = lane & 15;
+    const int myBin = half ? (TL_BINS - 1 - idx) : idx;
+    float bestCost = INFINITY; uint32_t bestKey = 0xFFFFFFFFu, bestLeft = 0u;
+    #pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const uint32_t* B = S.bins[a][myBin];
+      float lo[3] = {ord2f(B[0]), ord2f(B[1]), ord2f(B[2])}, hi[3] = {ord2f(B[3]), ord2f(B[4]), ord2f(B[5])};
+      uint32_t cnt = B[6];
+      #pragma unroll
+      for (int d = 1; d < TL_BINS; d <<= 1) {
+        float vlo[3], vhi[3];
+        #pragma unroll
+        for (int c = 0; c < 3; c++) { vlo[c] = __shfl_up_sync(FULL, lo[c], d, 16); vhi[c] = __shfl_up_sync(FULL, hi[c], d, 16); }
+        const uint32_t vc = __shfl_up_sync(FULL, cnt, d, 16);
+        if (idx >= d) {
+          #pragma unroll
+          for (int c = 0; c < 3; c++) { lo[c] = fminf(lo[c], vlo[c]); hi[c] = fmaxf(hi[c], vhi[c]); }
+          cnt += vc;
+        }
+      }
+      const float area = cnt ? boxArea6(lo, hi) : 0.f;
+      // plane idx (between bin idx and idx+1): left = lanes' own prefix, right = the mirrored prefix of lane 30 - idx
+      const int src = (30 - idx) & 31;
+      const float areaR = __shfl_sync(FULL, area, src);
+      const uint32_t cntR = __shfl_sync(FULL, cnt, src);
+      if (half == 0 && idx < TL_BINS - 1 && cnt != 0u && cntR != 0u) {
+        const float cost = area * (float)cnt + areaR * (float)cntR;
+        if (cost < bestCost) { bestCost = cost; bestKey = ((uint32_t)a << 8) | (uint32_t)idx; bestLeft = cnt; }
+      }
+    }
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float oc = __shfl_xor_sync(FULL, bestCost, o);
+      const uint32_t ok = __shfl_xor_sync(FULL, bestKey, o), ol = __shfl_xor_sync(FULL, bestLeft, o);
+      if (oc < bestCost || (oc == bestCost && ok < bestKey)) { bestCost = oc; bestKey = ok; bestLeft = ol; }
+    }
+    uint32_t mL;
+    if (bestKey == 0xFFFFFFFFu) {
+      mL = m >> 1;                                              // all centroids in one bin on every axis: object median, order kept
+    } else {
+      // ---- split (heuristic_binning_array_aligned.h:79-123): stable partition of the index slice through perm2 ----
+      const int a = (int)(bestKey >> 8), pos = (int)(bestKey & 255u);
+      mL = bestLeft;
+      uint32_t offL = 0u, offR = 0u;
+      for (uint32_t i0 = b; i0 < e; i0 += 32u) {
+        const uint32_t i = i0 + lane;
+        const bool ok = i < e;
+        uint32_t p = 0u; bool left = false;
+        if (ok) {
+          p = S.perm[i];
+          const float c = S.box[a][p] + S.box[3 + a][p];
+          left = min(TL_BINS - 1, (int)((c - cmin[a]) * scale[a])) <= pos;
+        }
+        const unsigned lm = __ballot_sync(FULL, ok && left), rm = __ballot_sync(FULL, ok && !left);
+        const unsigned below = (1u << lane) - 1u;
+        if (ok) {
+          if (left) S.perm2[b + offL + __popc(lm & below)] = (uint16_t)p;
+          else S.perm2[b + mL + offR + __popc(rm & below)] = (uint16_t)p;
+        }
+        offL += __popc(lm); offR += __popc(rm);
+      }
+      __syncwarp();
+      for (uint32_t i = b + lane; i < e; i += 32u) S.perm[i] = S.perm2[i];
+      __syncwarp();
+    }
+    const uint32_t mR = m - mL, jL = j + 1u, jR = j + mL;
+    if (lane == 0) {
+      const uint32_t g = base + j;
+      const uint32_t refL = mL == 1u ? leaf0 + S.perm[b] : base + jL;
+      const uint32_t refR = mR == 1u ? leaf0 + S.perm[b + mL] : base + jR;
+      t.left[g] = refL; t.right[g] = refR; t.parent[refL] = g; t.parent[refR] = g;
+    }
+    // children: large ones back on the stack (the larger first, so the smaller is split next and the stack stays
+    // logarithmic), small ones to the thread phase
+    const uint32_t cb[2] = {b, b + mL}, ce[2] = {b + mL, e}, cj[2] = {jL, jR};
+    const int first = mL >= mR ? 0 : 1;
+    #pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int c = q == 0 ? first : 1 - first;
+      const uint32_t cm = ce[c] - cb[c];
+      if (cm < 2u) continue;
+      // (every stacked range is at least as large as all ranges above it together, so at most log2(K / TL_SMALL) + 1 <= 6 are pending)
+      if (cm > (uint32_t)TL_SMALL) { if (lane == 0) { S.stack[sp][0] = cb[c] | (ce[c] << 16); S.stack[sp][1] = cj[c]; } sp++; }
+      else { if (lane == 0) { S.small[nsmall][0] = cb[c] | (ce[c] << 16); S.small[nsmall][1] = cj[c]; } nsmall++; }
+    }
+    __syncwarp();
+  }
+
+  // ---------------- thread phase: one lane per small subtree ----------------
+  for (int s0 = 0; s0 < nsmall; s0 += 32) {
+    const int s = s0 + lane;
+    if (s < nsmall) {
+      const uint32_t be = S.small[s][0];
+      treeletSmallSubtree<K>(S, t, be & 0xFFFFu, be >> 16, S.small[s][1], base, leaf0, lane);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_leaf_init(B2 t, int n, const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals, float costTri) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  initLeaf(t, (uint32_t)(n - 1 + k), trisIn, vals[k], costTri);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -811,7 +1179,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   ScratchScope scratch(stream);
   t_scratchStream = stream;
   int err = 0;
-  RQBuildParams P = {1.0f, 1.0f, 3, 0, 1, 8};
+  RQBuildParams P = {1.0f, 1.0f, 3, 0, 2, 8, 1, 512};
   if (params) P = *params;
   if (P.maxLeafTris < 1) P.maxLeafTris = 1;
   if (P.maxLeafTris > 3) P.maxLeafTris = 3;
@@ -826,6 +1194,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   DevBuf<RQGeomDesc> dGeoms; DevBuf<RQTri> trisIn, trisOut; DevBuf<uint64_t> keys0, keys1;
   DevBuf<uint32_t> vals0, vals1, hist, digitTotal, left, right, parent, rangeFirst, flag, dec, qParent0, qParent1;
   DevBuf<uint32_t> cid0, cid1, nnBuf, blockCount, plocCtr; uint32_t plocIters = 0;
+  DevBuf<uint32_t> rparent, rfirst, rlast, sizeAt, tlStart, tlBlock, tlTotal; uint32_t numTreelets = 0;
   DevBuf<float4> blo, bhi; DevBuf<float> cost; DevBuf<uint2> queue0, queue1; DevBuf<RQNode> nodes;
   DevBuf<Bounds12> dBounds; DevBuf<uint32_t> dInvalid; DevBuf<EmitCounters> dCtr;
   Bounds12 hb; uint32_t hInvalid = 0; EmitCounters hc;
@@ -848,7 +1217,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     CK(cudaMemcpyAsync(dGeoms.p, hg.data(), sizeof(RQGeomDesc) * numGeoms, cudaMemcpyHostToDevice, stream));
     CK(trisIn.alloc(N)); CK(keys0.alloc(N)); CK(keys1.alloc(N)); CK(vals0.alloc(N)); CK(vals1.alloc(N));
     k_setup_prims<<<blocksFor(N, 256), 256, 0, stream>>>(dGeoms.p, numGeoms, N, trisIn.p, dBounds.p, dInvalid.p);
-    k_morton<<<blocksFor(N, 256), 256, 0, stream>>>(trisIn.p, N, dBounds.p, keys0.p, vals0.p);
+    k_morton<<<blocksFor(N, 256), 256, 0, stream>>>(trisIn.p, N, dBounds.p, keys0.p, vals0.p, P.mortonCubic);
     rqCountLaunch(2);
     CK(cudaGetLastError());
   }
@@ -888,19 +1257,57 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       t.parent = parent.p; t.rangeFirst = rangeFirst.p; t.flag = flag.p;
       CK(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t) * n, stream));
       CK(cudaMemsetAsync(parent.p, 0xFF, sizeof(uint32_t) * n2, stream));
-      if (P.builder == 1 && n > 1) {
-        // ---- PLOC: iterate nearest-neighbour search / merge / compaction until one cluster is left ----
+      if ((P.builder == 1 || P.builder == 2) && n > 1) {
         const int radius = P.plocRadius < 1 ? 1 : (P.plocRadius > PLOC_MAX_RADIUS ? PLOC_MAX_RADIUS : P.plocRadius);
         CK(cid0.alloc(n)); CK(cid1.alloc(n)); CK(nnBuf.alloc(n)); CK(blockCount.alloc(blocksFor(n, PLOC_THREADS) + 1)); CK(plocCtr.alloc(5));
+        uint32_t m0 = n;                                          // clusters PLOC starts from
+        if (P.builder == 2) {
+          // ---- binned-SAH treelets: radix tree -> treelet cut -> one warp per treelet -> bottom-up bounds + collapse programme ----
+          const uint32_t K = P.treeletSize >= 512 ? 512u : 256u;
+          const uint32_t numTiles = blocksFor(n, TLS_TILE);
+          CK(rparent.alloc(n2)); CK(rfirst.alloc(n)); CK(rlast.alloc(n)); CK(sizeAt.alloc(n)); CK(tlStart.alloc(n)); CK(tlBlock.alloc(numTiles + 1)); CK(tlTotal.alloc(1));
+          CK(cudaMemsetAsync(rparent.p, 0xFF, sizeof(uint32_t) * n2, stream));
+          CK(cudaMemsetAsync(sizeAt.p, 0, sizeof(uint32_t) * n, stream));
+          // the radix tree is only consulted for its ranges; its child arrays land in buffers PLOC overwrites later
+          k_hierarchy<<<blocksFor(n - 1, 256), 256, 0, stream>>>(keys0.p, (int)n, cid0.p, cid1.p, rparent.p, rfirst.p, rlast.p);
+          k_treelet_mark<<<blocksFor(2 * (size_t)n - 1, 256), 256, 0, stream>>>((int)n, rparent.p, rfirst.p, rlast.p, K, sizeAt.p);
+          k_treelet_count<<<numTiles, TLS_THREADS, 0, stream>>>(sizeAt.p, n, tlBlock.p);
+          k_treelet_scan<<<1, 1024, 0, stream>>>(tlBlock.p, numTiles, tlTotal.p);
+          k_treelet_write<<<numTiles, TLS_THREADS, 0, stream>>>(sizeAt.p, n, tlBlock.p, tlStart.p);
+          k_leaf_init<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costTri);
+          rqCountLaunch(6);
+          uint32_t T = 0;
+          CK(cudaMemcpyAsync(&T, tlTotal.p, 4, cudaMemcpyDeviceToHost, stream));
+          CK(cudaStreamSynchronize(stream));
+          CK(cudaGetLastError());
+          if (T == 0 || T > n) { err = (int)cudaErrorUnknown; goto fail; }
+          if (K == 512u) {
+            const size_t smem = 4 * sizeof(TreeletSmem<512>);
+            CK(cudaFuncSetAttribute(k_treelet_build<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_treelet_build<512><<<blocksFor(T, 4), 128, smem, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T);
+          } else {
+            const size_t smem = 4 * sizeof(TreeletSmem<256>);
+            CK(cudaFuncSetAttribute(k_treelet_build<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_treelet_build<256><<<blocksFor(T, 4), 128, smem, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T);
+          }
+          CK(cudaEventRecord(ev[3], stream));
+          k_refit_dp<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costNode, P.costTri, P.maxLeafTris, 0);
+          k_treelet_roots<<<blocksFor(T, 256), 256, 0, stream>>>((int)n, tlStart.p, sizeAt.p, T, cid0.p);
+          rqCountLaunch(3);
+          CK(cudaGetLastError());
+          m0 = T; numTreelets = T;
+        } else {
+          k_ploc_init<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costTri, cid0.p);
+          rqCountLaunch(1);
+          CK(cudaEventRecord(ev[3], stream));
+        }
+        // ---- PLOC: iterate nearest-neighbour search / merge / compaction until one cluster is left ----
         // counters on the device: [0] next inner node id, [1]/[2] cluster count of the current / next iteration (ping-pong),
         // [3] iterations that merged something, [4] blocks of the running merge kernel that are done.  The host reads the count back only every few iterations (to shrink the
         // grids and to detect the end); in between the kernels are launched for the last known upper bound.
-        const uint32_t initCtr[5] = {n - 2u, n, n, 0u, 0u};
+        const uint32_t initCtr[5] = {m0 >= 2u ? m0 - 2u : 0u, m0, m0, 0u, 0u};
         CK(cudaMemcpyAsync(plocCtr.p, initCtr, sizeof(initCtr), cudaMemcpyHostToDevice, stream));
-        k_ploc_init<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costTri, cid0.p);
-        rqCountLaunch(1);
-        CK(cudaEventRecord(ev[3], stream));
-        uint32_t m = n; uint32_t *cin = cid0.p, *cout = cid1.p;
+        uint32_t m = m0; uint32_t *cin = cid0.p, *cout = cid1.p;
         uint32_t it = 0;
         while (m > 1) {
           const unsigned nb = blocksFor(m, PLOC_THREADS);
@@ -990,6 +1397,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       stats->sahLeafTris = rootA > 0 ? hc.sahLeafTrisQ / rootA : 0.0;
       stats->bytes = H.totalBytes;
       stats->builderIterations = plocIters;
+      stats->numTreelets = numTreelets;
       cudaEventElapsedTime(&stats->msTotal, ev[0], ev[6]);
       cudaEventElapsedTime(&stats->msPrims, ev[0], ev[1]);
       cudaEventElapsedTime(&stats->msSort, ev[1], ev[2]);

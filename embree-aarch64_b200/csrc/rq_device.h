@@ -12,8 +12,11 @@ struct RQBuildParams {
   float costTri;         // SAH cost of testing one triangle               (default 0.3)
   int   maxLeafTris;     // triangles per leaf slot, 1..3                  (default 3)
   int   verbose;
-  int   builder;         // binary-tree front end: 0 = radix tree over Morton codes (LBVH), 1 = PLOC
+  int   builder;         // binary-tree front end: 0 = radix tree over Morton codes (LBVH), 1 = PLOC over the triangles,
+                         // 2 = binned-SAH treelets (top-down SAH inside Morton cells of <= treeletSize triangles, PLOC above them)
   int   plocRadius;      // PLOC search radius in Morton-order positions, 1..32          (default 8)
+  int   mortonCubic;     // 1 = Morton cells are cubes (one scale for all axes), 0 = per-axis normalisation
+  int   treeletSize;     // builder 2: largest treelet, 256 or 512 triangles
 };
 
 // A committed BVH living in device memory: one allocation, header first.

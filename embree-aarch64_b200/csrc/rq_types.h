@@ -126,6 +126,8 @@ struct RQBuildStats {
   uint32_t refitCount;        // refits applied to this BVH since its last full build (0 = freshly built)
   double   sahInner;          // inner-node term of `sah` alone (sah - sahInner = leaf term, one block per leaf slot)
   double   sahLeafTris;       // leaf term weighted by triangles: sum A(leaf slot) * numTris / A(root)
+  uint32_t numTreelets;       // binned-SAH treelets of the last full build (0 for the other front ends)
+  uint32_t pad;
 };
 
 // Per-call traversal counters (instrumented kernel variant only).

@@ -85,7 +85,7 @@ struct Device : RefCounted {
   bool hasGpu = false;
   int verbose = 0, benchmark = 0, async = 0;
   size_t chunkRays = 1u << 20;
-  RQBuildParams build{1.0f, 1.0f, 3, 0, 1, 8};   // PLOC front end by default: same-box A/B +1 % closest, +8 % occluded Mrays/s vs the radix tree (profiles/r01l_ab.log)
+  RQBuildParams build{1.0f, 1.0f, 3, 0, 2, 8, 1, 512};   // binned-SAH treelets + PLOC above them by default (gpu_builder=sah); see DESIGN.md 4.1 for the A/B against PLOC / radix tree
   cudaStream_t ownStream = nullptr, userStream = nullptr;
   std::mutex errMutex;
   RTCError error = RTC_ERROR_NONE;
@@ -133,6 +133,7 @@ struct Device : RefCounted {
   // packing reads the caller's 80-byte records at ~50 GB/s, the same rate the copy engine uploads them, and together with the
   // hit scatter the host memory system (~150 GB/s) becomes the bound; so the default leaves the host cores alone.
   int packRays = 0;
+  int packPageable = 1;                   // pageable caller memory is always packed by the host pool (see traceStreamCompact)
   int packDepth = 2;                      // hybrid: chunks allowed in the pack stage at once
   void* packHost[kRing] = {nullptr, nullptr, nullptr, nullptr};
   size_t packCap[kRing] = {0, 0, 0, 0};
@@ -236,7 +237,9 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "cost_node") d->build.costNode = (float)atof(v.c_str());
     else if (k == "cost_tri") d->build.costTri = (float)atof(v.c_str());
     else if (k == "leaf_tris") d->build.maxLeafTris = atoi(v.c_str());
-    else if (k == "gpu_builder") d->build.builder = (v == "ploc") ? 1 : 0;
+    else if (k == "gpu_builder") d->build.builder = (v == "sah") ? 2 : (v == "ploc") ? 1 : 0;
+    else if (k == "morton_cubic") d->build.mortonCubic = atoi(v.c_str()) != 0;
+    else if (k == "treelet") d->build.treeletSize = atoi(v.c_str()) >= 512 ? 512 : 256;
     else if (k == "ploc_radius") d->build.plocRadius = atoi(v.c_str());
     else if (k == "split_closest") d->splitClosest = atoi(v.c_str());
     else if (k == "stack_smem") d->stackSmem = std::max(0, std::min(16, atoi(v.c_str())));
@@ -246,6 +249,7 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "compact_min_rays") d->compactMinRays = (unsigned)std::max(0ll, atoll(v.c_str()));
     else if (k == "scatter_threads" || k == "host_threads") d->scatterThreads = atoi(v.c_str());
     else if (k == "pack_rays") d->packRays = atoi(v.c_str());
+    else if (k == "pack_pageable") d->packPageable = atoi(v.c_str());
     else if (k == "pack_depth") d->packDepth = std::max(1, atoi(v.c_str()));
     else if (k == "tvote") d->tVote = std::max(0, std::min(32, atoi(v.c_str())));
     else if (k == "split_occluded") d->splitOccluded = atoi(v.c_str());
@@ -484,7 +488,7 @@ void commitScene(Scene* sc) {
     // spatial splits here, which this builder does not do)
     if (!insts.empty()) bp.maxLeafTris = 1;                  // every instance gets its own child box: entering one costs a ray transform + a root fetch
     if (sc->quality == RTC_BUILD_QUALITY_LOW) bp.builder = 0;
-    else if (sc->quality == RTC_BUILD_QUALITY_HIGH) { bp.builder = 1; bp.plocRadius = std::max(bp.plocRadius, 16); }
+    else if (sc->quality == RTC_BUILD_QUALITY_HIGH) { bp.plocRadius = std::max(bp.plocRadius, 16); bp.treeletSize = 512; if (bp.builder == 0) bp.builder = 2; }
     cudaCheck(rqBuildBVH(descs.data(), (int)descs.size(), (uint32_t)sc->flags, &bp, (rqStream)s, &img, &st), "BVH build");
     if (sc->image.base) rqFreeImage(&sc->image);
     sc->image = img; sc->stats = st;
@@ -696,7 +700,13 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
   for (int r = 0; r < Device::kRing; r++)
     if (!dev->ringStream[r]) cudaCheck(cudaStreamCreateWithFlags(&dev->ringStream[r], cudaStreamNonBlocking), "stream");
   CompactCall call;
-  call.dev = dev; call.a = a; call.stride = stride; call.occluded = occluded; call.pack = dev->packRays != 0;
+  // Pageable caller memory (what a drop-in application hands over: malloc'ed rays): cudaMemcpyAsync would bounce it through the
+  // driver's own small staging buffer at ~12 GB/s, synchronously (measured 154 Mrays/s end to end against 693 from page-locked
+  // memory, profiles/r02a_bench.json).  The host pool packs it instead -- CPU loads from the caller's pages, streaming stores of the
+  // 32 bytes per ray the kernels read into page-locked staging -- so the link carries 32 instead of 80 / 48 bytes per ray.
+  const bool pageable = dev->packPageable && mappedHostPointer(rays) == nullptr;
+  call.dev = dev; call.a = a; call.stride = stride; call.occluded = occluded; call.pack = dev->packRays != 0 || pageable;
+  const bool packAll = dev->packRays >= 2 || pageable;
   call.recBytes = recBytes; call.recList = occluded ? 4 : 48; call.T = (unsigned)dev->hostPool().size();
   const unsigned numChunks = (unsigned)((M + chunk - 1) / chunk);
   std::vector<CompactChunk> chunks(numChunks);
@@ -748,7 +758,7 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
       // packed while fewer than packDepth chunks are in the pack stage, otherwise it goes to the copy engine as it is.
       {
         std::lock_guard<std::mutex> lk(call.m);
-        c->packed = call.pack && (dev->packRays >= 2 || call.packing < dev->packDepth);
+        c->packed = call.pack && (packAll || call.packing < dev->packDepth);
         if (c->packed) call.packing++;
         call.slotBusy[r] = true;
       }
@@ -828,7 +838,9 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
     }
     if (!dev->async || countersOut || mapped) cudaCheck(cudaStreamSynchronize(s), "trace");
-  } else if (dev->d2hMode == 3 && !mapped && !countersOut && !sc->numInstances && M >= dev->compactMinRays && M >= 65536 && stride >= recBytes &&
+  } else if (dev->d2hMode == 3 && !mapped && !countersOut && !sc->numInstances && M >= 65536 && stride >= recBytes &&
+             // page-locked streams below ~4 M rays are faster through whole-span copies; pageable ones never are (the driver bounces them)
+             (M >= dev->compactMinRays || (M >= (1u << 18) && dev->packPageable && mappedHostPointer(rays) == nullptr)) &&
              a.depth <= 32 + (unsigned)dev->stackSmem) {
     traceStreamCompact(dev, a, (char*)rays, M, stride, occluded, recBytes);
   } else if (!mapped && !countersOut && M < 65536) {
@@ -1499,7 +1511,8 @@ RTC_API void rtcOccluded1Mp(RTCScene hs, struct RTCIntersectContext* ctx, struct
   Scene* s = (Scene*)hs;
   RTC_TRY checkQuery(s, ctx); traceAoP(s, ctx, (void**)r, M, true); RTC_CATCH(devOf(s))
 }
-// rtcore.cpp:733-790,906-945: N == 1 is an AoS stream of M records, otherwise filterSOA: M packets of N lanes, packet rules
+// rtcore.cpp:733-790,906-945: N == 1 is an AoS stream of M records, otherwise filterSOA: M packets of N lanes.  Occlusion rays take
+// the filter's octant-sorting branch (stream_filters.cpp:333-404 -> occludedN), i.e. the stream entry rules
 RTC_API void rtcIntersectNM(RTCScene hs, struct RTCIntersectContext* ctx, struct RTCRayHitN* rh, unsigned int N, unsigned int M, size_t byteStride) {
   Scene* s = (Scene*)hs;
   RTC_TRY
@@ -1515,17 +1528,17 @@ RTC_API void rtcOccludedNM(RTCScene hs, struct RTCIntersectContext* ctx, struct 
     checkQuery(s, ctx);
     if (N == 1) traceStream(s, ctx, r, M, byteStride, true, sizeof(RTCRay), nullptr);
     else if ((unsigned long long)N * M > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_ARGUMENT, "too many rays in one call");
-    else traceSoA(s, ctx, viewOfN(r, N, byteStride, false), nullptr, N * M, true, 0);
+    else traceSoA(s, ctx, viewOfN(r, N, byteStride, false), nullptr, N * M, true, 1);
   RTC_CATCH(devOf(s))
 }
-// rtcore.cpp:792-846,947-974: filterSOP
+// rtcore.cpp:792-846,947-974: filterSOP (occlusion: octant-sorting branch, stream_filters.cpp:497-577 -> stream entry rules)
 RTC_API void rtcIntersectNp(RTCScene hs, struct RTCIntersectContext* ctx, const struct RTCRayHitNp* rh, unsigned int N) {
   Scene* s = (Scene*)hs;
   RTC_TRY checkQuery(s, ctx); VERIFY_HANDLE(rh); traceSoA(s, ctx, viewOfNp(&rh->ray, &rh->hit, N), nullptr, N, false, 0); RTC_CATCH(devOf(s))
 }
 RTC_API void rtcOccludedNp(RTCScene hs, struct RTCIntersectContext* ctx, const struct RTCRayNp* r, unsigned int N) {
   Scene* s = (Scene*)hs;
-  RTC_TRY checkQuery(s, ctx); VERIFY_HANDLE(r); traceSoA(s, ctx, viewOfNp(r, nullptr, N), nullptr, N, true, 0); RTC_CATCH(devOf(s))
+  RTC_TRY checkQuery(s, ctx); VERIFY_HANDLE(r); traceSoA(s, ctx, viewOfNp(r, nullptr, N), nullptr, N, true, 1); RTC_CATCH(devOf(s))
 }
 
 // ================================================================================================

@@ -30,6 +30,8 @@ struct RTCXBuildStats {
                                    the weighting of BVHNStatistics (a reference leaf block holds <= 4 triangles, a slot <= 3) */
   double sahLeafTris;           /* leaf term weighted by triangles instead of blocks: sum A(slot) * numTris / A(root);
                                    sahInner + sahLeafTris / 4 is the figure to hold against the reference's blocks of four */
+  unsigned int numTreelets;     /* binned-SAH treelets of the last full build (gpu_builder=sah), 0 for the other front ends */
+  unsigned int pad;
 };
 
 struct RTCXTraceCounters {

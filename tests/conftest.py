@@ -26,9 +26,9 @@ def product():
     return cases.rt.RTCore()
 
 
-@pytest.fixture(scope="session", params=["gpu_builder=lbvh", "gpu_builder=ploc"])
+@pytest.fixture(scope="session", params=["gpu_builder=lbvh", "gpu_builder=ploc", "gpu_builder=sah"])
 def gpu_device(product, request):
-    """Every GPU test runs against both binary-tree front ends of the builder (radix tree / PLOC)."""
+    """Every GPU test runs against all three binary-tree front ends of the builder (radix tree / PLOC / binned-SAH treelets)."""
     return product.new_device(request.param)
 
 

@@ -75,8 +75,10 @@ def test_nm_and_np_are_one_launch_per_call(product, gpu_device):
 
 @pytest.mark.gpu
 def test_packet_lanes_follow_packet_entry_rules(product, gpu_device, reflib):
-    """Occlusion rays with tnear < 0: the stream filter skips them (bvh_intersector_stream.cpp:303-305) while the packet
-    kernels clamp tnear to 0 and test the ray (bvh_intersector_hybrid.cpp:153,403).  Compared live with the reference."""
+    """Occlusion rays with tnear < 0: the stream filters (1M, NM with N = the SIMD width, Np: octant-sorting branches of
+    stream_filters.cpp -> occludedN) skip them (bvh_intersector_stream.cpp:303-305) while single rays and the packet kernels
+    clamp tnear to 0 and test the ray (bvh_intersector1.cpp:132, bvh_intersector_hybrid.cpp:153,403).  Compared live with
+    the reference (built for AVX2: packets of 8 are its native SoA width)."""
     g = cases.load_golden("sphere_small")
     rays = fx.to_ray(g["rays"][:64].copy())
     rays["tnear"] = -1.0
