@@ -127,7 +127,7 @@ struct RQBuildStats {
   double   sahInner;          // inner-node term of `sah` alone (sah - sahInner = leaf term, one block per leaf slot)
   double   sahLeafTris;       // leaf term weighted by triangles: sum A(leaf slot) * numTris / A(root)
   uint32_t numTreelets;       // binned-SAH treelets of the last full build (0 for the other front ends)
-  uint32_t pad;
+  float    msBroadcast;       // gpus=N: wall time of replicating the image to the peer GPUs after the last commit
 };
 
 // Per-call traversal counters (instrumented kernel variant only).

@@ -168,11 +168,19 @@ struct Device : RefCounted {
     return *pool;
   }
   int refitEnabled = 1;                   // refit=0: RTC_BUILD_QUALITY_REFIT geometries are rebuilt like any other
+  // Multi-GPU ("gpus=N"): this device object drives GPU `ordinal`; every further GPU is a peer device object of its
+  // own (own streams, staging rings, host pool).  A commit builds here and replicates the flat image to the peers over
+  // NVLink (cudaMemcpyPeerAsync); a host-resident stream is cut into one contiguous shard per GPU, traced concurrently, and
+  // every GPU lands its hits in the caller's buffer -- broadcast and gather are the only inter-GPU steps.
+  int numGpus = 1;
+  std::vector<Device*> peers;             // owned
+  unsigned shardMinRays = 1u << 20;       // shorter host streams stay on the primary GPU
 
   cudaStream_t stream() const { return userStream ? userStream : ownStream; }
   void bind() const { if (hasGpu) cudaSetDevice(ordinal); }
 
   ~Device() override {
+    for (Device* p : peers) p->release();
     delete pool;
     if (hasGpu) {
       cudaSetDevice(ordinal);
@@ -232,6 +240,8 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     if (k == "verbose") d->verbose = atoi(v.c_str());
     else if (k == "benchmark") d->benchmark = atoi(v.c_str());
     else if (k == "gpu") d->ordinal = atoi(v.c_str());
+    else if (k == "gpus") d->numGpus = std::max(1, atoi(v.c_str()));
+    else if (k == "shard_min_rays") d->shardMinRays = (unsigned)std::max(1ll, atoll(v.c_str()));
     else if (k == "async") d->async = atoi(v.c_str());
     else if (k == "chunk_rays") d->chunkRays = (size_t)std::max(1024ll, atoll(v.c_str()));
     else if (k == "cost_node") d->build.costNode = (float)atof(v.c_str());
@@ -321,9 +331,12 @@ struct Scene : RefCounted {
   std::vector<std::pair<Scene*, unsigned long long>> instancedEpochs;   // distinct instanced scenes (each retained) and the epoch their device pointers were taken at
   void clearInstanced() { for (auto& e : instancedEpochs) e.first->release(); instancedEpochs.clear(); }
   RQBuildStats stats{};
+  std::vector<Scene*> peerScenes;                        // gpus=N: one replica scene per peer device (same index as Device::peers), owned
+  bool replicated = false;                               // the replicas hold the image of the current commit
   RTCProgressMonitorFunction progress = nullptr; void* progressPtr = nullptr;
   explicit Scene(Device* d) : dev(d) { dev->retain(); memset(&stats, 0, sizeof(stats)); }
   ~Scene() override {
+    for (Scene* p : peerScenes) if (p) p->release();
     for (Geometry* g : geoms) if (g) g->release();
     if (image.base) { dev->bind(); rqFreeImage(&image); }
     if (dInstances) { dev->bind(); cudaFree(dInstances); }
@@ -357,6 +370,49 @@ struct TempDev {                                         // device copies of hos
     return (const uint8_t*)d;
   }
 };
+
+// gpus=N: copy the committed image of `sc` to every peer GPU (collective 1 of 2: the NVLink broadcast of SURVEY 8e, here a
+// fan-out of cudaMemcpyPeerAsync on the peers' own streams so the copies run concurrently through the switch).
+void replicateScene(Scene* sc) {
+  Device* dev = sc->dev;
+  sc->replicated = false;
+  sc->stats.msBroadcast = 0.f;
+  if (dev->peers.empty()) return;
+  if (sc->numInstances) return;                          // an instanced image refers to other scenes' device memory: queries stay on the primary GPU
+  const RQImageHeader& H = sc->image.header;
+  const size_t bytes = (size_t)H.totalBytes;
+  if (sc->peerScenes.size() != dev->peers.size()) {
+    for (Scene* p : sc->peerScenes) if (p) p->release();
+    sc->peerScenes.clear();
+    for (Device* pd : dev->peers) sc->peerScenes.push_back(new Scene(pd));
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<void*> dst(dev->peers.size(), nullptr);
+  try {
+    for (size_t g = 0; g < dev->peers.size(); g++) {
+      Device* pd = dev->peers[g];
+      pd->bind();
+      cudaCheck(rqAllocImage(&dst[g], bytes, (rqStream)pd->stream()), "replica alloc");
+      cudaCheck(cudaMemcpyPeerAsync(dst[g], pd->ordinal, sc->image.base, dev->ordinal, bytes, pd->stream()), "replica copy");
+    }
+    for (size_t g = 0; g < dev->peers.size(); g++) {
+      Device* pd = dev->peers[g];
+      pd->bind();
+      cudaCheck(cudaStreamSynchronize(pd->stream()), "replica copy");
+      Scene* ps = sc->peerScenes[g];
+      if (ps->image.base) rqFreeImage(&ps->image);
+      ps->image.base = dst[g]; dst[g] = nullptr; ps->image.header = H; ps->image.numLevels = 0;
+      ps->flags = sc->flags; ps->stats = sc->stats; ps->modified = false; ps->everCommitted = true; ps->epoch++;
+    }
+  } catch (...) {
+    for (size_t g = 0; g < dst.size(); g++) if (dst[g]) { dev->peers[g]->bind(); RQDeviceImage tmp; memset(&tmp, 0, sizeof(tmp)); tmp.base = dst[g]; rqFreeImage(&tmp); }
+    dev->bind();
+    throw;
+  }
+  dev->bind();
+  sc->stats.msBroadcast = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  sc->replicated = true;
+}
 
 void commitScene(Scene* sc) {
   Device* dev = sc->dev;
@@ -513,6 +569,7 @@ void commitScene(Scene* sc) {
       sc->traceDepth = img.header.depth + 3 + instDepth;       // the lane parks 3 entries of top-level state while inside an instance
     }
   }
+  replicateScene(sc);                                    // gpus=N: the peers' replicas follow every build and refit
   {
     std::lock_guard<std::mutex> gl(sc->geomMutex);
     for (size_t i = 0; i < newMod.size() && i < sc->seenMod.size(); i++) { sc->seenMod[i] = newMod[i]; sc->seenTopo[i] = newTopo[i]; }
@@ -795,6 +852,9 @@ void traceStreamCompact(Device* dev, RQTraceArgs a, char* rays, unsigned M, size
 // Trace M records of `stride` bytes at `rays`; occluded selects the any-hit kernel; recBytes is
 // 80 (RTCRayHit) or 48 (RTCRay).  Device-resident memory is traced in place; host memory is staged
 // through a ring of device buffers so copies of one chunk overlap the kernel of another.
+void traceStreamOn(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, size_t stride, bool occluded,
+                   size_t recBytes, int streamRule, RQTraceCounters* countersOut = nullptr);
+
 // streamRule: entry rules of occlusion rays -- 1 = stream filter (AoS / AoP streams with M > 1: rays with tnear < 0 are skipped,
 // bvh_intersector_stream.cpp:303-305), 0 = single ray / packet (tnear is clamped to 0 instead, bvh_intersector1.cpp:132,
 // bvh_intersector_hybrid.cpp:153,403), -1 = decide by M like rtcOccluded1M does.
@@ -806,8 +866,50 @@ void traceStream(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, si
   // the kernels read records through 4-byte (16-byte when possible) words: a misaligned address would fault and poison the context
   if (((uintptr_t)rays & 3u) || (stride & 3u)) fail(RTC_ERROR_INVALID_ARGUMENT, "ray not aligned to 4 bytes");
   if (M > 1 && stride < recBytes) fail(RTC_ERROR_INVALID_OPERATION, "byteStride too small");   // overlapping records: hit writes would race with ray reads
+  if (streamRule < 0) streamRule = M > 1 ? 1 : 0;
+  if (sc->replicated && !countersOut) {
+    cudaPointerAttributes pa;
+    const bool known = cudaPointerGetAttributes(&pa, rays) == cudaSuccess;
+    if (!known) cudaGetLastError();
+    if (known && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged)) {
+      // device-resident stream: traced where it lives (the replica of that GPU)
+      for (size_t g = 0; g < dev->peers.size(); g++)
+        if (pa.type == cudaMemoryTypeDevice && dev->peers[g]->ordinal == pa.device) {
+          traceStream(sc->peerScenes[g], ctx, rays, M, stride, occluded, recBytes, nullptr, streamRule);
+          dev->bind();
+          return;
+        }
+    } else if (M >= dev->shardMinRays) {
+      // host-resident stream: one contiguous shard per GPU (keeps whatever coherence the stream has), all shards in flight at
+      // once, each GPU stages its shard through its own ring and lands its hits in the caller's records (collective 2 of 2)
+      const unsigned G = 1u + (unsigned)dev->peers.size();
+      std::vector<std::thread> th;
+      std::vector<std::exception_ptr> errs(G);
+      auto shard = [&](unsigned g) {
+        const unsigned b = (unsigned)((unsigned long long)M * g / G), e = (unsigned)((unsigned long long)M * (g + 1) / G);
+        if (e <= b) return;
+        Scene* target = g == 0 ? sc : sc->peerScenes[g - 1];
+        try {
+          traceStreamOn(target, ctx, (char*)rays + (size_t)b * stride, e - b, stride, occluded, recBytes, streamRule);
+        } catch (...) { errs[g] = std::current_exception(); }
+      };
+      for (unsigned g = 1; g < G; g++) th.emplace_back(shard, g);
+      shard(0);
+      for (auto& t : th) t.join();
+      dev->bind();
+      for (unsigned g = 0; g < G; g++) if (errs[g]) std::rethrow_exception(errs[g]);
+      return;
+    }
+  }
+  traceStreamOn(sc, ctx, rays, M, stride, occluded, recBytes, streamRule, countersOut);
+}
+
+// one stream on the GPU of sc->dev
+void traceStreamOn(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, size_t stride, bool occluded,
+                   size_t recBytes, int streamRule, RQTraceCounters* countersOut) {
+  Device* dev = sc->dev;
   dev->bind();
-  RQTraceArgs a; fillArgs(sc, ctx, a, streamRule < 0 ? M > 1 : streamRule != 0);
+  RQTraceArgs a; fillArgs(sc, ctx, a, streamRule != 0);
   RQTraceCounters* dC = nullptr;
   if (countersOut) {
     std::lock_guard<std::mutex> l(dev->stageMutex);
@@ -1073,6 +1175,29 @@ RTC_API RTCDevice rtcNewDevice(const char* config) {
       cudaCheck(cudaMalloc((void**)&d->dWork, 32 * (Device::kRing + 1)), "work counters");
       if (d->verbose >= 1)
         printf("b200-rayquery %s on GPU %d: %s, %d SMs, %.1f GB\n", RTC_VERSION_STRING, d->ordinal, p.name, p.multiProcessorCount, p.totalGlobalMem / 1e9);
+      if (d->numGpus > 1) {
+        // gpus=N: GPUs ordinal .. ordinal+N-1; the host threads of the box are shared between them
+        if (d->ordinal + d->numGpus > n) { delete d; d = nullptr; fail(RTC_ERROR_INVALID_ARGUMENT, "gpus=N exceeds the number of CUDA devices"); }
+        const int hw = (int)std::thread::hardware_concurrency();
+        const int perGpu = std::max(2, std::min(8, hw / d->numGpus));
+        if (d->scatterThreads == 8) d->scatterThreads = perGpu;
+        for (int g = 1; g < d->numGpus; g++) {
+          Device* pd = new Device();
+          d->peers.push_back(pd);
+          bool dummy = false;
+          parseConfig(pd, config, &dummy);
+          pd->numGpus = 1; pd->ordinal = d->ordinal + g; pd->scatterThreads = d->scatterThreads; pd->hasGpu = true;
+          pd->bind();
+          cudaCheck(cudaStreamCreateWithFlags(&pd->ownStream, cudaStreamNonBlocking), "stream");
+          cudaCheck(cudaMalloc((void**)&pd->dWork, 32 * (Device::kRing + 1)), "work counters");
+          int can = 0;
+          if (cudaDeviceCanAccessPeer(&can, pd->ordinal, d->ordinal) == cudaSuccess && can) { if (cudaDeviceEnablePeerAccess(d->ordinal, 0) != cudaSuccess) cudaGetLastError(); }
+          d->bind();
+          can = 0;
+          if (cudaDeviceCanAccessPeer(&can, d->ordinal, pd->ordinal) == cudaSuccess && can) { if (cudaDeviceEnablePeerAccess(pd->ordinal, 0) != cudaSuccess) cudaGetLastError(); }
+        }
+        d->bind();
+      }
     }
     return (RTCDevice)d;
   RTC_CATCH(nullptr)
@@ -1550,6 +1675,7 @@ RTC_API void rtcxSynchronizeDevice(RTCDevice h) {
   RTC_TRY VERIFY_HANDLE(h); if (d->hasGpu) { d->bind(); cudaCheck(cudaStreamSynchronize(d->stream()), "synchronize"); } RTC_CATCH(d)
 }
 RTC_API int rtcxGetDeviceOrdinal(RTCDevice h) { Device* d = (Device*)h; return d && d->hasGpu ? d->ordinal : -1; }
+RTC_API int rtcxGetDeviceGpuCount(RTCDevice h) { Device* d = (Device*)h; return d && d->hasGpu ? 1 + (int)d->peers.size() : 0; }
 RTC_API int rtcxGetSceneBuildStats(RTCScene hs, struct RTCXBuildStats* o) {
   Scene* s = (Scene*)hs;
   RTC_TRY
@@ -1684,7 +1810,13 @@ RTC_API void rtcxOccluded1MCounted(RTCScene hs, struct RTCIntersectContext* ctx,
 RTC_API unsigned long long rtcxGetLaunchCount(void) { return rqLaunchCount(); }
 RTC_API void rtcxGetTransferBytes(RTCDevice h, unsigned long long* h2d, unsigned long long* d2h) {
   Device* d = (Device*)h;
-  RTC_TRY VERIFY_HANDLE(h); if (h2d) *h2d = d->h2dBytes.load(); if (d2h) *d2h = d->d2hBytes.load(); RTC_CATCH(d)
+  RTC_TRY
+    VERIFY_HANDLE(h);
+    unsigned long long a = d->h2dBytes.load(), b = d->d2hBytes.load();
+    for (Device* p : d->peers) { a += p->h2dBytes.load(); b += p->d2hBytes.load(); }
+    if (h2d) *h2d = a;
+    if (d2h) *d2h = b;
+  RTC_CATCH(d)
 }
 
 // ================================================================================================

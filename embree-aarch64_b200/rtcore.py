@@ -65,7 +65,7 @@ class BuildStats(C.Structure):
                 ("msTotal", C.c_float), ("msPrims", C.c_float), ("msSort", C.c_float),
                 ("msHierarchy", C.c_float), ("msRefit", C.c_float), ("msEmit", C.c_float),
                 ("bytes", C.c_ulonglong), ("builderIterations", C.c_uint), ("refitCount", C.c_uint),
-                ("sahInner", C.c_double), ("sahLeafTris", C.c_double), ("numTreelets", C.c_uint), ("pad", C.c_uint)]
+                ("sahInner", C.c_double), ("sahLeafTris", C.c_double), ("numTreelets", C.c_uint), ("msBroadcast", C.c_float)]
 
 
 class TraceCounters(C.Structure):
@@ -154,6 +154,7 @@ class RTCore:
             _sig(L, "rtcxSetDeviceStream", None, [vp, vp])
             _sig(L, "rtcxSynchronizeDevice", None, [vp])
             _sig(L, "rtcxGetDeviceOrdinal", C.c_int, [vp])
+            _sig(L, "rtcxGetDeviceGpuCount", C.c_int, [vp])
             _sig(L, "rtcxGetSceneBuildStats", C.c_int, [vp, C.POINTER(BuildStats)])
             _sig(L, "rtcxGetSceneImage", vp, [vp, C.POINTER(sz)])
             _sig(L, "rtcxSetSceneImage", None, [vp, vp, sz])

@@ -31,7 +31,7 @@ struct RTCXBuildStats {
   double sahLeafTris;           /* leaf term weighted by triangles instead of blocks: sum A(slot) * numTris / A(root);
                                    sahInner + sahLeafTris / 4 is the figure to hold against the reference's blocks of four */
   unsigned int numTreelets;     /* binned-SAH treelets of the last full build (gpu_builder=sah), 0 for the other front ends */
-  unsigned int pad;
+  float msBroadcast;            /* device option gpus=N: wall time of the NVLink replication of the image to the peer GPUs */
 };
 
 struct RTCXTraceCounters {
@@ -51,6 +51,9 @@ struct RTCXTraceCounters {
 RTC_API void rtcxSetDeviceStream(RTCDevice device, void* cudaStream);
 RTC_API void rtcxSynchronizeDevice(RTCDevice device);
 RTC_API int  rtcxGetDeviceOrdinal(RTCDevice device);
+/* GPUs this device object drives (device option "gpus=N": GPUs ordinal .. ordinal+N-1 of one box; a commit builds on the first
+ * and replicates the image over NVLink, host-resident streams are sharded contiguously across all of them). */
+RTC_API int  rtcxGetDeviceGpuCount(RTCDevice device);
 
 /* Statistics of the last commit of `scene`; returns 0 on success. */
 RTC_API int rtcxGetSceneBuildStats(RTCScene scene, struct RTCXBuildStats* stats_o);

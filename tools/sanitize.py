@@ -16,7 +16,7 @@ rt, fx = pkg.rtcore, pkg.fixtures
 import instancing  # noqa: E402
 
 lib = rt.RTCore()
-for cfg in ("gpu_builder=ploc", "gpu_builder=lbvh,chunk_rays=20000"):
+for cfg in ("gpu_builder=sah,treelet=256", "gpu_builder=sah", "gpu_builder=ploc", "gpu_builder=lbvh,chunk_rays=20000"):
     dev = lib.new_device(cfg)
     meshes = [fx.displaced_plane(40, extent=3.0), fx.triangle_sphere((0, 1, 0), 0.7, 16)]
     sc = lib.lib.rtcNewScene(dev)
