@@ -184,7 +184,7 @@ __device__ __forceinline__ uint64_t expand21(uint32_t v) {    // spread 21 bits 
 
 __global__ void __launch_bounds__(256)
 k_morton(const RQTri* __restrict__ trisIn, uint32_t N, const Bounds12* __restrict__ bounds,
-         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int cubic) {
+         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int cubic, uint64_t keyMask) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= N) return;
   const float4* src = (const float4*)(trisIn + g);
@@ -207,7 +207,7 @@ k_morton(const RQTri* __restrict__ trisIn, uint32_t N, const Bounds12* __restric
       x = fminf(fmaxf(x, 0.f), 1.f);
       q[k] = min(2097151u, (uint32_t)(x * 2097152.0f));
     }
-    key = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+    key = ((expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2])) & keyMask;
   }
   keys[g] = key;
   vals[g] = g;
@@ -592,6 +592,71 @@ k_ploc_compact(const uint32_t* __restrict__ cidIn, const uint32_t* __restrict__ 
   uint32_t off = blockOffset[blockIdx.x];
   for (int w = 0; w < warp; w++) off += warpSum[w];
   if (alive) cidOut[off + __popc(bal & ((1u << lane) - 1u))] = cidIn[i];
+}
+
+// The tail of the clustering -- and all of it when PLOC only has to join a few ten thousand treelet roots -- runs in ONE block:
+// below ~64 K clusters an iteration is a handful of microseconds of work, and three launches plus a host read-back every few
+// iterations cost more than the work itself (round 1: 163 launches to build a 3 K-triangle scene).  Same algorithm, same
+// tie rules, block barriers instead of kernel boundaries; the cluster array ping-pongs between cidA and cidB.
+constexpr int PLOC_TAIL_THREADS = 1024;
+constexpr uint32_t PLOC_TAIL_MAX = 1u << 16;
+__global__ void __launch_bounds__(PLOC_TAIL_THREADS)
+k_ploc_tail(B2 t, uint32_t* __restrict__ cidA, uint32_t* __restrict__ cidB, uint32_t* __restrict__ nn, const uint32_t* __restrict__ mPtr,
+            uint32_t* nextInner, uint32_t* iterations, int radius, float costNode, float costTri, int maxLeafTris) {
+  __shared__ uint32_t warpCnt[PLOC_TAIL_THREADS / 32];
+  __shared__ uint32_t s_run;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t m = *mPtr;
+  uint32_t* cin = cidA; uint32_t* cout = cidB;
+  uint32_t its = 0;
+  while (m > 1u) {
+    for (uint32_t i = tid; i < m; i += PLOC_TAIL_THREADS) {
+      const float4 lo = __ldcg(t.lo + cin[i]), hi = __ldcg(t.hi + cin[i]);
+      float best = FLT_MAX; int bj = -1;
+      const int j0 = max((int)i - radius, 0), j1 = min((int)i + radius, (int)m - 1);
+      for (int j = j0; j <= j1; j++) {
+        if (j == (int)i) continue;
+        const float4 l2 = __ldcg(t.lo + cin[j]), h2 = __ldcg(t.hi + cin[j]);
+        const float d = halfArea(fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z));
+        if (d < best) { best = d; bj = j; }
+      }
+      nn[i] = (uint32_t)bj;
+    }
+    __syncthreads();
+    if (tid == 0) s_run = 0u;
+    __syncthreads();
+    for (uint32_t base = 0; base < m; base += PLOC_TAIL_THREADS) {      // ordered compaction, one chunk of 1024 positions at a time
+      const uint32_t i = base + tid;
+      bool alive = false; uint32_t id = 0u;
+      if (i < m) {
+        const uint32_t j = nn[i];
+        const bool mutual = j < m && nn[j] == i;
+        alive = !(mutual && j < i);
+        id = cin[i];
+        if (mutual && i < j) {
+          id = atomicSub(nextInner, 1u);
+          const uint32_t L = cin[i], R = cin[j];
+          t.left[id] = L; t.right[id] = R; t.parent[L] = id; t.parent[R] = id;
+          combineNode(t, id, L, R, costNode, costTri, maxLeafTris);
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0) warpCnt[warp] = __popc(bal);
+      __syncthreads();
+      uint32_t off = s_run;
+      for (int w = 0; w < warp; w++) off += warpCnt[w];
+      if (alive) cout[off + __popc(bal & ((1u << lane) - 1u))] = id;
+      __syncthreads();
+      if (tid == 0) { uint32_t tot = 0; for (int w = 0; w < PLOC_TAIL_THREADS / 32; w++) tot += warpCnt[w]; s_run += tot; }
+      __syncthreads();
+    }
+    const uint32_t next = s_run;
+    __syncthreads();
+    if (next >= m) break;                                            // cannot happen (the globally closest pair is always mutual); never spin
+    m = next; its++;
+    uint32_t* tmp = cin; cin = cout; cout = tmp;
+  }
+  if (tid == 0) atomicAdd(iterations, its);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1164,16 +1229,29 @@ struct ScratchScope {
   }
 };
 static thread_local cudaStream_t t_scratchStream = nullptr;
+static thread_local rqAllocMonitorFn t_monFn = nullptr;
+static thread_local void* t_monUser = nullptr;
+inline bool monitorAlloc(size_t bytes) { return !t_monFn || t_monFn(t_monUser, (long long)bytes, false); }
+inline void monitorFree(size_t bytes) { if (t_monFn) t_monFn(t_monUser, -(long long)bytes, true); }
 template <typename T>
 struct DevBuf {
-  T* p = nullptr; cudaStream_t s = nullptr;
-  cudaError_t alloc(size_t n) { s = t_scratchStream; return cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(T), s); }
-  ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+  T* p = nullptr; cudaStream_t s = nullptr; size_t bytes = 0;
+  cudaError_t alloc(size_t n) {
+    s = t_scratchStream;
+    const size_t want = (n ? n : 1) * sizeof(T);
+    if (!monitorAlloc(want)) return cudaErrorMemoryAllocation;   // vetoed by the application's memory monitor
+    const cudaError_t e = cudaMallocAsync((void**)&p, want, s);
+    if (e == cudaSuccess) bytes = want; else { p = nullptr; monitorFree(want); }
+    return e;
+  }
+  ~DevBuf() { if (p) { cudaFreeAsync(p, s); monitorFree(bytes); } }
 };
 
 inline unsigned blocksFor(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
+
+void rqSetAllocMonitor(rqAllocMonitorFn fn, void* user) { t_monFn = fn; t_monUser = user; }
 
 // Images come from the stream-ordered pool as well (a re-commit then reuses the pages of the image it replaces instead of paying
 // cudaMalloc / cudaFree: 5 ms of a 10 ms commit of 1 M triangles, profiles/r01t_bench.json).  Freeing keeps cudaFree's guarantee --
@@ -1215,7 +1293,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   uint32_t n = 0, depth = 0, numNodes = 1, numTris = 0;
   std::vector<uint32_t> levelEnd(1, 1u);                        // level 0 = the root = node range [0,1)
   RQImageHeader H;
-  void* image = nullptr;
+  void* image = nullptr; size_t imageAccounted = 0;
   memset(&hc, 0, sizeof(hc));
   memset(&H, 0, sizeof(H));
 
@@ -1231,7 +1309,10 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     CK(cudaMemcpyAsync(dGeoms.p, hg.data(), sizeof(RQGeomDesc) * numGeoms, cudaMemcpyHostToDevice, stream));
     CK(trisIn.alloc(N)); CK(keys0.alloc(N)); CK(keys1.alloc(N)); CK(vals0.alloc(N)); CK(vals1.alloc(N));
     k_setup_prims<<<blocksFor(N, 256), 256, 0, stream>>>(dGeoms.p, numGeoms, N, trisIn.p, dBounds.p, dInvalid.p);
-    k_morton<<<blocksFor(N, 256), 256, 0, stream>>>(trisIn.p, N, dBounds.p, keys0.p, vals0.p, P.mortonCubic);
+    // The treelet builder only needs the Morton order down to cells of a few hundred triangles (everything below is rebuilt by SAH):
+    // it sorts on the upper 32 bits of the code (10-11 bits per axis), i.e. half the radix passes; ties keep input order.
+    k_morton<<<blocksFor(N, 256), 256, 0, stream>>>(trisIn.p, N, dBounds.p, keys0.p, vals0.p, P.mortonCubic,
+                                                    P.builder == 2 ? 0xFFFFFFFF00000000ull : ~0ull);
     rqCountLaunch(2);
     CK(cudaGetLastError());
   }
@@ -1241,7 +1322,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     const uint32_t numTiles = blocksFor(N, SORT_TILE);
     CK(hist.alloc((size_t)256 * numTiles)); CK(digitTotal.alloc(256));
     uint64_t *kin = keys0.p, *kout = keys1.p; uint32_t *vin = vals0.p, *vout = vals1.p;
-    for (int pass = 0; pass < 8; pass++) {
+    for (int pass = (P.builder == 2 ? 4 : 0); pass < 8; pass++) {
       const int shift = pass * 8;
       k_sort_hist<<<numTiles, SORT_THREADS, 0, stream>>>(kin, N, shift, numTiles, hist.p);
       k_sort_scan_rows<<<256, 256, 0, stream>>>(hist.p, numTiles, digitTotal.p);
@@ -1251,7 +1332,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       std::swap(kin, kout); std::swap(vin, vout);
     }
     CK(cudaGetLastError());
-    // 8 passes: result is back in keys0/vals0
+    // 8 (or 4) passes: result is back in keys0/vals0
   }
   CK(cudaEventRecord(ev[2], stream));
   CK(cudaMemcpyAsync(&hInvalid, dInvalid.p, 4, cudaMemcpyDeviceToHost, stream));
@@ -1323,9 +1404,9 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
         CK(cudaMemcpyAsync(plocCtr.p, initCtr, sizeof(initCtr), cudaMemcpyHostToDevice, stream));
         uint32_t m = m0; uint32_t *cin = cid0.p, *cout = cid1.p;
         uint32_t it = 0;
-        while (m > 1) {
+        while (m > PLOC_TAIL_MAX) {                                 // large cluster counts: one grid per step
           const unsigned nb = blocksFor(m, PLOC_THREADS);
-          const uint32_t window = m > (1u << 20) ? 2u : (m > (1u << 16) ? 4u : 8u);
+          const uint32_t window = m > (1u << 20) ? 2u : 4u;
           for (uint32_t w = 0; w < window; w++, it++) {
             uint32_t* mCur = plocCtr.p + 1 + (it & 1u);
             uint32_t* mNext = plocCtr.p + 1 + ((it + 1u) & 1u);
@@ -1342,6 +1423,11 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
           if (next >= m || next == 0) { err = (int)cudaErrorUnknown; goto fail; }   // every iteration merges at least the globally closest pair
           m = next;
           if (it > 4096) { err = (int)cudaErrorUnknown; goto fail; }
+        }
+        if (m > 1) {                                                // the tail (or everything, for treelet roots): one block, no host round trips
+          k_ploc_tail<<<1, PLOC_TAIL_THREADS, 0, stream>>>(t, cin, cout, nnBuf.p, plocCtr.p + 1 + (it & 1u), plocCtr.p, plocCtr.p + 3, radius,
+                                                           P.costNode, P.costTri, P.maxLeafTris);
+          rqCountLaunch(1);
         }
         CK(cudaMemcpyAsync(&plocIters, plocCtr.p + 3, 4, cudaMemcpyDeviceToHost, stream));
         CK(cudaGetLastError());
@@ -1395,6 +1481,8 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     H.totalBytes = (H.trisOffset + (uint64_t)numTris * sizeof(RQTri) + 127ull) & ~127ull;
     const double rootA = n ? (double)halfArea(H.hi[0] - H.lo[0], H.hi[1] - H.lo[1], H.hi[2] - H.lo[2]) : 0.0;
     H.sah = rootA > 0 ? (hc.sahInnerQ + hc.sahLeafQ) / rootA : 0.0;
+    if (!monitorAlloc(H.totalBytes)) { err = (int)cudaErrorMemoryAllocation; goto fail; }
+    imageAccounted = (size_t)H.totalBytes;
     CK(cudaMallocAsync(&image, H.totalBytes, stream));
     CK(cudaMemsetAsync(image, 0, H.totalBytes, stream));
     CK(cudaMemcpyAsync(image, &H, sizeof(H), cudaMemcpyHostToDevice, stream));
@@ -1419,7 +1507,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       cudaEventElapsedTime(&stats->msRefit, ev[3], ev[4]);
       cudaEventElapsedTime(&stats->msEmit, ev[4], ev[6]);
     }
-    out->base = image; out->header = H; image = nullptr;
+    out->base = image; out->header = H; image = nullptr; imageAccounted = 0;
     out->numLevels = 0;
     if (levelEnd.size() == depth && depth <= RQ_MAX_LEVELS && levelEnd.back() == numNodes) {
       out->numLevels = depth;
@@ -1432,6 +1520,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
 fail:
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   if (image) cudaFreeAsync(image, stream);
+  if (imageAccounted) monitorFree(imageAccounted);
   cudaGetLastError();
   return err ? err : (int)cudaErrorUnknown;
 }

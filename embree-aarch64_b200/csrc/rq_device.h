@@ -96,6 +96,13 @@ int rqScatterAoP(void* const* ptrs, uint32_t n, const void* aosRayHit, int occlu
 // receives the number of offending records (0 = usable).
 int rqValidateImage(const void* image, const RQImageHeader* header, rqStream stream, unsigned int* violations);
 
+// Memory monitor hook (reference: RTCMemoryMonitorFunction, kernels/common/device.cpp:318-327).  While a monitor is set for the
+// calling thread, every device allocation of rqBuildBVH / rqRefitBVH (scratch and the image) first asks fn(user, +bytes, false) --
+// false vetoes it and the build fails with cudaErrorMemoryAllocation -- and reports fn(user, -bytes, true) when the memory is
+// released.  The image of a successful build stays accounted: whoever frees it reports -header.totalBytes.
+typedef bool (*rqAllocMonitorFn)(void* user, long long bytes, bool post);
+void rqSetAllocMonitor(rqAllocMonitorFn fn, void* user);
+
 // Number of kernel launches issued by this library since load (bench.py's gpu_launches claim).
 unsigned long long rqLaunchCount(void);
 void rqCountLaunch(unsigned n);

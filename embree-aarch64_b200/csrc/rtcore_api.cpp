@@ -326,6 +326,7 @@ struct Scene : RefCounted {
   RTCSceneFlags flags = RTC_SCENE_FLAG_NONE; RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
   bool modified = true, everCommitted = false;
   RQDeviceImage image{nullptr, {}};
+  bool accounted = false;                                // the image was reported to the memory monitor (built here, not adopted / replicated)
   RQInstance* dInstances = nullptr; unsigned numInstances = 0; unsigned traceDepth = 0;   // instance table of a scene with instance geometries
   unsigned long long epoch = 0;                          // bumped by every commit / image adoption
   std::vector<std::pair<Scene*, unsigned long long>> instancedEpochs;   // distinct instanced scenes (each retained) and the epoch their device pointers were taken at
@@ -338,7 +339,12 @@ struct Scene : RefCounted {
   ~Scene() override {
     for (Scene* p : peerScenes) if (p) p->release();
     for (Geometry* g : geoms) if (g) g->release();
-    if (image.base) { dev->bind(); rqFreeImage(&image); }
+    if (image.base) {
+      dev->bind();
+      const size_t bytes = (size_t)image.header.totalBytes;
+      rqFreeImage(&image);
+      if (accounted && dev->memFn) dev->memFn(dev->memPtr, -(ssize_t)bytes, true);
+    }
     if (dInstances) { dev->bind(); cudaFree(dInstances); }
     clearInstanced();
     dev->release();
@@ -358,14 +364,35 @@ void* mappedHostPointer(const void* p) {
   return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
+// The application's memory monitor (rtcSetDeviceMemoryMonitorFunction) also sees the DEVICE memory of a commit: the uploaded
+// geometry buffers, the build scratch and the BVH image (reference: every allocation of a build goes through
+// Device::memoryMonitor, kernels/common/device.cpp:318-327; verify.cpp:4564-4634 vetoes a random one and checks the balance).
+bool deviceMonitor(void* user, long long bytes, bool post) {
+  Device* dev = (Device*)user;
+  return !dev->memFn || dev->memFn(dev->memPtr, (ssize_t)bytes, post);
+}
+struct MonitorScope {
+  explicit MonitorScope(Device* dev) { rqSetAllocMonitor(dev->memFn ? deviceMonitor : nullptr, dev); }
+  ~MonitorScope() { rqSetAllocMonitor(nullptr, nullptr); }
+};
+void freeImage(Device* dev, RQDeviceImage* img) {
+  if (!img->base) return;
+  const size_t bytes = (size_t)img->header.totalBytes;
+  rqFreeImage(img);
+  if (dev->memFn) dev->memFn(dev->memPtr, -(ssize_t)bytes, true);
+}
+
 struct TempDev {                                         // device copies of host geometry buffers, freed after the build
-  std::vector<void*> ptrs; cudaStream_t stream = nullptr;   // stream-ordered pool: no cudaMalloc/cudaFree stalls on re-commit
-  ~TempDev() { for (void* p : ptrs) cudaFreeAsync(p, stream); }
+  std::vector<void*> ptrs; std::vector<size_t> sizes; cudaStream_t stream = nullptr; Device* dev = nullptr;   // stream-ordered pool: no cudaMalloc/cudaFree stalls on re-commit
+  ~TempDev() { for (size_t i = 0; i < ptrs.size(); i++) { cudaFreeAsync(ptrs[i], stream); if (dev && dev->memFn) dev->memFn(dev->memPtr, -(ssize_t)sizes[i], true); } }
   const uint8_t* upload(const char* src, size_t bytes, cudaStream_t s) {
     void* d = nullptr;
     stream = s;
-    cudaCheck(cudaMallocAsync(&d, bytes ? bytes : 16, s), "geometry upload (alloc)");
-    ptrs.push_back(d);
+    const size_t want = bytes ? bytes : 16;
+    if (dev && dev->memFn && !dev->memFn(dev->memPtr, (ssize_t)want, false)) fail(RTC_ERROR_OUT_OF_MEMORY, "memory monitor forced termination");
+    const int e = cudaMallocAsync(&d, want, s);
+    if (e) { if (dev && dev->memFn) dev->memFn(dev->memPtr, -(ssize_t)want, true); cudaCheck(e, "geometry upload (alloc)"); }
+    ptrs.push_back(d); sizes.push_back(want);
     if (bytes) cudaCheck(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s), "geometry upload (copy)");
     return (const uint8_t*)d;
   }
@@ -447,7 +474,8 @@ void commitScene(Scene* sc) {
   std::vector<RQGeomDesc> descs;
   std::vector<RQInstance> insts;
   unsigned instDepth = 0;
-  TempDev tmp;
+  TempDev tmp; tmp.dev = dev;
+  MonitorScope monitor(dev);
   // the counters this commit is about to absorb: written back to the scene only after the build / refit has succeeded, so a
   // failed commit (out of memory, cancelled, invalid instance) is retried by the next rtcCommitScene instead of being skipped
   std::vector<unsigned> newMod, newTopo;
@@ -546,8 +574,8 @@ void commitScene(Scene* sc) {
     if (sc->quality == RTC_BUILD_QUALITY_LOW) bp.builder = 0;
     else if (sc->quality == RTC_BUILD_QUALITY_HIGH) { bp.plocRadius = std::max(bp.plocRadius, 16); bp.treeletSize = 512; if (bp.builder == 0) bp.builder = 2; }
     cudaCheck(rqBuildBVH(descs.data(), (int)descs.size(), (uint32_t)sc->flags, &bp, (rqStream)s, &img, &st), "BVH build");
-    if (sc->image.base) rqFreeImage(&sc->image);
-    sc->image = img; sc->stats = st;
+    if (sc->image.base) { if (sc->accounted) freeImage(dev, &sc->image); else rqFreeImage(&sc->image); }
+    sc->image = img; sc->stats = st; sc->accounted = true;
     // instance table (traversal reads it through TraceParams::instances)
     if (sc->dInstances) { cudaFree(sc->dInstances); sc->dInstances = nullptr; }
     sc->numInstances = (unsigned)insts.size();
@@ -1738,7 +1766,8 @@ void adoptImage(Scene* s, const void* src, size_t bytes) {
     cudaCheck(e, "image copy");
     fail(RTC_ERROR_INVALID_ARGUMENT, "corrupt BVH image (references out of range)");
   }
-  if (s->image.base) rqFreeImage(&s->image);
+  if (s->image.base) { if (s->accounted) freeImage(dev, &s->image); else rqFreeImage(&s->image); }
+  s->accounted = false;
   if (s->dInstances) { cudaFree(s->dInstances); s->dInstances = nullptr; }
   s->numInstances = 0; s->clearInstanced(); s->epoch++;
   s->image.base = p; s->image.header = H; s->image.numLevels = 0;   // adopted image: level ranges unknown, never refitted

@@ -15,6 +15,7 @@ ap.add_argument("--cfg", default="")
 ap.add_argument("--counters", action="store_true")
 ap.add_argument("--sort", default="none", help="host-side reordering experiment: none|octant|chunkdir:<chunk>:<bins>|global:<obits>:<bins>")
 ap.add_argument("--lib", default=None, help="path of an experiment build (csrc/Makefile variant)")
+ap.add_argument("--meta", default=None, help="write {kernel_source_hash, git, rays_per_launch} here (read by tools/summarize_profiles.py)")
 args = ap.parse_args()
 lib = rt.RTCore(args.lib) if args.lib else rt.RTCore()
 dev = lib.new_device("async=1," + args.cfg)
@@ -68,6 +69,15 @@ def reorder(r, mode):
 
 diffuse, shadow = reorder(diffuse, args.sort), reorder(shadow, args.sort)
 nd, ns = len(diffuse), len(shadow)
+if args.meta:
+    import json, subprocess
+    sys.path.insert(0, ".")
+    import bench
+    try:
+        git = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() or None
+    except Exception:
+        git = None
+    json.dump({"kernel_source_hash": bench.kernel_source_hash(), "git": git, "rays_per_launch": nd, "workload": args.workload}, open(args.meta, "w"))
 p_d = torch.from_numpy(diffuse.view(np.uint8).reshape(nd, 80)).cuda()
 p_s = torch.from_numpy(shadow.view(np.uint8).reshape(ns, 48)).cuda()
 w_d, w_s = p_d.clone(), p_s.clone()

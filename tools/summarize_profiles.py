@@ -7,7 +7,9 @@ Usage: python tools/summarize_profiles.py <tag>            (runs here, no GPU ne
 import collections, csv, json, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 tag = sys.argv[1]
+workloads = sys.argv[2:] or ["c3", "c2"]
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
 
 
@@ -56,7 +58,7 @@ def to_bytes(v, unit):
     return float(v.replace(",", "")) * m.get(unit, 1)
 
 
-def ncu(suffix="trace"):
+def ncu(suffix="trace", what="configs[1] streams"):
     rep = os.path.join(G, f"{tag}_{suffix}.ncu-rep")
     if not os.path.exists(rep):
         return
@@ -65,7 +67,7 @@ def ncu(suffix="trace"):
     hdr, units = rows[0], rows[1]
     traffic = {}
     with open(os.path.join(P, f"{tag}_ncu_{suffix}.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on, one launch each (tools/profile_trace.py, configs[1] streams); source: gpurun_out/{tag}_{suffix}.ncu-rep\n")
+        f.write(f"# ncu --set full --clock-control none --import-source on, one launch each (tools/profile_trace.py, {what}); source: gpurun_out/{tag}_{suffix}.ncu-rep\n")
         for r in rows[2:]:
             name = short(r[hdr.index("Kernel Name")]) + r[hdr.index("Kernel Name")][r[hdr.index("Kernel Name")].find("<", 12):][:40]
             f.write(f"\n== {r[hdr.index('Kernel Name')][:110]}\n")
@@ -77,15 +79,40 @@ def ncu(suffix="trace"):
             wr = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
             kind = "occluded" if re.search(r"k_trace<\(?(bool\))?1|k_trace<true", r[hdr.index("Kernel Name")]) else "closest"
             traffic[f"dram_bytes_per_launch_{kind}"] = rd + wr
+            if kind == "closest":
+                for key, out in (("lts__t_sector_hit_rate.pct", "lts_hit_rate_pct"), ("l1tex__t_sector_hit_rate.pct", "l1_hit_rate_pct"),
+                                 ("smsp__thread_inst_executed_per_inst_executed.ratio", "lanes_per_inst"), ("gpu__time_duration.sum", "duration"),
+                                 ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_throughput_pct"),
+                                 ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_throughput_pct")):
+                    if key in hdr:
+                        traffic[out] = r[hdr.index(key)] + ("" if out != "duration" else " " + units[hdr.index(key)])
     print(open(os.path.join(P, f"{tag}_ncu_{suffix}.txt")).read())
     return traffic
 
 
 launches()
-t = ncu("trace")
-if t:
-    t["source"] = f"profiles/{tag}_ncu_trace.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch over the 16.7 M-ray configs[1] stream)"
-    json.dump(t, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
+import bench  # noqa: E402  (kernel_source_hash)
+path = os.path.join(P, "ncu_traffic.json")
+try:
+    allt = json.load(open(path))
+    if "dram_bytes_per_launch_closest" in allt:          # round-1 layout
+        allt = {}
+except Exception:
+    allt = {}
+for w in workloads:
+    names = {"c3": "configs[2]-[3] scene (10 M triangles), 16.7 M diffuse + shadow rays", "c2": "configs[1] scene (1.0 M triangles), 16.7 M diffuse + shadow rays"}
+    t = ncu(f"trace_{w}", names.get(w, w))
+    if t:
+        meta = {}
+        try:
+            meta = json.load(open(os.path.join(G, f"{tag}_trace_{w}.meta.json")))
+        except Exception:
+            pass
+        t.update({"capture": f"profiles/{tag}_ncu_trace_{w}.txt", "kernel_source_hash": meta.get("kernel_source_hash", bench.kernel_source_hash()),
+                  "git": meta.get("git"), "rays_per_launch": meta.get("rays_per_launch"),
+                  "source": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum of one closest-hit / one occlusion launch (tools/profile_trace.py)"})
+        allt[w] = t
+json.dump(allt, open(path, "w"), indent=1)
 for f in ("bench.json", "bench_reference.json", "pytest_gpu.log", "c3.log"):
     src = os.path.join(G, f"{tag}_{f}")
     if os.path.exists(src):
