@@ -70,7 +70,7 @@ struct Bounds12 {                                             // 12 ordered-uint
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_setup_prims(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t N,
-              RQTri* __restrict__ trisIn, Bounds12* bounds, uint32_t* invalidCount) {
+              RQTri* __restrict__ trisIn, Bounds12* bounds, uint32_t* invalidCount, uint32_t* __restrict__ idxOut /* compact layout: 3 pool indices per triangle, else NULL */) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -133,6 +133,10 @@ k_setup_prims(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t N,
         }
       }
     }
+    if (idxOut) {
+      const bool in = G.type != 1u && i0 < G.numVerts && i1 < G.numVerts && i2 < G.numVerts;
+      idxOut[3 * (size_t)g + 0] = in ? G.vertBase + i0 : 0u; idxOut[3 * (size_t)g + 1] = in ? G.vertBase + i1 : 0u; idxOut[3 * (size_t)g + 2] = in ? G.vertBase + i2 : 0u;
+    }
     // three 16-byte stores
     float4* dst = (float4*)(trisIn + g);
     dst[0] = make_float4(t.v0[0], t.v0[1], t.v0[2], t.v1[0]);
@@ -167,6 +171,23 @@ k_setup_prims(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t N,
     for (int w = 0; w < 8; w++) tot += redInvalid[w];
     if (tot) atomicAdd(invalidCount, tot);
   }
+}
+
+// vertex pool of a compact image: every mesh's vertices (arbitrary stride) as one float4 array, meshes in descriptor order
+__global__ void __launch_bounds__(256)
+k_copy_verts(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t totalVerts, float4* __restrict__ pool) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= totalVerts) return;
+  int a = 0, b = numGeoms - 1;                                // last mesh with vertBase <= v (instances hold no vertices: numVerts = 0)
+  while (a < b) { int m = (a + b + 1) >> 1; if (geoms[m].vertBase <= v) a = m; else b = m - 1; }
+  const RQGeomDesc& G = geoms[a];
+  const uint32_t local = v - G.vertBase;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (G.vertices != nullptr && local < G.numVerts) {
+    const float* p = (const float*)(G.vertices + (size_t)local * G.vertexStride);
+    o = make_float4(p[0], p[1], p[2], 0.f);
+  }
+  pool[v] = o;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -599,7 +620,7 @@ k_ploc_compact(const uint32_t* __restrict__ cidIn, const uint32_t* __restrict__ 
 // iterations cost more than the work itself (round 1: 163 launches to build a 3 K-triangle scene).  Same algorithm, same
 // tie rules, block barriers instead of kernel boundaries; the cluster array ping-pongs between cidA and cidB.
 constexpr int PLOC_TAIL_THREADS = 1024;
-constexpr uint32_t PLOC_TAIL_MAX = 1u << 16;
+constexpr uint32_t PLOC_TAIL_MAX = 1u << 12;                    // one SM against 148: above ~4 K clusters the grid version wins (35 K treelet roots: 2.0 ms single block, 0.45 ms grids)
 __global__ void __launch_bounds__(PLOC_TAIL_THREADS)
 k_ploc_tail(B2 t, uint32_t* __restrict__ cidA, uint32_t* __restrict__ cidB, uint32_t* __restrict__ nn, const uint32_t* __restrict__ mPtr,
             uint32_t* nextInner, uint32_t* iterations, int radius, float costNode, float costTri, int maxLeafTris) {
@@ -672,9 +693,12 @@ k_ploc_tail(B2 t, uint32_t* __restrict__ cidA, uint32_t* __restrict__ cidB, uint
 //         order-preserving uint keys), prefix / suffix box scans over the bins with width-16 shuffles (lanes 0..15 scan
 //         left to right, lanes 16..31 the mirrored bins, so one scan yields both sides), SAH = A_L n_L + A_R n_R for all
 //         45 candidate planes at once, warp arg-min, stable partition of the treelet's index permutation;
-//       * subtrees of at most TL_SMALL triangles: one THREAD each, exact sweep SAH -- the indices are insertion-sorted along
-//         each axis and every one of the m-1 split positions is evaluated (suffix areas in shared scratch), as a full-sweep
-//         builder does; 32 such subtrees are built at once by the lanes of the warp.
+//       * subtrees of at most TL_SMALL triangles: one THREAD each.  The stable partitions above keep every slice in Morton
+//         order, so the slice is split where the highest differing bit of its first and last code flips (the radix-tree rule
+//         on the sub-sequence) -- a few dozen instructions per node.  (Round-2 history: an exact sweep SAH per thread here --
+//         insertion sort along each axis, all m-1 positions -- was 38 % of the kernel's 3.5 G warp instructions at 7 active
+//         lanes, profiles/r02d_ncu_treelet.txt, for 1 % of traversal speed; the last levels end up inside one 8-wide node
+//         whose leaf slots the collapse programme chooses anyway.)
 //     Above the treelets the existing PLOC stage clusters the treelet roots (a few ten thousand boxes) and the SAH dynamic
 //     programme then cuts the binary tree into 8-wide nodes as before.
 //     Node ids: the T-1 nodes above the treelets take ids [0, T-1) (PLOC hands them out downwards, the root ends up as 0);
@@ -682,7 +706,7 @@ k_ploc_tail(B2 t, uint32_t* __restrict__ cidA, uint32_t* __restrict__ cidB, uint
 //     subtree over a range of m triangles rooted at local index j uses [j, j+m-1): left child j+1, right child j+m_left.
 // ----------------------------------------------------------------------------------------------
 constexpr int TL_BINS = 16;
-constexpr int TL_SMALL = 16;
+constexpr int TL_SMALL = 32;
 constexpr uint32_t TL_ORD_PINF = 0xFF800000u;                 // f2ord(+inf)
 constexpr uint32_t TL_ORD_NINF = 0x007FFFFFu;                 // f2ord(-inf)
 
@@ -764,85 +788,55 @@ k_treelet_roots(int n, const uint32_t* __restrict__ treeletStart, const uint32_t
 template <int K>
 struct TreeletSmem {                                           // one per warp
   float    box[6][K];                                          // lo.xyz, hi.xyz of the treelet's triangles (SoA: lane-strided access is conflict free)
+  uint32_t key[K];                                             // upper 32 bits of the Morton code (what the triangles were sorted by)
   uint16_t perm[K], perm2[K];                                  // the treelet's triangles, partitioned in place node by node
   uint32_t bins[3][TL_BINS][7];                                // per axis and bin: ordered-uint lo.xyz, hi.xyz, count
   uint32_t stack[16][2];                                       // pending large nodes: begin | end << 16, local node index
   uint32_t small[K / 2][2];                                    // subtrees left to the thread phase, same encoding
-  float    keys[TL_SMALL][32];                                 // thread phase: sort keys of the lane's current node
-  float    suffix[TL_SMALL][32];                               // thread phase: right-side areas of the lane's current node
 };
 
 __device__ __forceinline__ float boxArea6(const float lo[3], const float hi[3]) {
   return halfArea(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
 }
 
-// one lane builds the subtree over perm[b0, e0) (2 <= e0 - b0 <= TL_SMALL) rooted at local node index j0
+// one lane builds the subtree over perm[b0, e0) (2 <= e0 - b0 <= TL_SMALL) rooted at local node index j0: radix-tree splits of
+// the Morton-ordered slice (Karras 2012 on the sub-sequence; equal codes are halved by position)
 template <int K>
-__device__ void treeletSmallSubtree(TreeletSmem<K>& S, const B2& t, uint32_t b0, uint32_t e0, uint32_t j0, uint32_t base, uint32_t leaf0, int lane) {
-  uint32_t st[TL_SMALL]; int sp = 0;
+__device__ void treeletSmallSubtree(TreeletSmem<K>& S, const B2& t, uint32_t b0, uint32_t e0, uint32_t j0, uint32_t base, uint32_t leaf0) {
+  uint32_t st[8]; int sp = 0;                                   // the smaller child is finished first: <= log2(TL_SMALL) + 1 pending ranges
   st[sp++] = b0 | (e0 << 10) | (j0 << 20);
   while (sp > 0) {
     const uint32_t w = st[--sp];
     const uint32_t b = w & 1023u, e = (w >> 10) & 1023u, j = w >> 20;
-    const int m = (int)(e - b);
-    int split = 1;
-    if (m > 2) {
-      float best = INFINITY; int bestAxis = -1;
-      for (int a = 0; a < 3; a++) {
-        // insertion sort of the index slice along axis a (key = 2 x centroid; ties keep the lower index first)
-        for (int i = 0; i < m; i++) { const uint32_t p = S.perm[b + i]; S.keys[i][lane] = S.box[a][p] + S.box[3 + a][p]; }
-        for (int i = 1; i < m; i++) {
-          const float k = S.keys[i][lane]; const uint16_t p = S.perm[b + i];
-          int q = i - 1;
-          while (q >= 0 && (S.keys[q][lane] > k || (S.keys[q][lane] == k && S.perm[b + q] > p))) {
-            S.keys[q + 1][lane] = S.keys[q][lane]; S.perm[b + q + 1] = S.perm[b + q]; q--;
-          }
-          S.keys[q + 1][lane] = k; S.perm[b + q + 1] = p;
-        }
-        // right to left: area of the box of prims [i, m)
-        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (int i = m - 1; i >= 1; i--) {
-          const uint32_t p = S.perm[b + i];
-          for (int c = 0; c < 3; c++) { lo[c] = fminf(lo[c], S.box[c][p]); hi[c] = fmaxf(hi[c], S.box[3 + c][p]); }
-          S.suffix[i][lane] = boxArea6(lo, hi);
-        }
-        // left to right: SAH of every split position
-        for (int c = 0; c < 3; c++) { lo[c] = INFINITY; hi[c] = -INFINITY; }
-        for (int i = 1; i < m; i++) {
-          const uint32_t p = S.perm[b + i - 1];
-          for (int c = 0; c < 3; c++) { lo[c] = fminf(lo[c], S.box[c][p]); hi[c] = fmaxf(hi[c], S.box[3 + c][p]); }
-          const float cost = boxArea6(lo, hi) * (float)i + S.suffix[i][lane] * (float)(m - i);
-          if (cost < best) { best = cost; bestAxis = a; split = i; }
-        }
-      }
-      if (bestAxis < 0) split = m >> 1;                         // non-finite areas: object median in the current order
-      else if (bestAxis != 2) {                                 // the slice is sorted along z now: restore the winning order
-        const int a = bestAxis;
-        for (int i = 0; i < m; i++) { const uint32_t p = S.perm[b + i]; S.keys[i][lane] = S.box[a][p] + S.box[3 + a][p]; }
-        for (int i = 1; i < m; i++) {
-          const float k = S.keys[i][lane]; const uint16_t p = S.perm[b + i];
-          int q = i - 1;
-          while (q >= 0 && (S.keys[q][lane] > k || (S.keys[q][lane] == k && S.perm[b + q] > p))) {
-            S.keys[q + 1][lane] = S.keys[q][lane]; S.perm[b + q + 1] = S.perm[b + q]; q--;
-          }
-          S.keys[q + 1][lane] = k; S.perm[b + q + 1] = p;
-        }
-      }
+    const uint32_t m = e - b;
+    uint32_t mL = m >> 1;
+    const uint32_t kf = S.key[S.perm[b]], kl = S.key[S.perm[e - 1u]];
+    if (m > 2u && kf != kl) {
+      const int prefix = __clz((int)(kf ^ kl));                 // the slice is sorted: find the first code that differs from kf in the top differing bit
+      uint32_t lo = 0u, step = m;                               // largest lo with clz(kf ^ key[b + lo]) > prefix
+      do {
+        step = (step + 1u) >> 1;
+        const uint32_t q = lo + step;
+        if (q < m && __clz((int)(kf ^ S.key[S.perm[b + q]])) > prefix) lo = q;
+      } while (step > 1u);
+      mL = lo + 1u;
     }
-    const uint32_t mL = (uint32_t)split, mR = (uint32_t)m - mL;
+    const uint32_t mR = m - mL;
     const uint32_t jL = j + 1u, jR = j + mL;
     const uint32_t g = base + j;
     const uint32_t refL = mL == 1u ? leaf0 + S.perm[b] : base + jL;
     const uint32_t refR = mR == 1u ? leaf0 + S.perm[b + mL] : base + jR;
     t.left[g] = refL; t.right[g] = refR; t.parent[refL] = g; t.parent[refR] = g;
-    if (mR >= 2u) st[sp++] = (b + mL) | (e << 10) | (jR << 20);
-    if (mL >= 2u) st[sp++] = b | ((b + mL) << 10) | (jL << 20);
+    const bool leftBig = mL >= mR;
+    if (leftBig) { if (mL >= 2u) st[sp++] = b | ((b + mL) << 10) | (jL << 20); if (mR >= 2u) st[sp++] = (b + mL) | (e << 10) | (jR << 20); }
+    else { if (mR >= 2u) st[sp++] = (b + mL) | (e << 10) | (jR << 20); if (mL >= 2u) st[sp++] = b | ((b + mL) << 10) | (jL << 20); }
   }
 }
 
 template <int K>
 __global__ void __launch_bounds__(128)
-k_treelet_build(B2 t, int n, const uint32_t* __restrict__ treeletStart, const uint32_t* __restrict__ sizeAt, uint32_t T) {
+k_treelet_build(B2 t, int n, const uint32_t* __restrict__ treeletStart, const uint32_t* __restrict__ sizeAt, uint32_t T,
+                const uint64_t* __restrict__ keys) {
   extern __shared__ __align__(16) unsigned char tlSmemRaw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
@@ -857,6 +851,7 @@ k_treelet_build(B2 t, int n, const uint32_t* __restrict__ treeletStart, const ui
     const float4 lo = t.lo[leaf0 + i], hi = t.hi[leaf0 + i];
     S.box[0][i] = lo.x; S.box[1][i] = lo.y; S.box[2][i] = lo.z; S.box[3][i] = hi.x; S.box[4][i] = hi.y; S.box[5][i] = hi.z;
     S.perm[i] = (uint16_t)i;
+    S.key[i] = (uint32_t)(keys[a0 + i] >> 32);
   }
   int sp = 0, nsmall = 0;                                       // warp-uniform
   if (m0 > (uint32_t)TL_SMALL) { if (lane == 0) { S.stack[0][0] = m0 << 16; S.stack[0][1] = 0u; } sp = 1; }
@@ -886,35 +881,32 @@ k_treelet_build(B2 t, int n, const uint32_t* __restrict__ treeletStart, const ui
       (&S.bins[0][0][0])[w] = f < 3 ? TL_ORD_PINF : (f < 6 ? TL_ORD_NINF : 0u);
     }
     __syncwarp();
-    // The triangles of a node are still roughly in Morton order, so most lanes of an iteration fall into the same two or three
-    // bins: plain shared-memory atomics then serialise 16-32 ways on every one of the 21 updates (measured: 1.7 ms per tree
-    // level for 10 M triangles, profiles/r02b_ab_c3.jsonl).  Lanes with the same bin are grouped with match.any, reduced with
-    // redux.sync, and only the group leader touches the bin -- one lane per bin, no conflicts, no atomics needed.
-    for (uint32_t i0 = b; i0 < e; i0 += 32u) {
-      const uint32_t i = i0 + lane;
-      const bool ok = i < e;
-      const unsigned vm = __ballot_sync(FULL, ok);
-      if (ok) {
-        const uint32_t p = S.perm[i];
-        const float lx = S.box[0][p], ly = S.box[1][p], lz = S.box[2][p], hx = S.box[3][p], hy = S.box[4][p], hz = S.box[5][p];
-        const uint32_t olx = f2ord(lx), oly = f2ord(ly), olz = f2ord(lz), ohx = f2ord(hx), ohy = f2ord(hy), ohz = f2ord(hz);
-        const float c[3] = {lx + hx, ly + hy, lz + hz};
-        #pragma unroll
-        for (int a = 0; a < 3; a++) {
-          const int bin = min(TL_BINS - 1, (int)((c[a] - cmin[a]) * scale[a]));
-          const unsigned peers = __match_any_sync(vm, bin);
-          const uint32_t r0 = __reduce_min_sync(peers, olx), r1 = __reduce_min_sync(peers, oly), r2 = __reduce_min_sync(peers, olz);
-          const uint32_t r3 = __reduce_max_sync(peers, ohx), r4 = __reduce_max_sync(peers, ohy), r5 = __reduce_max_sync(peers, ohz);
-          if (lane == __ffs(peers) - 1) {
+    // The triangles of a node are still in Morton order, so 32 consecutive ones fall into the same two or three bins and
+    // their shared-memory atomics serialise 16-32 ways (round-2 history: 1.7 ms per tree level for 10 M triangles; grouping
+    // equal bins with match.any + redux.sync was slower still -- the hardware runs one redux per group, profiles/r02d_ncu_treelet.txt).
+    // Instead every lane walks its OWN contiguous share of the node, so that at any moment the 32 lanes touch triangles
+    // from all over the node: the bins they hit are as spread out as the node's triangles are.
+    {
+      const uint32_t per = (m + 31u) >> 5;
+      for (uint32_t it = 0; it < per; it++) {
+        const uint32_t o = (uint32_t)lane * per + it;
+        if (o < m) {
+          const uint32_t p = S.perm[b + o];
+          const float lx = S.box[0][p], ly = S.box[1][p], lz = S.box[2][p], hx = S.box[3][p], hy = S.box[4][p], hz = S.box[5][p];
+          const uint32_t olx = f2ord(lx), oly = f2ord(ly), olz = f2ord(lz), ohx = f2ord(hx), ohy = f2ord(hy), ohz = f2ord(hz);
+          const float c[3] = {lx + hx, ly + hy, lz + hz};
+          #pragma unroll
+          for (int a = 0; a < 3; a++) {
+            const int bin = min(TL_BINS - 1, (int)((c[a] - cmin[a]) * scale[a]));
             uint32_t* B = S.bins[a][bin];
-            B[0] = min(B[0], r0); B[1] = min(B[1], r1); B[2] = min(B[2], r2);
-            B[3] = max(B[3], r3); B[4] = max(B[4], r4); B[5] = max(B[5], r5);
-            B[6] += (uint32_t)__popc(peers);
+            atomicMin(&B[0], olx); atomicMin(&B[1], oly); atomicMin(&B[2], olz);
+            atomicMax(&B[3], ohx); atomicMax(&B[4], ohy); atomicMax(&B[5], ohz);
+            atomicAdd(&B[6], 1u);
           }
         }
       }
-      __syncwarp();
     }
+    __syncwarp();
     // ---- best (heuristic_binning.h:336-392): lanes 0..15 accumulate bins 0..idx, lanes 16..31 bins 15..15-idx ----
     const int half = lane >> 4, idx = lane & 15;
     const int myBin = half ? (TL_BINS - 1 - idx) : idx;
@@ -1009,7 +1001,7 @@ k_treelet_build(B2 t, int n, const uint32_t* __restrict__ treeletStart, const ui
     const int s = s0 + lane;
     if (s < nsmall) {
       const uint32_t be = S.small[s][0];
-      treeletSmallSubtree<K>(S, t, be & 0xFFFFu, be >> 16, S.small[s][1], base, leaf0, lane);
+      treeletSmallSubtree<K>(S, t, be & 0xFFFFu, be >> 16, S.small[s][1], base, leaf0);
     }
   }
 }
@@ -1048,7 +1040,8 @@ __device__ __forceinline__ void
 emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2* __restrict__ nextQueue,
          EmitCounters* ctr, RQNode* __restrict__ nodes, RQTri* __restrict__ trisOut,
          const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals, uint32_t level,
-         const uint32_t* __restrict__ parentOf, uint32_t* __restrict__ nextParentOf, double sahOut[5]) {
+         const uint32_t* __restrict__ parentOf, uint32_t* __restrict__ nextParentOf, double sahOut[5],
+         const uint32_t* __restrict__ idxIn, RQTriC* __restrict__ trisC, uint32_t* __restrict__ metaOut) {
   const uint32_t b = queue[q].x, w = queue[q].y;
   const uint32_t firstLeaf = (uint32_t)(n - 1);
 
@@ -1160,10 +1153,18 @@ emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2*
       while (wsp > 0 && j < nt) {
         const uint32_t x = walk[--wsp];
         if (x >= firstLeaf) {
-          const float4* src = (const float4*)(trisIn + vals[x - firstLeaf]);
-          float4* dst = (float4*)(trisOut + triBase + triOff + j);
-          if ((triBase + triOff + j) & 1u) { dst[0] = src[2]; dst[1] = src[0]; dst[2] = src[1]; }   // odd records: last 16 bytes first (rq_types.h)
-          else { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
+          const uint32_t tin = vals[x - firstLeaf];
+          const float4* src = (const float4*)(trisIn + tin);
+          if (trisC) {                                          // compact layout: indices + primID, geomID / quad flag on the side
+            const float4 c = src[2];
+            RQTriC r; r.v0 = idxIn[3 * (size_t)tin]; r.v1 = idxIn[3 * (size_t)tin + 1]; r.v2 = idxIn[3 * (size_t)tin + 2]; r.primID = __float_as_uint(c.y);
+            trisC[triBase + triOff + j] = r;
+            metaOut[triBase + triOff + j] = (__float_as_uint(c.z) & ~RQ_META_FLIPUV) | ((__float_as_uint(c.w) & RQ_PAD_FLIPUV) ? RQ_META_FLIPUV : 0u);
+          } else {
+            float4* dst = (float4*)(trisOut + triBase + triOff + j);
+            if ((triBase + triOff + j) & 1u) { dst[0] = src[2]; dst[1] = src[0]; dst[2] = src[1]; }   // odd records: last 16 bytes first (rq_types.h)
+            else { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
+          }
           j++;
         } else if (wsp < 3) { walk[wsp++] = t.right[x]; walk[wsp++] = t.left[x]; }
       }
@@ -1187,11 +1188,12 @@ __global__ void __launch_bounds__(128)
 k_emit(B2 t, int n, const uint2* __restrict__ queue, uint32_t count, uint2* __restrict__ nextQueue,
        EmitCounters* ctr, RQNode* __restrict__ nodes, RQTri* __restrict__ trisOut,
        const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals, uint32_t level,
-       const uint32_t* __restrict__ parentOf /* wide parent per queue entry */, uint32_t* __restrict__ nextParentOf) {
+       const uint32_t* __restrict__ parentOf /* wide parent per queue entry */, uint32_t* __restrict__ nextParentOf,
+       const uint32_t* __restrict__ idxIn, RQTriC* __restrict__ trisC, uint32_t* __restrict__ metaOut) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (q < count)
-    emit_one(t, n, q, queue, nextQueue, ctr, nodes, trisOut, trisIn, vals, level, parentOf, nextParentOf, s);
+    emit_one(t, n, q, queue, nextQueue, ctr, nodes, trisOut, trisIn, vals, level, parentOf, nextParentOf, s, idxIn, trisC, metaOut);
   #pragma unroll
   for (int k = 0; k < 5; k++)
     for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
@@ -1278,9 +1280,18 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
 
   uint64_t total = 0;
   std::vector<RQGeomDesc> hg(geoms, geoms + numGeoms);
-  for (auto& g : hg) { g.primBase = (uint32_t)total; total += g.numTris; }
-  if (total >= 0x7FFFFFF0ull) return (int)cudaErrorInvalidValue;
+  uint64_t totalVerts = 0; bool hasInstances = false;
+  for (auto& g : hg) {
+    g.primBase = (uint32_t)total; total += g.numTris;
+    g.vertBase = (uint32_t)totalVerts;
+    if (g.type == 1u) hasInstances = true; else totalVerts += g.numVerts;
+  }
+  if (total >= 0x7FFFFFF0ull || totalVerts >= 0xFFFFFFF0ull) return (int)cudaErrorInvalidValue;
   const uint32_t N = (uint32_t)total;
+  // RTC_SCENE_FLAG_COMPACT (= 2): indexed leaves + a vertex pool inside the image.  Instance primitives have no room in a
+  // 16-byte record, so a scene with instances keeps the 48-byte layout (the flag is a memory hint, as in the reference).
+  const bool compact = (sceneFlags & 2u) != 0u && !hasInstances;
+  const uint32_t numVerts = (compact && total > 0) ? (uint32_t)totalVerts : 0u;
 
   cudaEvent_t ev[7]; for (auto& e : ev) e = nullptr;
   DevBuf<RQGeomDesc> dGeoms; DevBuf<RQTri> trisIn, trisOut; DevBuf<uint64_t> keys0, keys1;
@@ -1289,6 +1300,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   DevBuf<uint32_t> rparent, rfirst, rlast, sizeAt, tlStart, tlBlock, tlTotal; uint32_t numTreelets = 0;
   DevBuf<float4> blo, bhi; DevBuf<float> cost; DevBuf<uint2> queue0, queue1; DevBuf<RQNode> nodes;
   DevBuf<Bounds12> dBounds; DevBuf<uint32_t> dInvalid; DevBuf<EmitCounters> dCtr;
+  DevBuf<uint32_t> idx3, metaOut; DevBuf<RQTriC> trisC; DevBuf<float4> vpool;
   Bounds12 hb; uint32_t hInvalid = 0; EmitCounters hc;
   uint32_t n = 0, depth = 0, numNodes = 1, numTris = 0;
   std::vector<uint32_t> levelEnd(1, 1u);                        // level 0 = the root = node range [0,1)
@@ -1308,7 +1320,8 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     CK(dGeoms.alloc(numGeoms));
     CK(cudaMemcpyAsync(dGeoms.p, hg.data(), sizeof(RQGeomDesc) * numGeoms, cudaMemcpyHostToDevice, stream));
     CK(trisIn.alloc(N)); CK(keys0.alloc(N)); CK(keys1.alloc(N)); CK(vals0.alloc(N)); CK(vals1.alloc(N));
-    k_setup_prims<<<blocksFor(N, 256), 256, 0, stream>>>(dGeoms.p, numGeoms, N, trisIn.p, dBounds.p, dInvalid.p);
+    if (compact) CK(idx3.alloc(3 * (size_t)N));
+    k_setup_prims<<<blocksFor(N, 256), 256, 0, stream>>>(dGeoms.p, numGeoms, N, trisIn.p, dBounds.p, dInvalid.p, compact ? idx3.p : nullptr);
     // The treelet builder only needs the Morton order down to cells of a few hundred triangles (everything below is rebuilt by SAH):
     // it sorts on the upper 32 bits of the code (10-11 bits per axis), i.e. half the radix passes; ties keep input order.
     k_morton<<<blocksFor(N, 256), 256, 0, stream>>>(trisIn.p, N, dBounds.p, keys0.p, vals0.p, P.mortonCubic,
@@ -1347,7 +1360,8 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     if (n > 0) {
       CK(blo.alloc(n2)); CK(bhi.alloc(n2)); CK(cost.alloc(n2 * 8)); CK(dec.alloc(n2));
       CK(left.alloc(n)); CK(right.alloc(n)); CK(parent.alloc(n2)); CK(rangeFirst.alloc(n)); CK(flag.alloc(n));
-      CK(trisOut.alloc(n)); CK(queue0.alloc(n)); CK(queue1.alloc(n)); CK(qParent0.alloc(n)); CK(qParent1.alloc(n));
+      if (compact) { CK(trisC.alloc(n)); CK(metaOut.alloc(n)); } else CK(trisOut.alloc(n));
+      CK(queue0.alloc(n)); CK(queue1.alloc(n)); CK(qParent0.alloc(n)); CK(qParent1.alloc(n));
       t.lo = blo.p; t.hi = bhi.p; t.cost = cost.p; t.dec = dec.p; t.left = left.p; t.right = right.p;
       t.parent = parent.p; t.rangeFirst = rangeFirst.p; t.flag = flag.p;
       CK(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t) * n, stream));
@@ -1379,11 +1393,11 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
           if (K == 512u) {
             const size_t smem = 4 * sizeof(TreeletSmem<512>);
             CK(cudaFuncSetAttribute(k_treelet_build<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_treelet_build<512><<<blocksFor(T, 4), 128, smem, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T);
+            k_treelet_build<512><<<blocksFor(T, 4), 128, smem, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T, keys0.p);
           } else {
             const size_t smem = 4 * sizeof(TreeletSmem<256>);
             CK(cudaFuncSetAttribute(k_treelet_build<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_treelet_build<256><<<blocksFor(T, 4), 128, smem, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T);
+            k_treelet_build<256><<<blocksFor(T, 4), 128, smem, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T, keys0.p);
           }
           CK(cudaEventRecord(ev[3], stream));
           k_refit_dp<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costNode, P.costTri, P.maxLeafTris, 0);
@@ -1406,7 +1420,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
         uint32_t it = 0;
         while (m > PLOC_TAIL_MAX) {                                 // large cluster counts: one grid per step
           const unsigned nb = blocksFor(m, PLOC_THREADS);
-          const uint32_t window = m > (1u << 20) ? 2u : 4u;
+          const uint32_t window = m > (1u << 20) ? 2u : (m > (1u << 16) ? 4u : 8u);
           for (uint32_t w = 0; w < window; w++, it++) {
             uint32_t* mCur = plocCtr.p + 1 + (it & 1u);
             uint32_t* mNext = plocCtr.p + 1 + ((it + 1u) & 1u);
@@ -1449,7 +1463,8 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       uint32_t count = 1;
       while (count > 0) {
         k_emit<<<blocksFor(count, 128), 128, 0, stream>>>(t, (int)n, qin, count, qout, dCtr.p, nodes.p, trisOut.p,
-                                                       trisIn.p, vals0.p, depth, depth ? pin : nullptr, pout);
+                                                       trisIn.p, vals0.p, depth, depth ? pin : nullptr, pout,
+                                                       compact ? idx3.p : nullptr, compact ? trisC.p : nullptr, compact ? metaOut.p : nullptr);
         rqCountLaunch(1);
         CK(cudaMemcpyAsync(&hc, dCtr.p, sizeof(hc), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
@@ -1478,7 +1493,14 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     H.lo[3] = H.hi[3] = 0.f;
     H.nodesOffset = 128;
     H.trisOffset = H.nodesOffset + (uint64_t)numNodes * sizeof(RQNode);
-    H.totalBytes = (H.trisOffset + (uint64_t)numTris * sizeof(RQTri) + 127ull) & ~127ull;
+    if (compact) {
+      H.layout = 1u; H.numVerts = numVerts;
+      H.metaOffset = (H.trisOffset + (uint64_t)numTris * sizeof(RQTriC) + 127ull) & ~127ull;
+      H.vertsOffset = (H.metaOffset + (uint64_t)numTris * 4ull + 127ull) & ~127ull;
+      H.totalBytes = (H.vertsOffset + (uint64_t)numVerts * 16ull + 127ull) & ~127ull;
+    } else {
+      H.totalBytes = (H.trisOffset + (uint64_t)numTris * sizeof(RQTri) + 127ull) & ~127ull;
+    }
     const double rootA = n ? (double)halfArea(H.hi[0] - H.lo[0], H.hi[1] - H.lo[1], H.hi[2] - H.lo[2]) : 0.0;
     H.sah = rootA > 0 ? (hc.sahInnerQ + hc.sahLeafQ) / rootA : 0.0;
     if (!monitorAlloc(H.totalBytes)) { err = (int)cudaErrorMemoryAllocation; goto fail; }
@@ -1487,7 +1509,17 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     CK(cudaMemsetAsync(image, 0, H.totalBytes, stream));
     CK(cudaMemcpyAsync(image, &H, sizeof(H), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync((char*)image + H.nodesOffset, nodes.p, (size_t)numNodes * sizeof(RQNode), cudaMemcpyDeviceToDevice, stream));
-    if (numTris) CK(cudaMemcpyAsync((char*)image + H.trisOffset, trisOut.p, (size_t)numTris * sizeof(RQTri), cudaMemcpyDeviceToDevice, stream));
+    if (compact) {
+      if (numTris) {
+        CK(cudaMemcpyAsync((char*)image + H.trisOffset, trisC.p, (size_t)numTris * sizeof(RQTriC), cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync((char*)image + H.metaOffset, metaOut.p, (size_t)numTris * 4, cudaMemcpyDeviceToDevice, stream));
+      }
+      if (numVerts) {                                            // the pool is written straight into the image
+        k_copy_verts<<<blocksFor(numVerts, 256), 256, 0, stream>>>(dGeoms.p, numGeoms, numVerts, (float4*)((char*)image + H.vertsOffset));
+        rqCountLaunch(1);
+        CK(cudaGetLastError());
+      }
+    } else if (numTris) CK(cudaMemcpyAsync((char*)image + H.trisOffset, trisOut.p, (size_t)numTris * sizeof(RQTri), cudaMemcpyDeviceToDevice, stream));
     CK(cudaEventRecord(ev[6], stream));
     CK(cudaStreamSynchronize(stream));
     if (stats) {
@@ -1586,8 +1618,10 @@ k_refit_tris(const RQGeomDesc* __restrict__ geomsByID, uint32_t numSlots, RQTri*
 
 struct RefitSums { double sahInnerQ, sahLeafQ, sahInnerX, sahLeafX, sahLeafTrisQ; };
 
+template <bool COMPACT>
 __global__ void __launch_bounds__(128)
-k_refit_nodes(RQNode* __restrict__ nodes, const RQTri* __restrict__ tris, uint32_t first, uint32_t count, RefitSums* sums) {
+k_refit_nodes(RQNode* __restrict__ nodes, const RQTri* __restrict__ tris, uint32_t first, uint32_t count, RefitSums* sums,
+              const RQTriC* __restrict__ trisC, const float4* __restrict__ pool) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (q < count) {
@@ -1615,10 +1649,16 @@ k_refit_nodes(RQNode* __restrict__ nodes, const RQTri* __restrict__ tris, uint32
             if (!(bits & (1u << j))) continue;
             const uint32_t b = 3u * k + j;
             const uint32_t ti = N.triBase + __popc(tvalid & ((1u << b) - 1u));
-            const float4* src = (const float4*)(tris + ti);
             float4 ta, tb, tc;
-            if (ti & 1u) { tc = src[0]; ta = src[1]; tb = src[2]; } else { ta = src[0]; tb = src[1]; tc = src[2]; }
-            // fminf / fmaxf drop NaN operands: a triangle invalidated by k_refit_tris adds nothing
+            if (COMPACT) {                                      // same nine floats, gathered through the indices
+              const RQTriC r = trisC[ti];
+              const float4 p0 = pool[r.v0], p1 = pool[r.v1], p2 = pool[r.v2];
+              ta = make_float4(p0.x, p0.y, p0.z, p1.x); tb = make_float4(p1.y, p1.z, p2.x, p2.y); tc = make_float4(p2.z, 0.f, 0.f, 0.f);
+            } else {
+              const float4* src = (const float4*)(tris + ti);
+              if (ti & 1u) { tc = src[0]; ta = src[1]; tb = src[2]; } else { ta = src[0]; tb = src[1]; tc = src[2]; }
+            }
+            // fminf / fmaxf drop NaN operands: a triangle invalidated by k_refit_tris (or with non-finite pool vertices) adds nothing
             clo[k][0] = fminf(clo[k][0], fminf(fminf(ta.x, ta.w), tb.z)); chi[k][0] = fmaxf(chi[k][0], fmaxf(fmaxf(ta.x, ta.w), tb.z));
             clo[k][1] = fminf(clo[k][1], fminf(fminf(ta.y, tb.x), tb.w)); chi[k][1] = fmaxf(chi[k][1], fmaxf(fmaxf(ta.y, tb.x), tb.w));
             clo[k][2] = fminf(clo[k][2], fminf(fminf(ta.z, tb.y), tc.x)); chi[k][2] = fmaxf(chi[k][2], fmaxf(fmaxf(ta.z, tb.y), tc.x));
@@ -1698,7 +1738,19 @@ int rqRefitBVH(const RQGeomDesc* geomsByID, int numSlots, RQDeviceImage* img, rq
   CK(dGeoms.alloc(numSlots > 0 ? numSlots : 1)); CK(dSums.alloc(1));
   if (numSlots > 0) CK(cudaMemcpyAsync(dGeoms.p, geomsByID, sizeof(RQGeomDesc) * numSlots, cudaMemcpyHostToDevice, stream));
   CK(cudaMemsetAsync(dSums.p, 0, sizeof(RefitSums), stream));
-  if (H.numTris) {
+  if (H.layout == 1u) {
+    // compact image: the records hold indices, only the vertex pool changes (meshes in geomID order, as at build time)
+    std::vector<RQGeomDesc> hg(geomsByID, geomsByID + (numSlots > 0 ? numSlots : 0));
+    uint64_t tv = 0;
+    for (auto& g : hg) { g.vertBase = (uint32_t)tv; if (g.type != 1u && g.indices != nullptr) tv += g.numVerts; else g.numVerts = 0; }
+    if (tv != H.numVerts) { err = (int)cudaErrorInvalidValue; goto fail; }      // not the meshes this image was built from
+    if (numSlots > 0) CK(cudaMemcpyAsync(dGeoms.p, hg.data(), sizeof(RQGeomDesc) * numSlots, cudaMemcpyHostToDevice, stream));
+    if (H.numVerts) {
+      k_copy_verts<<<blocksFor(H.numVerts, 256), 256, 0, stream>>>(dGeoms.p, numSlots, H.numVerts, (float4*)((char*)img->base + H.vertsOffset));
+      rqCountLaunch(1);
+      CK(cudaGetLastError());
+    }
+  } else if (H.numTris) {
     k_refit_tris<<<blocksFor(H.numTris, 256), 256, 0, stream>>>(dGeoms.p, (uint32_t)(numSlots > 0 ? numSlots : 0), tris, H.numTris);
     rqCountLaunch(1);
     CK(cudaGetLastError());
@@ -1707,7 +1759,11 @@ int rqRefitBVH(const RQGeomDesc* geomsByID, int numSlots, RQDeviceImage* img, rq
   for (int l = (int)img->numLevels - 1; l >= 0; l--) {
     const uint32_t first = l ? img->levelEnd[l - 1] : 0u, count = img->levelEnd[l] - first;
     if (!count) continue;
-    k_refit_nodes<<<blocksFor(count, 128), 128, 0, stream>>>(nodes, tris, first, count, dSums.p);
+    if (H.layout == 1u)
+      k_refit_nodes<true><<<blocksFor(count, 128), 128, 0, stream>>>(nodes, tris, first, count, dSums.p, (const RQTriC*)((char*)img->base + H.trisOffset),
+                                                                     (const float4*)((char*)img->base + H.vertsOffset));
+    else
+      k_refit_nodes<false><<<blocksFor(count, 128), 128, 0, stream>>>(nodes, tris, first, count, dSums.p, nullptr, nullptr);
     rqCountLaunch(1);
   }
   CK(cudaGetLastError());
@@ -1750,7 +1806,7 @@ fail:
 namespace {
 __global__ void __launch_bounds__(256)
 k_validate_image(const RQNode* __restrict__ nodes, const RQTri* __restrict__ tris, uint32_t numNodes, uint32_t numTris, uint32_t depth,
-                 unsigned int* violations) {
+                 unsigned int* violations, uint32_t compact, uint32_t numVerts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool bad = false;
   if (i < numNodes) {
@@ -1770,7 +1826,10 @@ k_validate_image(const RQNode* __restrict__ nodes, const RQTri* __restrict__ tri
       if (tb != 0u && tb != 1u && tb != 3u && tb != 7u) bad = true;
     }
   }
-  if (i < numTris) {
+  if (i < numTris && compact) {
+    const RQTriC r = ((const RQTriC*)tris)[i];
+    if (r.v0 >= numVerts || r.v1 >= numVerts || r.v2 >= numVerts) bad = true;
+  } else if (i < numTris) {
     const uint4* rec = (const uint4*)(tris + i);
     const uint32_t pad = (i & 1u) ? rec[0].w : rec[2].w;        // odd records are stored rotated (rq_types.h)
     if (pad & RQ_PAD_INSTANCE) bad = true;                      // instance records refer to other scenes' device memory
@@ -1788,7 +1847,8 @@ int rqValidateImage(const void* image, const RQImageHeader* H, rqStream stream_,
   const uint32_t n = H->numNodes > H->numTris ? H->numNodes : H->numTris;
   if (e == cudaSuccess && n) {
     k_validate_image<<<blocksFor(n, 256), 256, 0, stream>>>((const RQNode*)((const char*)image + H->nodesOffset),
-                                                            (const RQTri*)((const char*)image + H->trisOffset), H->numNodes, H->numTris, H->depth, d);
+                                                            (const RQTri*)((const char*)image + H->trisOffset), H->numNodes, H->numTris, H->depth, d,
+                                                            H->layout, H->numVerts);
     rqCountLaunch(1);
     e = cudaGetLastError();
   }

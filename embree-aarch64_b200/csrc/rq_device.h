@@ -68,6 +68,8 @@ struct RQTraceArgs {
   uint32_t    packed;           // 1 = `rays` holds dense 32-byte records {org.xyz, tnear, dir.xyz, tfar} (stride 32); needs hitList
   void*       hitList;          // compact output (flat scenes only): device buffer for one record per hit ray, 48 B (closest) or
   unsigned int* hitCount;       //   4 B (occluded), appended through this device counter (zeroed by the launcher); `out` is then unused
+  uint32_t    compact;          // 1 = the image uses the compact (indexed) triangle layout: metaOffset / vertsOffset are valid
+  uint64_t    metaOffset, vertsOffset;
   const void* instances;        // device array of RQInstance when the scene holds instance geometries, else NULL;
                                 // `depth` must then cover top-level depth + 3 + the deepest instanced BVH
 };

@@ -45,6 +45,8 @@ struct TraceParams {
   char* hitList;               // LIST kernels only: compact output, one record per ray that hit (48 B closest, 4 B occluded) ...
   unsigned int* hitCount;      // ... appended through this counter (zero at launch); nothing is written to `out`
   uint32_t packed;             // LIST kernels only: rays are dense 32-byte records {org.xyz, tnear, dir.xyz, tfar}
+  const float4* verts;         // COMPACT kernels only: vertex pool of the image ...
+  const uint32_t* meta;        // ... and the per-triangle geomID | quad-flag words
 };
 
 __device__ __forceinline__ float rcpSafe(float d) {           // common/math/vec3fa.h:172-177
@@ -98,7 +100,9 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
 // records, a ray that hit appends one record {rid, tfar, -, - | Ng.xyz, u | v, primID, geomID, instID}
 // (closest) or its index (occluded) to a list; the host downloads only that list and scatters it
 // into the caller's buffer, so the PCIe link carries ~13 instead of 80 bytes per ray outbound.
-template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int SPILL, bool INST = false, bool LIST = false>
+// COMPACT = the image uses indexed 16-byte triangle records (RTC_SCENE_FLAG_COMPACT; reference: Triangle4i, trianglei.h): the
+// three vertices are fetched through the indices (one more dependent load per test), geomID and the quad flag only for the final hit.
+template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int SPILL, bool INST = false, bool LIST = false, bool COMPACT = false>
 #ifndef RQ_MIN_CTAS
 #define RQ_MIN_CTAS 8   /* 64 registers: 8 CTAs = 32 warps per SM; (128,1) let ptxas take 95 registers and cost 20 % (profiles/r01k_ab.log) */
 #endif
@@ -227,11 +231,20 @@ k_trace(const TraceParams P) {
           const uint32_t b = 31u - (uint32_t)__clz((int)tmask);
           tmask &= ~(1u << b);
           const uint32_t ti = triBase + __popc(tvalid & ((1u << b) - 1u));
-          const char* tp = (INST ? ctris : P.tris) + (size_t)ti * 48;
-          const uint32_t odd = ti & 1u;                         // odd records store their last 16 bytes first (32-byte alignment of the wide load)
-          uint32_t tw[8];
-          ldg256(tp + (odd ? 16 : 0), tw);
-          const float4 t2 = __ldg((const float4*)(tp + (odd ? 0 : 32)));
+          uint32_t tw[8]; float4 t2;
+          if (COMPACT) {
+            const uint4 rec = __ldg((const uint4*)(P.tris + (size_t)ti * 16));
+            const float4 p0 = __ldg(P.verts + rec.x), p1 = __ldg(P.verts + rec.y), p2 = __ldg(P.verts + rec.z);
+            tw[0] = __float_as_uint(p0.x); tw[1] = __float_as_uint(p0.y); tw[2] = __float_as_uint(p0.z);
+            tw[3] = __float_as_uint(p1.x); tw[4] = __float_as_uint(p1.y); tw[5] = __float_as_uint(p1.z);
+            tw[6] = __float_as_uint(p2.x); tw[7] = __float_as_uint(p2.y);
+            t2 = make_float4(p2.z, __uint_as_float(rec.w), __uint_as_float(ti), 0.f);   // "geomID" = the triangle's index until the ray is finished
+          } else {
+            const char* tp = (INST ? ctris : P.tris) + (size_t)ti * 48;
+            const uint32_t odd = ti & 1u;                       // odd records store their last 16 bytes first (32-byte alignment of the wide load)
+            ldg256(tp + (odd ? 16 : 0), tw);
+            t2 = __ldg((const float4*)(tp + (odd ? 0 : 32)));
+          }
           if (COUNT) cntTris++;
           if (INST && (__float_as_uint(t2.w) & 0x80000000u)) {
             // ---- instance record: enter the instanced scene ----
@@ -312,6 +325,11 @@ k_trace(const TraceParams P) {
           if (sp > (int)sdepth + SPILL) sp = (int)sdepth + SPILL;  // entries beyond the stack were dropped (cannot happen: capacity >= depth)
           if (sp == 0) {
             active = false;
+            if (COMPACT && found && !OCCLUDED) {                // the hit's triangle index -> geomID, quad half (quad_intersector_moeller.h:28-37)
+              const uint32_t m = __ldg(P.meta + hGeom);
+              if (m & RQ_META_FLIPUV) { hu = 1.0f - fminf(hu, 1.0f); hv = 1.0f - fminf(hv, 1.0f); }
+              hGeom = m & ~RQ_META_FLIPUV;
+            }
             if (found && LIST) {
               // warp-aggregated append: the lanes that finish a hit ray in this very iteration share one atomic
               const unsigned fm = __activemask();
@@ -510,6 +528,19 @@ cudaError_t launchStack(TraceParams& P, uint32_t depth, cudaStream_t s) {
     if (P.split) return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, true, 32, false, true>, P, s);
     return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, false, 32, false, true>, P, s);
   }
+  if (P.verts) {
+    // compact (indexed) images: flat scenes only, in-place output, no counters; deep trees fall into the widest local stack
+    if (P.instances || P.hitList) return cudaErrorInvalidValue;
+    if (spill == 0) {
+      if (P.split) return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, true, 0, false, false, true>, P, s);
+      return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, false, 0, false, false, true>, P, s);
+    }
+    if (spill <= 32) {
+      if (P.split) return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, true, 32, false, false, true>, P, s);
+      return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, false, 32, false, false, true>, P, s);
+    }
+    return launchOne(k_trace<OCC, ROBUST, false, ALIGNED, false, 208, false, false, true>, P, s);
+  }
   if (P.instances) {
     // instanced scenes: one stack configuration (shared levels + 32 local entries), no counters
     if (spill > 32) return cudaErrorInvalidValue;
@@ -543,7 +574,10 @@ static int launchTrace(bool occ, const RQTraceArgs* a, cudaStream_t s) {
   P.refillBelow = a->refillBelow ? a->refillBelow : 26u;
   P.split = a->split; P.tVote = a->tVote; P.sdepth = a->stackSmem;
   P.instances = (const RQInstance*)a->instances;
+  P.verts = a->compact ? (const float4*)((const char*)a->image + a->vertsOffset) : nullptr;
+  P.meta = a->compact ? (const uint32_t*)((const char*)a->image + a->metaOffset) : nullptr;
   P.hitList = (char*)a->hitList; P.hitCount = a->hitCount; P.packed = a->hitList ? a->packed : 0u;
+  if (P.verts && (P.hitList || P.instances || a->counters)) return (int)cudaErrorInvalidValue;   // the host never asks for these combinations
   if (P.hitList) {
     if (!P.hitCount) return (int)cudaErrorInvalidValue;
     cudaError_t ec = cudaMemsetAsync(P.hitCount, 0, sizeof(unsigned int), s);

@@ -58,6 +58,13 @@ struct alignas(16) RQTri {
 };
 static_assert(sizeof(RQTri) == 48, "RQTri must be 48 bytes");
 
+struct alignas(16) RQTriC {   // compact (indexed) triangle record, see RQImageHeader::layout
+  uint32_t v0, v1, v2;       // vertex pool indices
+  uint32_t primID;
+};
+static_assert(sizeof(RQTriC) == 16, "RQTriC must be 16 bytes");
+#define RQ_META_FLIPUV 0x80000000u
+
 // One instance of another committed scene (RTC_GEOMETRY_TYPE_INSTANCE, single level), 80 bytes =
 // five 16-byte loads.  A triangle record of the top-level BVH whose `pad` word is
 // RQ_PAD_INSTANCE | i stands for instances[i]; its v0 / v1 hold the world-space bounds.
@@ -90,6 +97,8 @@ struct RQGeomDesc {
                              // 2 = quad mesh: RTC_FORMAT_UINT4 index records, numTris = 2 x quads (triangle 2q = (v0,v1,v3), 2q+1 = (v2,v3,v1))
   uint32_t instIndex;        // index into the scene's RQInstance table
   float    lo[3], hi[3];     // instance only: world-space bounds = xfmBounds(local2world, bounds of the instanced scene)
+  uint32_t vertBase;         // first vertex of this mesh in the vertex pool of a compact image (filled in by the builder)
+  uint32_t pad;
 };
 
 // Flat image of a committed BVH: header + nodes + triangles, all offset based, so a byte copy
@@ -106,7 +115,15 @@ struct RQImageHeader {
   uint64_t trisOffset;
   uint64_t totalBytes;
   double   sah;              // SAH cost, reference formula (bvh_statistics.h:36-38,99-101)
-  uint64_t pad[5];
+  // RTC_SCENE_FLAG_COMPACT layout (layout == 1; reference: Triangle4i, kernels/geometry/trianglei.h): the triangle section holds
+  // 16-byte RQTriC records (three indices into the image's own vertex pool + primID), followed by one 4-byte word per triangle
+  // (geomID, bit 31 = second half of a quad) that is only read for the final hit, and the vertex pool (one float4 per vertex of
+  // every attached mesh, in geomID order).  ~28 instead of 48 bytes per triangle; one more dependent load per triangle test.
+  uint64_t metaOffset;
+  uint64_t vertsOffset;
+  uint32_t numVerts;
+  uint32_t layout;           // 0 = 48-byte RQTri records, 1 = compact
+  uint64_t pad[2];
 };
 static_assert(sizeof(RQImageHeader) == 128, "header is one line");
 #define RQ_IMAGE_MAGIC 0x3276303032425152ull   /* 'RQB200v2' */

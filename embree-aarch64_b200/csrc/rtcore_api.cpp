@@ -628,6 +628,7 @@ void checkQuery(Scene* sc, RTCIntersectContext* ctx) {
 void fillArgs(Scene* sc, RTCIntersectContext* ctx, RQTraceArgs& a, bool stream) {
   memset(&a, 0, sizeof(a));
   a.image = sc->image.base; a.nodesOffset = sc->image.header.nodesOffset; a.trisOffset = sc->image.header.trisOffset;
+  a.compact = sc->image.header.layout == 1u ? 1u : 0u; a.metaOffset = sc->image.header.metaOffset; a.vertsOffset = sc->image.header.vertsOffset;
   a.depth = sc->numInstances ? sc->traceDepth : sc->image.header.depth;
   a.instances = sc->numInstances ? sc->dInstances : nullptr;
   a.robust = (sc->flags & RTC_SCENE_FLAG_ROBUST) ? 1u : 0u;
@@ -939,6 +940,7 @@ void traceStreamOn(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, 
   dev->bind();
   RQTraceArgs a; fillArgs(sc, ctx, a, streamRule != 0);
   RQTraceCounters* dC = nullptr;
+  if (countersOut && a.compact) fail(RTC_ERROR_INVALID_OPERATION, "traversal counters are not available for RTC_SCENE_FLAG_COMPACT scenes");
   if (countersOut) {
     std::lock_guard<std::mutex> l(dev->stageMutex);
     if (!dev->dCounters) cudaCheck(cudaMalloc((void**)&dev->dCounters, sizeof(RQTraceCounters)), "counters");
@@ -968,7 +970,7 @@ void traceStreamOn(Scene* sc, RTCIntersectContext* ctx, void* rays, unsigned M, 
       cudaCheck(occluded ? rqLaunchOccluded(&a, (rqStream)s) : rqLaunchIntersect(&a, (rqStream)s), "trace launch");
     }
     if (!dev->async || countersOut || mapped) cudaCheck(cudaStreamSynchronize(s), "trace");
-  } else if (dev->d2hMode == 3 && !mapped && !countersOut && !sc->numInstances && M >= 65536 && stride >= recBytes &&
+  } else if (dev->d2hMode == 3 && !mapped && !countersOut && !sc->numInstances && !a.compact && M >= 65536 && stride >= recBytes &&
              // page-locked streams below ~4 M rays are faster through whole-span copies; pageable ones never are (the driver bounces them)
              (M >= dev->compactMinRays || (M >= (1u << 18) && dev->packPageable && mappedHostPointer(rays) == nullptr)) &&
              a.depth <= 32 + (unsigned)dev->stackSmem) {
@@ -1748,10 +1750,14 @@ void adoptImage(Scene* s, const void* src, size_t bytes) {
   std::unique_lock<std::mutex> lock(s->buildMutex);
   RQImageHeader H;
   cudaCheck(cudaMemcpy(&H, src, sizeof(H), cudaMemcpyDefault), "image header");
-  if (H.magic != RQ_IMAGE_MAGIC || H.totalBytes != bytes || H.nodesOffset != 128 ||
-      H.trisOffset != H.nodesOffset + (uint64_t)H.numNodes * sizeof(RQNode) ||
-      H.trisOffset + (uint64_t)H.numTris * sizeof(RQTri) > H.totalBytes)
-    fail(RTC_ERROR_INVALID_ARGUMENT, "not a BVH image");
+  bool okHeader = H.magic == RQ_IMAGE_MAGIC && H.totalBytes == bytes && H.nodesOffset == 128 && H.layout <= 1u &&
+                  H.trisOffset == H.nodesOffset + (uint64_t)H.numNodes * sizeof(RQNode);
+  if (okHeader && H.layout == 1u)
+    okHeader = H.metaOffset >= H.trisOffset + (uint64_t)H.numTris * sizeof(RQTriC) && H.vertsOffset >= H.metaOffset + (uint64_t)H.numTris * 4ull &&
+               H.vertsOffset + (uint64_t)H.numVerts * 16ull <= H.totalBytes && (H.metaOffset & 15u) == 0 && (H.vertsOffset & 15u) == 0;
+  else if (okHeader)
+    okHeader = H.trisOffset + (uint64_t)H.numTris * sizeof(RQTri) <= H.totalBytes;
+  if (!okHeader) fail(RTC_ERROR_INVALID_ARGUMENT, "not a BVH image");
   if (H.depth == 0 || H.depth > RQ_MAX_LEVELS || H.numNodes == 0) fail(RTC_ERROR_INVALID_ARGUMENT, "not a BVH image (depth / node count out of range)");
   void* p = nullptr;
   cudaCheck(rqAllocImage(&p, bytes, (rqStream)dev->stream()), "image alloc");

@@ -14,7 +14,8 @@ NODE_DT = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("pad0", "u1"), ("childBase
                     ("parent", "<u4"), ("numTris", "<u4"), ("level", "<u4"), ("pad", "<u4", 3)])
 assert NODE_DT.itemsize == 128
 HEADER_DT = np.dtype([("magic", "<u8"), ("numNodes", "<u4"), ("numTris", "<u4"), ("depth", "<u4"), ("flags", "<u4"), ("lo", "<f4", 4),
-                      ("hi", "<f4", 4), ("nodesOffset", "<u8"), ("trisOffset", "<u8"), ("totalBytes", "<u8"), ("sah", "<f8"), ("pad", "<u8", 5)])
+                      ("hi", "<f4", 4), ("nodesOffset", "<u8"), ("trisOffset", "<u8"), ("totalBytes", "<u8"), ("sah", "<f8"),
+                      ("metaOffset", "<u8"), ("vertsOffset", "<u8"), ("numVerts", "<u4"), ("layout", "<u4"), ("pad", "<u8", 2)])
 assert HEADER_DT.itemsize == 128
 
 
@@ -32,6 +33,19 @@ class Image:
         assert int(H["magic"]) == MAGIC and int(H["totalBytes"]) == raw.size
         n, t = int(H["numNodes"]), int(H["numTris"])
         self.nodes = raw[int(H["nodesOffset"]):int(H["nodesOffset"]) + 128 * n].view(NODE_DT)
+        self.compact = int(H["layout"]) == 1
+        if self.compact:
+            # RTC_SCENE_FLAG_COMPACT: 16-byte records (3 vertex-pool indices + primID), per-triangle geomID | quad flag, float4 pool
+            rec = raw[int(H["trisOffset"]):int(H["trisOffset"]) + 16 * t].view("<u4").reshape(t, 4)
+            meta = raw[int(H["metaOffset"]):int(H["metaOffset"]) + 4 * t].view("<u4")
+            nv = int(H["numVerts"])
+            pool = raw[int(H["vertsOffset"]):int(H["vertsOffset"]) + 16 * nv].view("<f4").reshape(nv, 4)
+            assert (rec[:, :3] < max(nv, 1)).all(), "vertex index out of range"
+            self.tri_words = rec
+            self.verts = pool[rec[:, :3].astype(np.int64), :3]
+            self.primID, self.geomID = rec[:, 3], meta & np.uint32(0x7FFFFFFF)
+            self.pad = ((meta >> 31) << 30).astype(np.uint32)       # quad flag in the position check_structure expects
+            return
         tr = raw[int(H["trisOffset"]):int(H["trisOffset"]) + 48 * t].view("<u4").reshape(t, 12).copy()
         odd = np.arange(t) & 1 == 1                      # odd records are stored rotated by 16 bytes (rq_types.h)
         tr[odd] = np.concatenate([tr[odd][:, 4:], tr[odd][:, :4]], axis=1)
