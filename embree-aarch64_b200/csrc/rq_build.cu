@@ -707,6 +707,7 @@ k_ploc_tail(B2 t, uint32_t* __restrict__ cidA, uint32_t* __restrict__ cidB, uint
 // ----------------------------------------------------------------------------------------------
 constexpr int TL_BINS = 16;
 constexpr int TL_SMALL = 32;
+constexpr int TL_SWEEP = 16;                                   // RTC_BUILD_QUALITY_HIGH: nodes of at most this many triangles get an exact sweep SAH in the thread phase
 constexpr uint32_t TL_ORD_PINF = 0xFF800000u;                 // f2ord(+inf)
 constexpr uint32_t TL_ORD_NINF = 0x007FFFFFu;                 // f2ord(-inf)
 
@@ -785,7 +786,7 @@ k_treelet_roots(int n, const uint32_t* __restrict__ treeletStart, const uint32_t
   cid[t] = sizeAt[a] == 1u ? (uint32_t)(n - 1) + a : (T - 1u) + (a - t);
 }
 
-template <int K>
+template <int K, int SWEEP>
 struct TreeletSmem {                                           // one per warp
   float    box[6][K];                                          // lo.xyz, hi.xyz of the treelet's triangles (SoA: lane-strided access is conflict free)
   uint32_t key[K];                                             // upper 32 bits of the Morton code (what the triangles were sorted by)
@@ -793,6 +794,8 @@ struct TreeletSmem {                                           // one per warp
   uint32_t bins[3][TL_BINS][7];                                // per axis and bin: ordered-uint lo.xyz, hi.xyz, count
   uint32_t stack[16][2];                                       // pending large nodes: begin | end << 16, local node index
   uint32_t small[K / 2][2];                                    // subtrees left to the thread phase, same encoding
+  float    keys[SWEEP ? SWEEP : 1][32];                        // thread phase (SWEEP > 0): sort keys of the lane's current node
+  float    suffix[SWEEP ? SWEEP : 1][32];                      // thread phase (SWEEP > 0): right-side areas of the lane's current node
 };
 
 __device__ __forceinline__ float boxArea6(const float lo[3], const float hi[3]) {
@@ -801,8 +804,8 @@ __device__ __forceinline__ float boxArea6(const float lo[3], const float hi[3]) 
 
 // one lane builds the subtree over perm[b0, e0) (2 <= e0 - b0 <= TL_SMALL) rooted at local node index j0: radix-tree splits of
 // the Morton-ordered slice (Karras 2012 on the sub-sequence; equal codes are halved by position)
-template <int K>
-__device__ void treeletSmallSubtree(TreeletSmem<K>& S, const B2& t, uint32_t b0, uint32_t e0, uint32_t j0, uint32_t base, uint32_t leaf0) {
+template <int K, int SWEEP>
+__device__ void treeletSmallSubtree(TreeletSmem<K, SWEEP>& S, const B2& t, uint32_t b0, uint32_t e0, uint32_t j0, uint32_t base, uint32_t leaf0, int lane) {
   uint32_t st[8]; int sp = 0;                                   // the smaller child is finished first: <= log2(TL_SMALL) + 1 pending ranges
   st[sp++] = b0 | (e0 << 10) | (j0 << 20);
   while (sp > 0) {
@@ -810,6 +813,52 @@ __device__ void treeletSmallSubtree(TreeletSmem<K>& S, const B2& t, uint32_t b0,
     const uint32_t b = w & 1023u, e = (w >> 10) & 1023u, j = w >> 20;
     const uint32_t m = e - b;
     uint32_t mL = m >> 1;
+    if (SWEEP > 0 && m > 2u && m <= (uint32_t)SWEEP) {
+      // RTC_BUILD_QUALITY_HIGH only.  The last levels decide which two or three triangles share a leaf slot: exact sweep SAH,
+      // all three axes, every split position (the slice is insertion-sorted along the axis, suffix areas in shared scratch).
+      // Worth +8 % occlusion and +1.5 % closest-hit Mrays/s on the 10 M-triangle scene, but one thread per subtree runs at ~7
+      // active lanes: +6 ... +15 ms of build time (profiles/r02b_ab_c3.jsonl, r02e_ab.jsonl, r02f_ab.jsonl) -- the default
+      // quality (MEDIUM) keeps the radix rule below TL_SMALL triangles.
+      float best = INFINITY; int bestAxis = -1; int split = (int)mL;
+      const int mi = (int)m;
+      for (int a = 0; a < 3; a++) {
+        for (int i = 0; i < mi; i++) { const uint32_t p = S.perm[b + i]; S.keys[i][lane] = S.box[a][p] + S.box[3 + a][p]; }
+        for (int i = 1; i < mi; i++) {
+          const float k = S.keys[i][lane]; const uint16_t p = S.perm[b + i];
+          int q = i - 1;
+          while (q >= 0 && (S.keys[q][lane] > k || (S.keys[q][lane] == k && S.perm[b + q] > p))) {
+            S.keys[q + 1][lane] = S.keys[q][lane]; S.perm[b + q + 1] = S.perm[b + q]; q--;
+          }
+          S.keys[q + 1][lane] = k; S.perm[b + q + 1] = p;
+        }
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = mi - 1; i >= 1; i--) {
+          const uint32_t p = S.perm[b + i];
+          for (int c = 0; c < 3; c++) { lo[c] = fminf(lo[c], S.box[c][p]); hi[c] = fmaxf(hi[c], S.box[3 + c][p]); }
+          S.suffix[i][lane] = boxArea6(lo, hi);
+        }
+        for (int c = 0; c < 3; c++) { lo[c] = INFINITY; hi[c] = -INFINITY; }
+        for (int i = 1; i < mi; i++) {
+          const uint32_t p = S.perm[b + i - 1];
+          for (int c = 0; c < 3; c++) { lo[c] = fminf(lo[c], S.box[c][p]); hi[c] = fmaxf(hi[c], S.box[3 + c][p]); }
+          const float cost = boxArea6(lo, hi) * (float)i + S.suffix[i][lane] * (float)(mi - i);
+          if (cost < best) { best = cost; bestAxis = a; split = i; }
+        }
+      }
+      if (bestAxis >= 0 && bestAxis != 2) {                     // the slice is sorted along z now: restore the winning order
+        const int a = bestAxis;
+        for (int i = 0; i < mi; i++) { const uint32_t p = S.perm[b + i]; S.keys[i][lane] = S.box[a][p] + S.box[3 + a][p]; }
+        for (int i = 1; i < mi; i++) {
+          const float k = S.keys[i][lane]; const uint16_t p = S.perm[b + i];
+          int q = i - 1;
+          while (q >= 0 && (S.keys[q][lane] > k || (S.keys[q][lane] == k && S.perm[b + q] > p))) {
+            S.keys[q + 1][lane] = S.keys[q][lane]; S.perm[b + q + 1] = S.perm[b + q]; q--;
+          }
+          S.keys[q + 1][lane] = k; S.perm[b + q + 1] = p;
+        }
+      }
+      mL = (uint32_t)split;
+    } else {
     const uint32_t kf = S.key[S.perm[b]], kl = S.key[S.perm[e - 1u]];
     if (m > 2u && kf != kl) {
       const int prefix = __clz((int)(kf ^ kl));                 // the slice is sorted: find the first code that differs from kf in the top differing bit
@@ -820,6 +869,7 @@ __device__ void treeletSmallSubtree(TreeletSmem<K>& S, const B2& t, uint32_t b0,
         if (q < m && __clz((int)(kf ^ S.key[S.perm[b + q]])) > prefix) lo = q;
       } while (step > 1u);
       mL = lo + 1u;
+    }
     }
     const uint32_t mR = m - mL;
     const uint32_t jL = j + 1u, jR = j + mL;
@@ -833,14 +883,14 @@ __device__ void treeletSmallSubtree(TreeletSmem<K>& S, const B2& t, uint32_t b0,
   }
 }
 
-template <int K>
+template <int K, int SWEEP>
 __global__ void __launch_bounds__(128)
 k_treelet_build(B2 t, int n, const uint32_t* __restrict__ treeletStart, const uint32_t* __restrict__ sizeAt, uint32_t T,
                 const uint64_t* __restrict__ keys) {
   extern __shared__ __align__(16) unsigned char tlSmemRaw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
-  TreeletSmem<K>& S = reinterpret_cast<TreeletSmem<K>*>(tlSmemRaw)[warp];
+  TreeletSmem<K, SWEEP>& S = reinterpret_cast<TreeletSmem<K, SWEEP>*>(tlSmemRaw)[warp];
   const uint32_t tIdx = blockIdx.x * 4u + (uint32_t)warp;
   if (tIdx >= T) return;                                        // warps are independent: no block-wide barrier below
   const uint32_t a0 = treeletStart[tIdx], m0 = sizeAt[a0];
@@ -1001,7 +1051,7 @@ k_treelet_build(B2 t, int n, const uint32_t* __restrict__ treeletStart, const ui
     const int s = s0 + lane;
     if (s < nsmall) {
       const uint32_t be = S.small[s][0];
-      treeletSmallSubtree<K>(S, t, be & 0xFFFFu, be >> 16, S.small[s][1], base, leaf0);
+      treeletSmallSubtree<K, SWEEP>(S, t, be & 0xFFFFu, be >> 16, S.small[s][1], base, leaf0, lane);
     }
   }
 }
@@ -1273,7 +1323,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   ScratchScope scratch(stream);
   t_scratchStream = stream;
   int err = 0;
-  RQBuildParams P = {1.0f, 1.0f, 3, 0, 2, 8, 1, 512};
+  RQBuildParams P = {1.0f, 1.0f, 3, 0, 2, 8, 1, 256, 0};
   if (params) P = *params;
   if (P.maxLeafTris < 1) P.maxLeafTris = 1;
   if (P.maxLeafTris > 3) P.maxLeafTris = 3;
@@ -1390,15 +1440,14 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
           CK(cudaStreamSynchronize(stream));
           CK(cudaGetLastError());
           if (T == 0 || T > n) { err = (int)cudaErrorUnknown; goto fail; }
-          if (K == 512u) {
-            const size_t smem = 4 * sizeof(TreeletSmem<512>);
-            CK(cudaFuncSetAttribute(k_treelet_build<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_treelet_build<512><<<blocksFor(T, 4), 128, smem, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T, keys0.p);
-          } else {
-            const size_t smem = 4 * sizeof(TreeletSmem<256>);
-            CK(cudaFuncSetAttribute(k_treelet_build<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_treelet_build<256><<<blocksFor(T, 4), 128, smem, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T, keys0.p);
-          }
+#define RQ_TREELET_LAUNCH(KK, SW) do {                                                                                          \
+            const size_t smem = 4 * sizeof(TreeletSmem<KK, SW>);                                                                      \
+            CK(cudaFuncSetAttribute(k_treelet_build<KK, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+            k_treelet_build<KK, SW><<<blocksFor(T, 4), 128, smem, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T, keys0.p);              \
+          } while (0)
+          if (K == 512u) { if (P.sweepBottom) RQ_TREELET_LAUNCH(512, TL_SWEEP); else RQ_TREELET_LAUNCH(512, 0); }
+          else { if (P.sweepBottom) RQ_TREELET_LAUNCH(256, TL_SWEEP); else RQ_TREELET_LAUNCH(256, 0); }
+#undef RQ_TREELET_LAUNCH
           CK(cudaEventRecord(ev[3], stream));
           k_refit_dp<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costNode, P.costTri, P.maxLeafTris, 0);
           k_treelet_roots<<<blocksFor(T, 256), 256, 0, stream>>>((int)n, tlStart.p, sizeAt.p, T, cid0.p);
