@@ -61,8 +61,10 @@ __host__ __device__ __forceinline__ float halfArea(float dx, float dy, float dz)
   return dx * (dy + dz) + dy * dz;                            // common/math/vec3.h halfArea
 }
 
-struct Bounds12 {                                             // 12 ordered-uint slots in global memory
+struct Bounds12 {                                             // 12 ordered-uint slots in global memory (+ statistics for the pre-split)
   uint32_t sceneLo[3], sceneHi[3], centLo[3], centHi[3];
+  float    extSum;                                            // sum over valid primitives of the largest box extent
+  uint32_t numValid;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -147,14 +149,19 @@ k_setup_prims(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t N,
   // (one atomic set per WARP meant 312 K x 12 same-address L2 atomics for 10 M triangles: 0.6 ms of the phase)
   __shared__ float red[8][12];
   __shared__ unsigned redInvalid[8];
+  __shared__ float redExt[8];
+  __shared__ unsigned redValid[8];
   const unsigned nInvalid = __popc(__ballot_sync(0xffffffffu, (g < N) && !valid));
+  const unsigned nValid = __popc(__ballot_sync(0xffffffffu, valid));
+  float extMaxAxis = valid ? fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]) : 0.f;   // before the warp reductions overwrite lo / hi
+  for (int o = 16; o; o >>= 1) extMaxAxis += __shfl_xor_sync(0xffffffffu, extMaxAxis, o);
   for (int k = 0; k < 3; k++) {
     lo[k] = warpMin(lo[k]); hi[k] = warpMax(hi[k]); clo[k] = warpMin(clo[k]); chi[k] = warpMax(chi[k]);
   }
   const int warp = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
     for (int k = 0; k < 3; k++) { red[warp][k] = lo[k]; red[warp][3 + k] = hi[k]; red[warp][6 + k] = clo[k]; red[warp][9 + k] = chi[k]; }
-    redInvalid[warp] = nInvalid;
+    redInvalid[warp] = nInvalid; redExt[warp] = extMaxAxis; redValid[warp] = nValid;
   }
   __syncthreads();
   if (threadIdx.x < 12) {
@@ -170,6 +177,11 @@ k_setup_prims(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t N,
     unsigned tot = 0;
     for (int w = 0; w < 8; w++) tot += redInvalid[w];
     if (tot) atomicAdd(invalidCount, tot);
+  }
+  if (threadIdx.x == 13) {
+    float e = 0.f; unsigned v = 0;
+    for (int w = 0; w < 8; w++) { e += redExt[w]; v += redValid[w]; }
+    if (v) { atomicAdd(&bounds->extSum, e); atomicAdd(&bounds->numValid, v); }
   }
 }
 
@@ -191,6 +203,160 @@ k_copy_verts(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t totalV
 }
 
 // ----------------------------------------------------------------------------------------------
+// 1b. Pre-split of large triangles (RTC_BUILD_QUALITY_HIGH).  Reference: the spatial-split builders the reference selects at
+//     HIGH quality (BVHNBuilderFastSpatialSAH, kernels/bvh/bvh_builder_sah_spatial.cpp; primrefgen_presplit.h splits the
+//     primitives with the highest priority on a grid before the build; splitter.h TriangleSplitter clips a triangle at a plane).
+//     Here: a triangle whose box is more than PRESPLIT_FACTOR x longer than the average primitive box is cut along a uniform grid
+//     (cell = PRESPLIT_CELL x the average extent, doubled until the triangle spans at most 64 cells); each non-empty piece
+//     becomes its own primitive REFERENCE -- a copy of the 48-byte record plus the tight box of the clipped polygon -- so a
+//     long triangle no longer drags one huge box through the hierarchy.  The leaves then hold the triangle once per reference;
+//     a ray may test it twice, answers do not change.
+// ----------------------------------------------------------------------------------------------
+constexpr float PRESPLIT_FACTOR = 8.0f, PRESPLIT_CELL = 4.0f;
+constexpr int TLS_THREADS_PRE = 256;                          // tiles of 1024 values, like the treelet compaction (k_treelet_scan scans the tile sums)
+constexpr int PRESPLIT_MAX_CELLS = 64;
+
+// Sutherland-Hodgman against one axis-aligned half space (inclusive: a vertex on the plane belongs to both sides)
+__device__ int clipAxis(const float (*in)[3], int n, int axis, float pos, bool keepAbove, float (*out)[3]) {
+  int m = 0;
+  for (int i = 0; i < n; i++) {
+    const float* a = in[i]; const float* b = in[(i + 1) % n];
+    const bool ia = keepAbove ? a[axis] >= pos : a[axis] <= pos, ib = keepAbove ? b[axis] >= pos : b[axis] <= pos;
+    if (ia) { out[m][0] = a[0]; out[m][1] = a[1]; out[m][2] = a[2]; m++; }
+    if (ia != ib) {
+      const float tpar = (pos - a[axis]) / (b[axis] - a[axis]);
+      for (int c = 0; c < 3; c++) out[m][c] = c == axis ? pos : a[c] + tpar * (b[c] - a[c]);
+      m++;
+    }
+  }
+  return m;
+}
+
+// Calls emit(lo, hi) for every non-empty piece of the triangle; returns the number of pieces (>= 1).
+template <typename Emit>
+__device__ int presplitTriangle(const float v[3][3], const float sceneLo[3], float avgExt, Emit emit) {
+  float lo[3], hi[3];
+  for (int c = 0; c < 3; c++) { lo[c] = fminf(fminf(v[0][c], v[1][c]), v[2][c]); hi[c] = fmaxf(fmaxf(v[0][c], v[1][c]), v[2][c]); }
+  const float emax = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+  if (!(avgExt > 0.f) || !(emax > PRESPLIT_FACTOR * avgExt)) { emit(lo, hi); return 1; }
+  float L = PRESPLIT_CELL * avgExt;
+  int i0[3], i1[3];
+  for (;;) {
+    long long cells = 1;
+    for (int c = 0; c < 3; c++) {
+      i0[c] = (int)floorf((lo[c] - sceneLo[c]) / L); i1[c] = (int)floorf((hi[c] - sceneLo[c]) / L);
+      cells *= (long long)(i1[c] - i0[c] + 1);
+    }
+    if (cells <= PRESPLIT_MAX_CELLS) break;
+    L *= 2.0f;
+  }
+  int pieces = 0;
+  float P0[10][3], P1[10][3];
+  for (int iz = i0[2]; iz <= i1[2]; iz++) for (int iy = i0[1]; iy <= i1[1]; iy++) for (int ix = i0[0]; ix <= i1[0]; ix++) {
+    const int ic[3] = {ix, iy, iz};
+    float cl[3], ch[3];
+    for (int c = 0; c < 3; c++) { cl[c] = sceneLo[c] + (float)ic[c] * L; ch[c] = sceneLo[c] + (float)(ic[c] + 1) * L; }
+    int n = 3;
+    for (int k = 0; k < 3; k++) for (int c = 0; c < 3; c++) P0[k][c] = v[k][c];
+    for (int c = 0; c < 3 && n > 0; c++) {
+      n = clipAxis(P0, n, c, cl[c], true, P1);
+      if (n > 0) n = clipAxis(P1, n, c, ch[c], false, P0);
+    }
+    if (n <= 0) continue;
+    float plo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, phi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int k = 0; k < n; k++) for (int c = 0; c < 3; c++) { plo[c] = fminf(plo[c], P0[k][c]); phi[c] = fmaxf(phi[c], P0[k][c]); }
+    // conservative: pad by more than the rounding of the clip arithmetic, never beyond the triangle's own box
+    for (int c = 0; c < 3; c++) {
+      const float d = 2e-6f * (fabsf(plo[c]) + fabsf(phi[c]) + (hi[c] - lo[c]));
+      plo[c] = fmaxf(plo[c] - d, lo[c]); phi[c] = fminf(phi[c] + d, hi[c]);
+    }
+    emit(plo, phi);
+    pieces++;
+  }
+  if (pieces == 0) { emit(lo, hi); pieces = 1; }                  // cannot happen (every vertex lies in a visited cell); keep the triangle anyway
+  return pieces;
+}
+
+__device__ __forceinline__ bool loadTriForSplit(const RQTri* __restrict__ trisIn, uint32_t g, float v[3][3]) {
+  const float4* src = (const float4*)(trisIn + g);
+  const float4 a = src[0], b = src[1], c = src[2];
+  v[0][0] = a.x; v[0][1] = a.y; v[0][2] = a.z; v[1][0] = a.w; v[1][1] = b.x; v[1][2] = b.y; v[2][0] = b.z; v[2][1] = b.w; v[2][2] = c.x;
+  const uint32_t pad = __float_as_uint(c.w);
+  return pad != RQ_PAD_INVALID && !(pad & RQ_PAD_INSTANCE);      // invalid primitives and instances are never split
+}
+
+__global__ void __launch_bounds__(256)
+k_presplit_count(const RQTri* __restrict__ trisIn, uint32_t N, const Bounds12* __restrict__ bounds, uint32_t* __restrict__ pieces) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  float v[3][3];
+  uint32_t cnt = 1u;
+  if (loadTriForSplit(trisIn, g, v)) {
+    const float sceneLo[3] = {ord2f(bounds->sceneLo[0]), ord2f(bounds->sceneLo[1]), ord2f(bounds->sceneLo[2])};
+    const float avg = bounds->numValid ? bounds->extSum / (float)bounds->numValid : 0.f;
+    cnt = (uint32_t)presplitTriangle(v, sceneLo, avg, [](const float*, const float*) {});
+  }
+  pieces[g] = cnt;
+}
+
+// exclusive scan of `pieces` in tiles of TLS_TILE values: tile sums here, k_treelet_scan over the sums, offsets applied in k_presplit_write
+__global__ void __launch_bounds__(TLS_THREADS_PRE)
+k_tile_sums(const uint32_t* __restrict__ vals, uint32_t n, uint32_t* __restrict__ tileSum) {
+  __shared__ uint32_t wsum[TLS_THREADS_PRE / 32];
+  const uint32_t base = blockIdx.x * (TLS_THREADS_PRE * 4) + threadIdx.x * 4;
+  uint32_t c = 0;
+  #pragma unroll
+  for (int i = 0; i < 4; i++) if (base + i < n) c += vals[base + i];
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < TLS_THREADS_PRE / 32; w++) t += wsum[w]; tileSum[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(TLS_THREADS_PRE)
+k_presplit_write(const RQTri* __restrict__ trisIn, uint32_t N, const Bounds12* __restrict__ bounds, const uint32_t* __restrict__ pieces,
+                 const uint32_t* __restrict__ tileOffset, RQTri* __restrict__ trisOut, float4* __restrict__ refLo, float4* __restrict__ refHi,
+                 const uint32_t* __restrict__ idxIn, uint32_t* __restrict__ idxOut) {
+  __shared__ uint32_t wsum[TLS_THREADS_PRE / 32];
+  const uint32_t base = blockIdx.x * (TLS_THREADS_PRE * 4) + threadIdx.x * 4;
+  uint32_t c = 0;
+  #pragma unroll
+  for (int i = 0; i < 4; i++) if (base + i < N) c += pieces[base + i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = c;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  uint32_t off = tileOffset[blockIdx.x] + incl - c;
+  for (int w = 0; w < warp; w++) off += wsum[w];
+  const float sceneLo[3] = {ord2f(bounds->sceneLo[0]), ord2f(bounds->sceneLo[1]), ord2f(bounds->sceneLo[2])};
+  const float avg = bounds->numValid ? bounds->extSum / (float)bounds->numValid : 0.f;
+  for (int i = 0; i < 4; i++) {
+    const uint32_t g = base + i;
+    if (g >= N) break;
+    const float4* src = (const float4*)(trisIn + g);
+    const float4 a = src[0], b = src[1], cc = src[2];
+    float v[3][3];
+    const bool splittable = loadTriForSplit(trisIn, g, v);
+    uint32_t o = off;
+    auto put = [&](const float* lo, const float* hi) {
+      float4* dst = (float4*)(trisOut + o);
+      dst[0] = a; dst[1] = b; dst[2] = cc;
+      refLo[o] = make_float4(lo[0], lo[1], lo[2], 0.f); refHi[o] = make_float4(hi[0], hi[1], hi[2], 0.f);
+      if (idxOut) { idxOut[3 * (size_t)o] = idxIn[3 * (size_t)g]; idxOut[3 * (size_t)o + 1] = idxIn[3 * (size_t)g + 1]; idxOut[3 * (size_t)o + 2] = idxIn[3 * (size_t)g + 2]; }
+      o++;
+    };
+    if (splittable) presplitTriangle(v, sceneLo, avg, put);
+    else {                                                        // kept as it is: its box is what its three "vertices" span (instances: lower / upper corner)
+      float lo[3], hi[3];
+      for (int k = 0; k < 3; k++) { lo[k] = fminf(fminf(v[0][k], v[1][k]), v[2][k]); hi[k] = fmaxf(fmaxf(v[0][k], v[1][k]), v[2][k]); }
+      put(lo, hi);
+    }
+    off += pieces[g];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // 2. Morton codes
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t expand21(uint32_t v) {    // spread 21 bits to every third bit
@@ -205,7 +371,8 @@ __device__ __forceinline__ uint64_t expand21(uint32_t v) {    // spread 21 bits 
 
 __global__ void __launch_bounds__(256)
 k_morton(const RQTri* __restrict__ trisIn, uint32_t N, const Bounds12* __restrict__ bounds,
-         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int cubic, uint64_t keyMask) {
+         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int cubic, uint64_t keyMask,
+         const float4* __restrict__ refLo, const float4* __restrict__ refHi /* pre-split references: their own boxes (codes then span the SCENE bounds), else NULL */) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= N) return;
   const float4* src = (const float4*)(trisIn + g);
@@ -218,11 +385,14 @@ k_morton(const RQTri* __restrict__ trisIn, uint32_t N, const Bounds12* __restric
     // scene gets cells that are as flat as the scene, and the bits of the short axis split neighbouring triangles by height
     // before the long axes have separated them (noisy terrain: 10 M-triangle scene, SAH 28.9 per-axis vs cubic).
     float extMax = 0.f;
-    for (int k = 0; k < 3; k++) extMax = fmaxf(extMax, ord2f(bounds->centHi[k]) - ord2f(bounds->centLo[k]));
+    const uint32_t* bLo = refLo ? bounds->sceneLo : bounds->centLo;   // centres of clipped references can leave the centroid bounds of the whole triangles
+    const uint32_t* bHi = refLo ? bounds->sceneHi : bounds->centHi;
+    for (int k = 0; k < 3; k++) extMax = fmaxf(extMax, ord2f(bHi[k]) - ord2f(bLo[k]));
     for (int k = 0; k < 3; k++) {
-      const float lo = fminf(fminf(v0[k], v1[k]), v2[k]), hi = fmaxf(fmaxf(v0[k], v1[k]), v2[k]);
+      float lo = fminf(fminf(v0[k], v1[k]), v2[k]), hi = fmaxf(fmaxf(v0[k], v1[k]), v2[k]);
+      if (refLo) { lo = k == 0 ? refLo[g].x : k == 1 ? refLo[g].y : refLo[g].z; hi = k == 0 ? refHi[g].x : k == 1 ? refHi[g].y : refHi[g].z; }
       const float cen = 0.5f * lo + 0.5f * hi;
-      const float cl = ord2f(bounds->centLo[k]), ch = ord2f(bounds->centHi[k]);
+      const float cl = ord2f(bLo[k]), ch = ord2f(bHi[k]);
       const float ext = cubic ? extMax : ch - cl;
       float x = ext > 0.f ? (cen - cl) / ext : 0.f;
       x = fminf(fmaxf(x, 0.f), 1.f);
@@ -407,14 +577,17 @@ struct B2 {                    // binary-tree arrays (2n-1 nodes unless noted)
   uint32_t* parent;            // 2n-1
   uint32_t* rangeFirst;        // n-1
   uint32_t* flag;              // n-1 arrival counters
+  const float4* refLo;         // pre-split (RTC_BUILD_QUALITY_HIGH): box of primitive reference i, indexed like trisIn; NULL otherwise
+  const float4* refHi;
 };
 
 // Leaf k of the binary tree (node id n-1+k): bounds of its triangle and the trivial collapse programme.
 __device__ __forceinline__ void initLeaf(const B2& t, uint32_t node, const RQTri* __restrict__ trisIn, uint32_t tri, float costTri) {
   const float4* src = (const float4*)(trisIn + tri);
   const float4 a = src[0], b = src[1], c = src[2];
-  const float lx = fminf(fminf(a.x, a.w), b.z), ly = fminf(fminf(a.y, b.x), b.w), lz = fminf(fminf(a.z, b.y), c.x);
-  const float hx = fmaxf(fmaxf(a.x, a.w), b.z), hy = fmaxf(fmaxf(a.y, b.x), b.w), hz = fmaxf(fmaxf(a.z, b.y), c.x);
+  float lx = fminf(fminf(a.x, a.w), b.z), ly = fminf(fminf(a.y, b.x), b.w), lz = fminf(fminf(a.z, b.y), c.x);
+  float hx = fmaxf(fmaxf(a.x, a.w), b.z), hy = fmaxf(fmaxf(a.y, b.x), b.w), hz = fmaxf(fmaxf(a.z, b.y), c.x);
+  if (t.refLo) { const float4 rl = t.refLo[tri], rh = t.refHi[tri]; lx = rl.x; ly = rl.y; lz = rl.z; hx = rh.x; hy = rh.y; hz = rh.z; }
   const float A = halfArea(hx - lx, hy - ly, hz - lz);
   t.lo[node] = make_float4(lx, ly, lz, A);
   t.hi[node] = make_float4(hx, hy, hz, __uint_as_float(1u));
@@ -1297,6 +1470,7 @@ struct DevBuf {
     return e;
   }
   ~DevBuf() { if (p) { cudaFreeAsync(p, s); monitorFree(bytes); } }
+  void swap(DevBuf& o) { std::swap(p, o.p); std::swap(s, o.s); std::swap(bytes, o.bytes); }
 };
 
 inline unsigned blocksFor(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
@@ -1323,7 +1497,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   ScratchScope scratch(stream);
   t_scratchStream = stream;
   int err = 0;
-  RQBuildParams P = {1.0f, 1.0f, 3, 0, 2, 8, 1, 256, 0};
+  RQBuildParams P = {1.0f, 1.0f, 3, 0, 2, 8, 1, 256, 0, 0};
   if (params) P = *params;
   if (P.maxLeafTris < 1) P.maxLeafTris = 1;
   if (P.maxLeafTris > 3) P.maxLeafTris = 3;
@@ -1337,7 +1511,8 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     if (g.type == 1u) hasInstances = true; else totalVerts += g.numVerts;
   }
   if (total >= 0x7FFFFFF0ull || totalVerts >= 0xFFFFFFF0ull) return (int)cudaErrorInvalidValue;
-  const uint32_t N = (uint32_t)total;
+  uint32_t N = (uint32_t)total;                                 // primitive references (grows when large triangles are pre-split)
+  const uint32_t Nin = N;
   // RTC_SCENE_FLAG_COMPACT (= 2): indexed leaves + a vertex pool inside the image.  Instance primitives have no room in a
   // 16-byte record, so a scene with instances keeps the 48-byte layout (the flag is a memory hint, as in the reference).
   const bool compact = (sceneFlags & 2u) != 0u && !hasInstances;
@@ -1351,6 +1526,8 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   DevBuf<float4> blo, bhi; DevBuf<float> cost; DevBuf<uint2> queue0, queue1; DevBuf<RQNode> nodes;
   DevBuf<Bounds12> dBounds; DevBuf<uint32_t> dInvalid; DevBuf<EmitCounters> dCtr;
   DevBuf<uint32_t> idx3, metaOut; DevBuf<RQTriC> trisC; DevBuf<float4> vpool;
+  DevBuf<uint32_t> pieces, tileSum, preTotal, idxSplit; DevBuf<RQTri> trisSplit; DevBuf<float4> refLo, refHi;
+  bool useRefBoxes = false; uint32_t numSplitRefs = 0;
   Bounds12 hb; uint32_t hInvalid = 0; EmitCounters hc;
   uint32_t n = 0, depth = 0, numNodes = 1, numTris = 0;
   std::vector<uint32_t> levelEnd(1, 1u);                        // level 0 = the root = node range [0,1)
@@ -1363,19 +1540,50 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   CK(cudaEventRecord(ev[0], stream));
   CK(dBounds.alloc(1)); CK(dInvalid.alloc(1)); CK(dCtr.alloc(1));
   for (int k = 0; k < 3; k++) { hb.sceneLo[k] = hb.centLo[k] = 0xFFFFFFFFu; hb.sceneHi[k] = hb.centHi[k] = 0u; }
+  hb.extSum = 0.f; hb.numValid = 0u;
   CK(cudaMemcpyAsync(dBounds.p, &hb, sizeof(hb), cudaMemcpyHostToDevice, stream));
   CK(cudaMemsetAsync(dInvalid.p, 0, 4, stream));
 
   if (N > 0) {
     CK(dGeoms.alloc(numGeoms));
     CK(cudaMemcpyAsync(dGeoms.p, hg.data(), sizeof(RQGeomDesc) * numGeoms, cudaMemcpyHostToDevice, stream));
-    CK(trisIn.alloc(N)); CK(keys0.alloc(N)); CK(keys1.alloc(N)); CK(vals0.alloc(N)); CK(vals1.alloc(N));
+    CK(trisIn.alloc(N));
     if (compact) CK(idx3.alloc(3 * (size_t)N));
     k_setup_prims<<<blocksFor(N, 256), 256, 0, stream>>>(dGeoms.p, numGeoms, N, trisIn.p, dBounds.p, dInvalid.p, compact ? idx3.p : nullptr);
+    if (P.presplit) {
+      // ---- RTC_BUILD_QUALITY_HIGH: large triangles become several references with clipped boxes (section 1b) ----
+      const uint32_t tiles = blocksFor(N, TLS_THREADS_PRE * 4);
+      CK(pieces.alloc(N)); CK(tileSum.alloc(tiles + 1)); CK(preTotal.alloc(1));
+      k_presplit_count<<<blocksFor(N, 256), 256, 0, stream>>>(trisIn.p, N, dBounds.p, pieces.p);
+      k_tile_sums<<<tiles, TLS_THREADS_PRE, 0, stream>>>(pieces.p, N, tileSum.p);
+      k_treelet_scan<<<1, 1024, 0, stream>>>(tileSum.p, tiles, preTotal.p);
+      rqCountLaunch(3);
+      uint32_t N2 = 0;
+      CK(cudaMemcpyAsync(&N2, preTotal.p, 4, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaGetLastError());
+      if (N2 < N || (uint64_t)N2 >= 0x7FFFFFF0ull) { err = (int)cudaErrorUnknown; goto fail; }
+      CK(refLo.alloc(N2)); CK(refHi.alloc(N2));
+      if (N2 > N) {
+        CK(trisSplit.alloc(N2));
+        if (compact) CK(idxSplit.alloc(3 * (size_t)N2));
+        k_presplit_write<<<tiles, TLS_THREADS_PRE, 0, stream>>>(trisIn.p, N, dBounds.p, pieces.p, tileSum.p, trisSplit.p, refLo.p, refHi.p,
+                                                                compact ? idx3.p : nullptr, compact ? idxSplit.p : nullptr);
+        rqCountLaunch(1);
+        CK(cudaGetLastError());
+        trisIn.swap(trisSplit);
+        if (compact) idx3.swap(idxSplit);
+        numSplitRefs = N2 - N;
+        N = N2;
+        useRefBoxes = true;
+      }
+    }
+    CK(keys0.alloc(N)); CK(keys1.alloc(N)); CK(vals0.alloc(N)); CK(vals1.alloc(N));
     // The treelet builder only needs the Morton order down to cells of a few hundred triangles (everything below is rebuilt by SAH):
     // it sorts on the upper 32 bits of the code (10-11 bits per axis), i.e. half the radix passes; ties keep input order.
     k_morton<<<blocksFor(N, 256), 256, 0, stream>>>(trisIn.p, N, dBounds.p, keys0.p, vals0.p, P.mortonCubic,
-                                                    P.builder == 2 ? 0xFFFFFFFF00000000ull : ~0ull);
+                                                    P.builder == 2 ? 0xFFFFFFFF00000000ull : ~0ull,
+                                                    useRefBoxes ? refLo.p : nullptr, useRefBoxes ? refHi.p : nullptr);
     rqCountLaunch(2);
     CK(cudaGetLastError());
   }
@@ -1414,6 +1622,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       CK(queue0.alloc(n)); CK(queue1.alloc(n)); CK(qParent0.alloc(n)); CK(qParent1.alloc(n));
       t.lo = blo.p; t.hi = bhi.p; t.cost = cost.p; t.dec = dec.p; t.left = left.p; t.right = right.p;
       t.parent = parent.p; t.rangeFirst = rangeFirst.p; t.flag = flag.p;
+      t.refLo = useRefBoxes ? refLo.p : nullptr; t.refHi = useRefBoxes ? refHi.p : nullptr;
       CK(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t) * n, stream));
       CK(cudaMemsetAsync(parent.p, 0xFF, sizeof(uint32_t) * n2, stream));
       if ((P.builder == 1 || P.builder == 2) && n > 1) {
@@ -1573,7 +1782,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     CK(cudaStreamSynchronize(stream));
     if (stats) {
       memset(stats, 0, sizeof(*stats));
-      stats->numPrimsIn = N; stats->numPrimsValid = n; stats->numNodes = numNodes; stats->numTris = numTris;
+      stats->numPrimsIn = Nin; stats->numPrimsValid = n; stats->numSplitRefs = numSplitRefs; stats->numNodes = numNodes; stats->numTris = numTris;
       stats->depth = depth; stats->numLeaves = hc.leafSlots; stats->sah = H.sah;
       stats->sahExact = rootA > 0 ? (hc.sahInnerX + hc.sahLeafX) / rootA : 0.0;
       stats->sahInner = rootA > 0 ? hc.sahInnerQ / rootA : 0.0;

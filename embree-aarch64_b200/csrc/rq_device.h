@@ -17,6 +17,7 @@ struct RQBuildParams {
   int   plocRadius;      // PLOC search radius in Morton-order positions, 1..32          (default 8)
   int   mortonCubic;     // 1 = Morton cells are cubes (one scale for all axes), 0 = per-axis normalisation
   int   treeletSize;     // builder 2: largest treelet, 256 or 512 triangles
+  int   presplit;        // 1 = large triangles are pre-split into several references with clipped boxes (RTC_BUILD_QUALITY_HIGH)
   int   sweepBottom;     // builder 2: 1 = exact sweep SAH for nodes of <= 16 triangles (slow, best leaves: RTC_BUILD_QUALITY_HIGH), 0 = radix rule
 };
 

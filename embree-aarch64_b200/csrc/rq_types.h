@@ -145,6 +145,8 @@ struct RQBuildStats {
   double   sahLeafTris;       // leaf term weighted by triangles: sum A(leaf slot) * numTris / A(root)
   uint32_t numTreelets;       // binned-SAH treelets of the last full build (0 for the other front ends)
   float    msBroadcast;       // gpus=N: wall time of replicating the image to the peer GPUs after the last commit
+  uint32_t numSplitRefs;      // extra primitive references created by the pre-split of large triangles (RTC_BUILD_QUALITY_HIGH)
+  uint32_t pad;
 };
 
 // Per-call traversal counters (instrumented kernel variant only).

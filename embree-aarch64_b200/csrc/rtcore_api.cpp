@@ -85,7 +85,7 @@ struct Device : RefCounted {
   bool hasGpu = false;
   int verbose = 0, benchmark = 0, async = 0;
   size_t chunkRays = 1u << 20;
-  RQBuildParams build{1.0f, 1.0f, 3, 0, 2, 8, 1, 256, 0};   // binned-SAH treelets + PLOC above them by default (gpu_builder=sah); see DESIGN.md 4.1 for the A/B against PLOC / radix tree
+  RQBuildParams build{1.0f, 1.0f, 3, 0, 2, 8, 1, 256, 0, 0};   // binned-SAH treelets + PLOC above them by default (gpu_builder=sah); see DESIGN.md 4.1 for the A/B against PLOC / radix tree
   cudaStream_t ownStream = nullptr, userStream = nullptr;
   std::mutex errMutex;
   RTCError error = RTC_ERROR_NONE;
@@ -251,6 +251,7 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "morton_cubic") d->build.mortonCubic = atoi(v.c_str()) != 0;
     else if (k == "treelet") d->build.treeletSize = atoi(v.c_str()) >= 512 ? 512 : 256;
     else if (k == "sweep_bottom") d->build.sweepBottom = atoi(v.c_str()) != 0;
+    else if (k == "presplit") d->build.presplit = atoi(v.c_str()) != 0;
     else if (k == "ploc_radius") d->build.plocRadius = atoi(v.c_str());
     else if (k == "split_closest") d->splitClosest = atoi(v.c_str());
     else if (k == "stack_smem") d->stackSmem = std::max(0, std::min(16, atoi(v.c_str())));
@@ -573,7 +574,7 @@ void commitScene(Scene* sc) {
     // spatial splits here, which this builder does not do)
     if (!insts.empty()) bp.maxLeafTris = 1;                  // every instance gets its own child box: entering one costs a ray transform + a root fetch
     if (sc->quality == RTC_BUILD_QUALITY_LOW) bp.builder = 0;
-    else if (sc->quality == RTC_BUILD_QUALITY_HIGH) { bp.plocRadius = std::max(bp.plocRadius, 16); bp.treeletSize = 512; bp.sweepBottom = 1; if (bp.builder == 0) bp.builder = 2; }
+    else if (sc->quality == RTC_BUILD_QUALITY_HIGH) { bp.plocRadius = std::max(bp.plocRadius, 16); bp.treeletSize = 512; bp.sweepBottom = 1; bp.presplit = 1; if (bp.builder == 0) bp.builder = 2; }
     cudaCheck(rqBuildBVH(descs.data(), (int)descs.size(), (uint32_t)sc->flags, &bp, (rqStream)s, &img, &st), "BVH build");
     if (sc->image.base) { if (sc->accounted) freeImage(dev, &sc->image); else rqFreeImage(&sc->image); }
     sc->image = img; sc->stats = st; sc->accounted = true;

@@ -65,7 +65,7 @@ class BuildStats(C.Structure):
                 ("msTotal", C.c_float), ("msPrims", C.c_float), ("msSort", C.c_float),
                 ("msHierarchy", C.c_float), ("msRefit", C.c_float), ("msEmit", C.c_float),
                 ("bytes", C.c_ulonglong), ("builderIterations", C.c_uint), ("refitCount", C.c_uint),
-                ("sahInner", C.c_double), ("sahLeafTris", C.c_double), ("numTreelets", C.c_uint), ("msBroadcast", C.c_float)]
+                ("sahInner", C.c_double), ("sahLeafTris", C.c_double), ("numTreelets", C.c_uint), ("msBroadcast", C.c_float), ("numSplitRefs", C.c_uint), ("pad", C.c_uint)]
 
 
 class TraceCounters(C.Structure):

@@ -32,6 +32,9 @@ struct RTCXBuildStats {
                                    sahInner + sahLeafTris / 4 is the figure to hold against the reference's blocks of four */
   unsigned int numTreelets;     /* binned-SAH treelets of the last full build (gpu_builder=sah), 0 for the other front ends */
   float msBroadcast;            /* device option gpus=N: wall time of the NVLink replication of the image to the peer GPUs */
+  unsigned int numSplitRefs;    /* RTC_BUILD_QUALITY_HIGH: extra primitive references created by pre-splitting large triangles
+                                   (numTris = numPrimsValid + numSplitRefs: a split triangle is stored once per reference) */
+  unsigned int pad;
 };
 
 struct RTCXTraceCounters {

@@ -82,9 +82,11 @@ class Image:
             return 0.0, 0.0, 0.0, 0.0
         return (inner + leaf) / root, inner / root, leaf / root, leaf_tris / root
 
-    def check_structure(self, expect_prims=None):
+    def check_structure(self, expect_prims=None, presplit=False):
         """Structural invariants of a usable tree; raises AssertionError with the first violation.
-        expect_prims: optional set-like array of (geomID << 32 | primID | flip bit) keys that must appear exactly once."""
+        expect_prims: optional set-like array of (geomID << 33 | primID << 1 | flip bit) keys that must appear exactly once.
+        presplit=True (RTC_BUILD_QUALITY_HIGH): a triangle may be stored once per clipped reference, so a leaf box need only
+        overlap its triangle and the primitive set is compared without multiplicity."""
         N, S = self.nodes, self.slots()
         n, t = len(N), len(self.tri_words)
         ni = S["inner"].sum(1)
@@ -127,10 +129,15 @@ class Image:
                 mj = S["ntri"][m, k] > j
                 ti = first[mj] + j
                 sel = np.where(m)[0][mj]
-                assert (S["lo"][sel, :, k] <= tl[ti]).all() and (S["hi"][sel, :, k] >= th[ti]).all(), "leaf triangle not contained"
+                if presplit:
+                    assert (S["lo"][sel, :, k] <= th[ti]).all() and (S["hi"][sel, :, k] >= tl[ti]).all(), "leaf box does not touch its triangle"
+                else:
+                    assert (S["lo"][sel, :, k] <= tl[ti]).all() and (S["hi"][sel, :, k] >= th[ti]).all(), "leaf triangle not contained"
         if expect_prims is not None:
             keys = (self.geomID.astype(np.uint64) << np.uint64(33)) | (self.primID.astype(np.uint64) << np.uint64(1)) | \
                    ((self.pad >> 30) & 1).astype(np.uint64)
+            if presplit:
+                keys = np.unique(keys)
             assert np.array_equal(np.sort(keys), np.sort(np.asarray(expect_prims, dtype=np.uint64))), "primitive set"
         return True
 
