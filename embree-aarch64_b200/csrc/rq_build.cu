@@ -206,13 +206,14 @@ k_copy_verts(const RQGeomDesc* __restrict__ geoms, int numGeoms, uint32_t totalV
 // 1b. Pre-split of large triangles (RTC_BUILD_QUALITY_HIGH).  Reference: the spatial-split builders the reference selects at
 //     HIGH quality (BVHNBuilderFastSpatialSAH, kernels/bvh/bvh_builder_sah_spatial.cpp; primrefgen_presplit.h splits the
 //     primitives with the highest priority on a grid before the build; splitter.h TriangleSplitter clips a triangle at a plane).
-//     Here: a triangle whose box is more than PRESPLIT_FACTOR x longer than the average primitive box is cut along a uniform grid
+//     Here: a triangle whose box is more than PRESPLIT_FACTOR x longer than the average primitive box AND leaves more than
+//     PRESPLIT_EMPTY of that box's surface empty (the reference's priority: area(box) - projected triangle area) is cut along a uniform grid
 //     (cell = PRESPLIT_CELL x the average extent, doubled until the triangle spans at most 64 cells); each non-empty piece
 //     becomes its own primitive REFERENCE -- a copy of the 48-byte record plus the tight box of the clipped polygon -- so a
 //     long triangle no longer drags one huge box through the hierarchy.  The leaves then hold the triangle once per reference;
 //     a ray may test it twice, answers do not change.
 // ----------------------------------------------------------------------------------------------
-constexpr float PRESPLIT_FACTOR = 8.0f, PRESPLIT_CELL = 4.0f;
+constexpr float PRESPLIT_FACTOR = 8.0f, PRESPLIT_CELL = 4.0f, PRESPLIT_EMPTY = 0.6f;
 constexpr int TLS_THREADS_PRE = 256;                          // tiles of 1024 values, like the treelet compaction (k_treelet_scan scans the tile sums)
 constexpr int PRESPLIT_MAX_CELLS = 64;
 
@@ -239,6 +240,16 @@ __device__ int presplitTriangle(const float v[3][3], const float sceneLo[3], flo
   for (int c = 0; c < 3; c++) { lo[c] = fminf(fminf(v[0][c], v[1][c]), v[2][c]); hi[c] = fmaxf(fmaxf(v[0][c], v[1][c]), v[2][c]); }
   const float emax = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
   if (!(avgExt > 0.f) || !(emax > PRESPLIT_FACTOR * avgExt)) { emit(lo, hi); return 1; }
+  {
+    // The reference's split priority (primrefgen_presplit.h:45-56): how much of the box's surface the triangle does NOT account
+    // for, area(box) - projected primitive area (priminfo.h:13-19: |d.x| + |d.y| + |d.z|, d = cross of two edges).  An axis-aligned
+    // floor triangle fills half of its box's surface and gains nothing from being cut; a diagonal sliver leaves almost all of it empty.
+    const float e0[3] = {v[1][0] - v[0][0], v[1][1] - v[0][1], v[1][2] - v[0][2]}, e1[3] = {v[2][0] - v[0][0], v[2][1] - v[0][1], v[2][2] - v[0][2]};
+    const float areaPrim = fabsf(e0[1] * e1[2] - e0[2] * e1[1]) + fabsf(e0[2] * e1[0] - e0[0] * e1[2]) + fabsf(e0[0] * e1[1] - e0[1] * e1[0]);
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    const float areaBox = 2.0f * (dx * dy + dy * dz + dz * dx);
+    if (!(areaBox - areaPrim > PRESPLIT_EMPTY * areaBox)) { emit(lo, hi); return 1; }
+  }
   float L = PRESPLIT_CELL * avgExt;
   int i0[3], i1[3];
   for (;;) {

@@ -16,9 +16,15 @@ INV = 0xFFFFFFFF
 def _scene_with_long_triangles():
     plane = fx.displaced_plane(96, extent=4.0)                                  # ~18 K triangles of ~0.08 units
     floor_v = np.array([[-30, -1, -30], [30, -1, -30], [30, -1, 30], [-30, -1, 30]], dtype=np.float32)
-    floor_t = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.uint32)                 # two 60-unit triangles under everything
-    sl_v = np.array([[-4, 1.2, -4], [4, 1.25, 4], [4, 1.2, 3.9], [-4, 1.6, 4], [4, 1.65, -4], [3.9, 1.6, -4]], dtype=np.float32)
-    sl_t = np.array([[0, 1, 2], [3, 4, 5]], dtype=np.uint32)                    # two thin slivers crossing the scene diagonally
+    floor_t = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.uint32)                 # two 60-unit axis-aligned triangles: large, but they fill their boxes
+    # 240 long thin slivers crossing the terrain's volume in all diagonal directions: their boxes cover large parts of the scene
+    rs = fx.RandomSampler(np.arange(240), 23)
+    c = np.stack([rs.get_float() * 6 - 3, rs.get_float() * 1.2 - 0.4, rs.get_float() * 6 - 3], 1).astype(np.float32)
+    d = np.stack([rs.get_float() * 2 - 1, rs.get_float() * 0.8 - 0.4, rs.get_float() * 2 - 1], 1).astype(np.float32)
+    d = d / np.linalg.norm(d, axis=1, keepdims=True) * (2.0 + 2.0 * rs.get_float()[:, None])
+    w = np.stack([rs.get_float() - 0.5, rs.get_float() - 0.5, rs.get_float() - 0.5], 1).astype(np.float32) * 0.04
+    sl_v = np.stack([c - d, c + d, c + d + w], 1).reshape(-1, 3).astype(np.float32)
+    sl_t = np.arange(3 * 240, dtype=np.uint32).reshape(-1, 3)
     return [plane, (floor_v, floor_t), (sl_v, sl_t)]
 
 
@@ -44,8 +50,8 @@ def test_presplit_keeps_answers_and_tightens_the_tree(product, oracle):
     s0, s1 = product.build_stats(med), product.build_stats(high)
     ntris = fx.num_tris(meshes)
     assert s0["numSplitRefs"] == 0 and s0["numTris"] == ntris
-    assert s1["numSplitRefs"] >= 8 and s1["numTris"] == ntris + s1["numSplitRefs"]        # the four long triangles became many references
-    assert s1["numSplitRefs"] <= 4 * 64
+    assert s1["numSplitRefs"] >= 240 and s1["numTris"] == ntris + s1["numSplitRefs"]      # the slivers became many references ...
+    assert s1["numSplitRefs"] <= 240 * 63                                                     # ... the axis-aligned floor triangles did not
     img = rq_image.fetch(product, high)
     keys = np.concatenate([(np.uint64(g) << np.uint64(33)) | (np.arange(len(t), dtype=np.uint64) << np.uint64(1)) for g, (v, t) in enumerate(meshes)])
     assert img.check_structure(keys, presplit=True)
@@ -66,7 +72,7 @@ def test_presplit_keeps_answers_and_tightens_the_tree(product, oracle):
     assert parity.compare_closest(a, w)["pass"]
     res = parity.compare_closest(b, w)
     assert res["pass"], res
-    assert (b["geomID"] == 1).sum() > 1000 and (b["geomID"] == 2).sum() > 10            # floor and slivers are hit
+    assert (b["geomID"] == 1).sum() > 1000 and (b["geomID"] == 2).sum() > 100           # floor and slivers are hit
     sa, sb = fx.to_ray(rays), fx.to_ray(rays)
     product.occluded(med, sa); product.occluded(high, sb)
     assert parity.compare_occluded(sb, sa)["disagree"] == 0
