@@ -177,7 +177,9 @@ class CpuDriver:
         return t
 
 
-def reference_setup(fx, rt, workload, seeds):
+def reference_setup(fx, rt, workload, seeds, streams=None):
+    """streams: (diffuse, shadow) to reuse instead of generating them with the reference library (the cpu_baseline leg of our
+    arm hands over the seed-0 streams it already has; the reference arm proper generates its own)."""
     if not os.path.exists(REF_LIB):
         return None
     ref = rt.RTCore(REF_LIB)
@@ -187,7 +189,7 @@ def reference_setup(fx, rt, workload, seeds):
     t0 = time.perf_counter()
     sc, keep = ref.build_scene(dev, meshes)
     build_s = time.perf_counter() - t0
-    diffuse, shadow = make_streams(fx, lambda r: drv.trace(sc, r, coherent=True), (0, FRAME), seeds)
+    diffuse, shadow = streams if streams is not None else make_streams(fx, lambda r: drv.trace(sc, r, coherent=True), (0, FRAME), seeds)
     return dict(ref=ref, drv=drv, dev=dev, sc=sc, keep=keep, cores=drv.cores, diffuse=diffuse, shadow=shadow, build_s=build_s, tris=fx.num_tris(meshes))
 
 
@@ -464,7 +466,7 @@ def run_ours(args):
                            "host_equals_device_result": e2e["same"]}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                S = reference_setup(fx, rt, args.workload, 1)                # bounded sample: the seed-0 streams of the batch
+                S = reference_setup(fx, rt, args.workload, 1, streams=(diffuse[:nd // seeds].copy(), shadow[:ns // seeds].copy()))   # bounded sample: the seed-0 streams of the batch
                 if S is not None:
                     reference_step(S)
                     tt, nn = 0.0, 0

@@ -146,7 +146,7 @@ k_trace(const TraceParams P) {
   int sp = 0;
   uint2 ng = make_uint2(0u, 0u);
   uint32_t tmask = 0u, triBase = 0u, tvalid = 0u;               // pending leaf triangles of the current node
-  bool found = false;
+  bool found = false, pend = false;                              // pend: the lane's finished ray has a result to write
   float hu = 0.f, hv = 0.f; RQVec3 hNg = rq_v3(0.f, 0.f, 0.f); uint32_t hPrim = 0, hGeom = 0;
   unsigned long long cntRays = 0, cntNodes = 0, cntTris = 0, cntHits = 0, cntEmpty = 0, cntHitNodes = 0, cntLate = 0; unsigned cntStack = 0, rayNodes = 0;
   bool exhausted = false;                                       // warp-uniform: the global counter ran past numRays
@@ -156,6 +156,53 @@ k_trace(const TraceParams P) {
   uint32_t curInst = RQ_INVALID, hInst = P.instID0; int spBase = 0;
 
   for (;;) {
+    // ================= results of the rays that finished since the last refill =================
+    // Written here and not where the ray ends: there, one or two lanes of the warp would execute the stores (7.5 % of the
+    // closest-hit kernel's warp instructions ran at <= 4 active lanes, profiles/r01final_ncu_source.txt); here all lanes that
+    // went idle in the meantime do it together.  An idle lane keeps its ray id and hit registers until it is refilled.
+    {
+      const unsigned fm = __ballot_sync(FULL, pend);
+      if (pend) {
+        pend = false;
+        if (COMPACT && !OCCLUDED) {                             // the hit's triangle index -> geomID, quad half (quad_intersector_moeller.h:28-37)
+          const uint32_t m = __ldg(P.meta + hGeom);
+          if (m & RQ_META_FLIPUV) { hu = 1.0f - fminf(hu, 1.0f); hv = 1.0f - fminf(hv, 1.0f); }
+          hGeom = m & ~RQ_META_FLIPUV;
+        }
+        if (LIST) {
+          // warp-aggregated append: the lanes flushing now share one atomic
+          const int fl = __ffs(fm) - 1;
+          unsigned fbase = 0;
+          if ((int)lane == fl) fbase = atomicAdd(P.hitCount, (unsigned)__popc(fm));
+          fbase = __shfl_sync(fm, fbase, fl);
+          const unsigned fslot = fbase + (unsigned)__popc(fm & ((1u << lane) - 1u));
+          if (OCCLUDED) {
+            ((uint32_t*)P.hitList)[fslot] = rid;
+          } else {
+            float4* d = (float4*)(P.hitList + (size_t)fslot * 48);
+            d[0] = make_float4(__uint_as_float(rid), tfar, 0.f, 0.f);
+            d[1] = make_float4(hNg.x, hNg.y, hNg.z, hu);
+            d[2] = make_float4(hv, __uint_as_float(hPrim), __uint_as_float(hGeom), __uint_as_float(INST ? hInst : P.instID0));
+          }
+        } else {
+          char* rp = P.out + (size_t)rid * P.stride;
+          if (COUNT) { cntHits++; cntHitNodes += rayNodes; }
+          if (OCCLUDED) {
+            *(float*)(rp + 32) = -INFINITY;
+          } else {
+            *(float*)(rp + 32) = tfar;
+            if (ALIGNED) {
+              *(float4*)(rp + 48) = make_float4(hNg.x, hNg.y, hNg.z, hu);
+              *(float4*)(rp + 64) = make_float4(hv, __uint_as_float(hPrim), __uint_as_float(hGeom), __uint_as_float(INST ? hInst : P.instID0));
+            } else {
+              float* f = (float*)(rp + 48);
+              f[0] = hNg.x; f[1] = hNg.y; f[2] = hNg.z; f[3] = hu; f[4] = hv;
+              ((uint32_t*)f)[5] = hPrim; ((uint32_t*)f)[6] = hGeom; ((uint32_t*)f)[7] = INST ? hInst : P.instID0;
+            }
+          }
+        }
+      }
+    }
     // ================= refill: idle lanes take the next rays of the stream =================
     const unsigned idle = __ballot_sync(FULL, !active);
     if (idle) {
@@ -325,45 +372,7 @@ k_trace(const TraceParams P) {
           if (sp > (int)sdepth + SPILL) sp = (int)sdepth + SPILL;  // entries beyond the stack were dropped (cannot happen: capacity >= depth)
           if (sp == 0) {
             active = false;
-            if (COMPACT && found && !OCCLUDED) {                // the hit's triangle index -> geomID, quad half (quad_intersector_moeller.h:28-37)
-              const uint32_t m = __ldg(P.meta + hGeom);
-              if (m & RQ_META_FLIPUV) { hu = 1.0f - fminf(hu, 1.0f); hv = 1.0f - fminf(hv, 1.0f); }
-              hGeom = m & ~RQ_META_FLIPUV;
-            }
-            if (found && LIST) {
-              // warp-aggregated append: the lanes that finish a hit ray in this very iteration share one atomic
-              const unsigned fm = __activemask();
-              const int fl = __ffs(fm) - 1;
-              unsigned fbase = 0;
-              if ((int)lane == fl) fbase = atomicAdd(P.hitCount, (unsigned)__popc(fm));
-              fbase = __shfl_sync(fm, fbase, fl);
-              const unsigned fslot = fbase + (unsigned)__popc(fm & ((1u << lane) - 1u));
-              if (OCCLUDED) {
-                ((uint32_t*)P.hitList)[fslot] = rid;
-              } else {
-                float4* d = (float4*)(P.hitList + (size_t)fslot * 48);
-                d[0] = make_float4(__uint_as_float(rid), tfar, 0.f, 0.f);
-                d[1] = make_float4(hNg.x, hNg.y, hNg.z, hu);
-                d[2] = make_float4(hv, __uint_as_float(hPrim), __uint_as_float(hGeom), __uint_as_float(INST ? hInst : P.instID0));
-              }
-            } else
-            if (found) {
-              char* rp = P.out + (size_t)rid * P.stride;
-              if (COUNT) { cntHits++; cntHitNodes += rayNodes; }
-              if (OCCLUDED) {
-                *(float*)(rp + 32) = -INFINITY;
-              } else {
-                *(float*)(rp + 32) = tfar;
-                if (ALIGNED) {
-                  *(float4*)(rp + 48) = make_float4(hNg.x, hNg.y, hNg.z, hu);
-                  *(float4*)(rp + 64) = make_float4(hv, __uint_as_float(hPrim), __uint_as_float(hGeom), __uint_as_float(INST ? hInst : P.instID0));
-                } else {
-                  float* f = (float*)(rp + 48);
-                  f[0] = hNg.x; f[1] = hNg.y; f[2] = hNg.z; f[3] = hu; f[4] = hv;
-                  ((uint32_t*)f)[5] = hPrim; ((uint32_t*)f)[6] = hGeom; ((uint32_t*)f)[7] = INST ? hInst : P.instID0;
-                }
-              }
-            }
+            pend = found;                                       // the result is written at the next refill point, together with the other lanes that finished
           } else {
             --sp;
             if ((uint32_t)sp < sdepth) ng = s_stack[(uint32_t)sp * 128u + threadIdx.x];

@@ -415,13 +415,19 @@ void replicateScene(Scene* sc) {
     sc->peerScenes.clear();
     for (Device* pd : dev->peers) sc->peerScenes.push_back(new Scene(pd));
   }
-  const auto t0 = std::chrono::steady_clock::now();
   std::vector<void*> dst(dev->peers.size(), nullptr);
+  auto t0 = std::chrono::steady_clock::now();
   try {
-    for (size_t g = 0; g < dev->peers.size(); g++) {
+    for (size_t g = 0; g < dev->peers.size(); g++) {                // allocations first (the first commit grows the peers' pools: not transfer time)
       Device* pd = dev->peers[g];
       pd->bind();
       cudaCheck(rqAllocImage(&dst[g], bytes, (rqStream)pd->stream()), "replica alloc");
+      cudaCheck(cudaStreamSynchronize(pd->stream()), "replica alloc");
+    }
+    t0 = std::chrono::steady_clock::now();
+    for (size_t g = 0; g < dev->peers.size(); g++) {
+      Device* pd = dev->peers[g];
+      pd->bind();
       cudaCheck(cudaMemcpyPeerAsync(dst[g], pd->ordinal, sc->image.base, dev->ordinal, bytes, pd->stream()), "replica copy");
     }
     for (size_t g = 0; g < dev->peers.size(); g++) {
