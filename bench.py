@@ -10,7 +10,7 @@ stream + one occlusion stream over the whole batch.  `value` = rays of the batch
 HBM (CUDA events on the launching stream); `e2e` = the same through the C ABI with page-locked HOST buffers (H2D, kernels,
 D2H inside the timed region; a pageable-memory figure beside it).
 N > 1 (one process per GPU under torchrun): rank 0 builds, the flat BVH image is broadcast over NCCL / NVLink, every rank
-traces its contiguous shard (rows of the frame) of the SAME batch -- strong scaling -- and the hit records are gathered on
+traces its shard (64-row bands of the frame, dealt round-robin) of the SAME batch -- strong scaling -- and the hit records are gathered on
 rank 0 (timed separately: `gather`).  `--workload c2` is BASELINE configs[1] (1.0 M triangles, 33.5 M rays, L2-resident BVH),
 `--workload c5` the build benchmark of configs[4].
 
@@ -135,17 +135,28 @@ def workload_name(w, tris, rays):
             f"(diffuse closest-hit stream (rtcIntersect1M) + shadow stream (rtcOccluded1M))")
 
 
-def make_streams(fx, trace_primary, rows, seeds, bands=8):
-    """The batch of this process: for every sampler seed one diffuse and one shadow stream over frame rows [rows[0], rows[1]).
-    trace_primary(rays) traces a coherent primary stream in place.  Returns (diffuse RAYHIT array, shadow RAY array)."""
-    r0, r1 = rows
-    edges = [r0 + (r1 - r0) * b // bands for b in range(bands + 1)]
+SHARD_ROWS = 64                                                            # N > 1: frame rows are dealt to the ranks in bands of this many rows
+
+
+def shard_bands(rank, world):
+    """Row bands [(r0, r1), ...] of the frame that rank `rank` of `world` traces.  One GPU: the whole frame (in 8 pieces, to bound the
+    host memory of the generator).  N GPUs: 64-row bands dealt round-robin -- contiguous N-ths of this frame differ by 10 % in
+    cost per ray (max / mean 1.106 at N = 8, 1.026 with the bands; profiles/r02l_shard_balance.jsonl), and strong scaling is
+    timed as the max over ranks."""
+    if world == 1:
+        return [(FRAME * b // 8, FRAME * (b + 1) // 8) for b in range(8)]
+    return [(r0, min(r0 + SHARD_ROWS, FRAME)) for k, r0 in enumerate(range(0, FRAME, SHARD_ROWS)) if k % world == rank]
+
+
+def make_streams(fx, trace_primary, bands, seeds):
+    """The batch of this process: for every sampler seed one diffuse and one shadow stream over the frame rows of `bands`
+    (list of (r0, r1)).  trace_primary(rays) traces a coherent primary stream in place.  Returns (diffuse RAYHIT array, shadow RAY array)."""
     d_parts = [[] for _ in range(seeds)]
     s_parts = [[] for _ in range(seeds)]
-    for b in range(bands):
-        if edges[b + 1] <= edges[b]:
+    for r0, r1 in bands:
+        if r1 <= r0:
             continue
-        prim = fx.primary_rays(FRAME, FRAME, rows=(edges[b], edges[b + 1]), **fx.C2_CAMERA)
+        prim = fx.primary_rays(FRAME, FRAME, rows=(r0, r1), **fx.C2_CAMERA)
         trace_primary(prim)
         for k in range(seeds):
             d_parts[k].append(fx.diffuse_rays(prim, sample_id=k))
@@ -189,7 +200,7 @@ def reference_setup(fx, rt, workload, seeds, streams=None):
     t0 = time.perf_counter()
     sc, keep = ref.build_scene(dev, meshes)
     build_s = time.perf_counter() - t0
-    diffuse, shadow = streams if streams is not None else make_streams(fx, lambda r: drv.trace(sc, r, coherent=True), (0, FRAME), seeds)
+    diffuse, shadow = streams if streams is not None else make_streams(fx, lambda r: drv.trace(sc, r, coherent=True), shard_bands(0, 1), seeds)
     return dict(ref=ref, drv=drv, dev=dev, sc=sc, keep=keep, cores=drv.cores, diffuse=diffuse, shadow=shadow, build_s=build_s, tris=fx.num_tris(meshes))
 
 
@@ -293,9 +304,8 @@ def run_ours(args):
         sc, bcast_ms = mg.replicate_scene(lib, dev, sc if rank == 0 else None, 0)
     assert lib.lib.rtcGetDeviceError(dev) == 0
 
-    # ---- this rank's contiguous shard of the batch: rows [rank, rank+1) * 4096 / world of every stream ----
-    rows = (rank * FRAME // world, (rank + 1) * FRAME // world)
-    diffuse, shadow = make_streams(fx, lambda r: lib.intersect(sc, r, coherent=True), rows, seeds)
+    # ---- this rank's shard of the batch: its row bands of every stream (the whole frame on one GPU) ----
+    diffuse, shadow = make_streams(fx, lambda r: lib.intersect(sc, r, coherent=True), shard_bands(rank, world), seeds)
     nd, ns = len(diffuse), len(shadow)
     h_d = torch.from_numpy(diffuse.view(np.uint8).reshape(nd, 80)).pin_memory()
     h_s = torch.from_numpy(shadow.view(np.uint8).reshape(ns, 48)).pin_memory()
@@ -391,8 +401,12 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # ---- max over ranks ----
+    per_rank = None
     if world > 1:
         t = torch.tensor([ms_step, e2e.get("t", 0.0) * 1e3, t_close, t_occ, e2e.get("t_pg", 0.0) * 1e3, gather_ms], dtype=torch.float64, device="cuda")
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)                                            # every rank's own times: how even the shards are
+        per_rank = {"device_ms": [round(float(x[0]), 3) for x in allt], "e2e_ms": [round(float(x[1]), 3) for x in allt]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, e2e_ms, t_close, t_occ, pg_ms, gather_ms = [float(x) for x in t.tolist()]
         cnt = torch.tensor([nd + ns, launches, e2e.get("h2d", 0), e2e.get("d2h", 0), nd, ns, c_close["nodes"], c_close["tris"], hits,
@@ -437,7 +451,8 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, ntris, total_rays), "rays_per_step": total_rays, "rays_per_gpu_per_step": nd + ns,
                        "l2_policy": "inputs (GBs of ray records per step) exceed the 126 MB L2; streams re-copied from pristine buffers between timed steps",
-                       "parallelism": f"rays sharded contiguously x{world} (strong scaling: the batch is fixed), BVH replica per GPU"},
+                       "parallelism": (f"frame rows dealt to the {world} ranks in {SHARD_ROWS}-row bands (strong scaling: the batch is fixed), BVH replica per GPU"
+                                       if world > 1 else "one GPU traces the whole batch")},
             "closest_mrays_per_s": tnd / (t_close * 1e-3) / 1e6, "occluded_mrays_per_s": tns / (t_occ * 1e-3) / 1e6,
             "build": build, "build_mtris_per_s": (ntris / (build["msTotal"] * 1e-3) / 1e6) if build else None,
             "build_phases": build_phase_rates(build, float(peaks["hbm_gbs"]) if peaks else 6650.0) if build else None,
@@ -456,6 +471,8 @@ def run_ours(args):
                                  "active lanes per instruction) -- the kernel is issue / divergence bound, not DRAM bound, on both scenes"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if per_rank:
+            line["per_rank"] = per_rank
         if e2e:
             line["e2e"] = {"value": total_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d_step),
                            "d2h_bytes_per_step": int(d2h_step), "host_record_bytes_per_step": tnd * 80 + tns * 48,

@@ -612,7 +612,7 @@ __device__ __forceinline__ void initLeaf(const B2& t, uint32_t node, const RQTri
 // Bounds, triangle count and the collapse programme of binary node `cur` from its finished children L, R.
 __device__ __forceinline__ void combineNode(const B2& t, uint32_t cur, uint32_t L, uint32_t R,
                                             float costNode, float costTri, int maxLeafTris) {
-    // data produced by other SMs in this launch: read through L2 (ld.cg), never L1
+    // data produced by other threads / SMs in this launch: read through L2 (ld.cg), never L1
     const float4 llo = __ldcg(t.lo + L), lhi = __ldcg(t.hi + L), rlo = __ldcg(t.lo + R), rhi = __ldcg(t.hi + R);
     const float4 l0 = __ldcg((const float4*)(t.cost + (size_t)L * 8)), l1 = __ldcg((const float4*)(t.cost + (size_t)L * 8) + 1);
     const float4 r0 = __ldcg((const float4*)(t.cost + (size_t)R * 8)), r1 = __ldcg((const float4*)(t.cost + (size_t)R * 8) + 1);
@@ -986,15 +986,12 @@ __device__ __forceinline__ float boxArea6(const float lo[3], const float hi[3]) 
   return halfArea(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
 }
 
-// one lane builds the subtree over perm[b0, e0) (2 <= e0 - b0 <= TL_SMALL) rooted at local node index j0: radix-tree splits of
-// the Morton-ordered slice (Karras 2012 on the sub-sequence; equal codes are halved by position)
+// one lane splits ONE node of a small subtree: the slice perm[b, e) (2 <= e - b <= TL_SMALL) with local node index j.  Radix-tree
+// split of the Morton-ordered slice (Karras 2012 on the sub-sequence; equal codes are halved by position).  Returns the size of the
+// left child; the caller queues the children.
 template <int K, int SWEEP>
-__device__ void treeletSmallSubtree(TreeletSmem<K, SWEEP>& S, const B2& t, uint32_t b0, uint32_t e0, uint32_t j0, uint32_t base, uint32_t leaf0, int lane) {
-  uint32_t st[8]; int sp = 0;                                   // the smaller child is finished first: <= log2(TL_SMALL) + 1 pending ranges
-  st[sp++] = b0 | (e0 << 10) | (j0 << 20);
-  while (sp > 0) {
-    const uint32_t w = st[--sp];
-    const uint32_t b = w & 1023u, e = (w >> 10) & 1023u, j = w >> 20;
+__device__ __forceinline__ uint32_t treeletSmallNode(TreeletSmem<K, SWEEP>& S, const B2& t, uint32_t b, uint32_t e, uint32_t j, uint32_t base, uint32_t leaf0, int lane) {
+  {
     const uint32_t m = e - b;
     uint32_t mL = m >> 1;
     if (SWEEP > 0 && m > 2u && m <= (uint32_t)SWEEP) {
@@ -1061,9 +1058,7 @@ __device__ void treeletSmallSubtree(TreeletSmem<K, SWEEP>& S, const B2& t, uint3
     const uint32_t refL = mL == 1u ? leaf0 + S.perm[b] : base + jL;
     const uint32_t refR = mR == 1u ? leaf0 + S.perm[b + mL] : base + jR;
     t.left[g] = refL; t.right[g] = refR; t.parent[refL] = g; t.parent[refR] = g;
-    const bool leftBig = mL >= mR;
-    if (leftBig) { if (mL >= 2u) st[sp++] = b | ((b + mL) << 10) | (jL << 20); if (mR >= 2u) st[sp++] = (b + mL) | (e << 10) | (jR << 20); }
-    else { if (mR >= 2u) st[sp++] = (b + mL) | (e << 10) | (jR << 20); if (mL >= 2u) st[sp++] = b | ((b + mL) << 10) | (jL << 20); }
+    return mL;
   }
 }
 
@@ -1089,7 +1084,7 @@ k_treelet_build(B2 t, int n, const uint32_t* __restrict__ treeletStart, const ui
   }
   int sp = 0, nsmall = 0;                                       // warp-uniform
   if (m0 > (uint32_t)TL_SMALL) { if (lane == 0) { S.stack[0][0] = m0 << 16; S.stack[0][1] = 0u; } sp = 1; }
-  else { if (lane == 0) { S.small[0][0] = m0 << 16; S.small[0][1] = 0u; } nsmall = 1; }
+  else { if (lane == 0) S.small[0][0] = m0 << 10; nsmall = 1; }   // small-subtree entries: begin | end << 10 | local node index << 20
   __syncwarp();
 
   // ---------------- warp-cooperative phase: nodes of more than TL_SMALL triangles ----------------
@@ -1225,18 +1220,97 @@ k_treelet_build(B2 t, int n, const uint32_t* __restrict__ treeletStart, const ui
       if (cm < 2u) continue;
       // (every stacked range is at least as large as all ranges above it together, so at most log2(K / TL_SMALL) + 1 <= 6 are pending)
       if (cm > (uint32_t)TL_SMALL) { if (lane == 0) { S.stack[sp][0] = cb[c] | (ce[c] << 16); S.stack[sp][1] = cj[c]; } sp++; }
-      else { if (lane == 0) { S.small[nsmall][0] = cb[c] | (ce[c] << 16); S.small[nsmall][1] = cj[c]; } nsmall++; }
+      else { if (lane == 0) (&S.small[0][0])[nsmall] = cb[c] | (ce[c] << 10) | (cj[c] << 20); nsmall++; }
     }
     __syncwarp();
   }
 
-  // ---------------- thread phase: one lane per small subtree ----------------
-  for (int s0 = 0; s0 < nsmall; s0 += 32) {
-    const int s = s0 + lane;
-    if (s < nsmall) {
-      const uint32_t be = S.small[s][0];
-      treeletSmallSubtree<K, SWEEP>(S, t, be & 0xFFFFu, be >> 16, S.small[s][1], base, leaf0, lane);
+  // ---------------- thread phase: the small subtrees, level by level, one lane per NODE ----------------
+  // (one lane per SUBTREE ran 2-5 lanes wide -- a 133-triangle treelet has 6-8 small subtrees of very different sizes -- and was a
+  // quarter of this kernel, profiles/r02m_ncu_build.txt; the nodes of one level of all small subtrees are independent, so the warp
+  // takes them 32 at a time from a queue in shared memory and pushes their children for the next round.)
+  {
+    uint32_t* qa = &S.small[0][0]; uint32_t* qb = qa + K / 2;   // ranges of >= 2 triangles are disjoint: at most K/2 per level
+    int na = nsmall;
+    const unsigned below = (1u << lane) - 1u;
+    __syncwarp();
+    while (na > 0) {
+      int nb = 0;
+      for (int i0 = 0; i0 < na; i0 += 32) {
+        const int i = i0 + lane;
+        uint32_t cL = 0u, cR = 0u;
+        if (i < na) {
+          const uint32_t w = qa[i];
+          const uint32_t b = w & 1023u, e = (w >> 10) & 1023u, j = w >> 20;
+          const uint32_t mL = treeletSmallNode<K, SWEEP>(S, t, b, e, j, base, leaf0, lane);
+          if (mL >= 2u) cL = b | ((b + mL) << 10) | ((j + 1u) << 20);
+          if (e - b - mL >= 2u) cR = (b + mL) | (e << 10) | ((j + mL) << 20);
+        }
+        const unsigned bl = __ballot_sync(FULL, cL != 0u), br = __ballot_sync(FULL, cR != 0u);
+        if (cL) qb[nb + __popc(bl & below)] = cL;
+        if (cR) qb[nb + __popc(bl) + __popc(br & below)] = cR;
+        nb += __popc(bl) + __popc(br);
+      }
+      __syncwarp();
+      uint32_t* x = qa; qa = qb; qb = x; na = nb;
     }
+  }
+}
+
+// Bounds + SAH collapse programme inside the treelets, one WARP per treelet, level by level.
+// The leaf-to-root climb with arrival counters (k_refit_dp) loses half of its lanes at every level and pays an atomic, two fences and an
+// L2 round trip per node: 1.4 ms for the 10 M-triangle scene.  Doing the combine in the lane that built a small subtree (inside
+// k_treelet_build) was no better: that phase runs 4.4 lanes wide at 20 warps per SM (profiles/r02m_ncu_build.txt).  Here the warp first
+// lists the treelet's inner nodes in breadth-first order (shared memory only), then sweeps the levels bottom-up: all nodes of a level
+// are independent, so the 32 lanes combine 32 nodes at a time and the L2 latency is paid once per level, not once per node.
+constexpr int TDP_WARPS = 8;
+template <int K>
+__global__ void __launch_bounds__(TDP_WARPS * 32)
+k_treelet_dp(B2 t, int n, const uint32_t* __restrict__ treeletStart, const uint32_t* __restrict__ sizeAt, uint32_t T,
+             float costNode, float costTri, int maxLeafTris) {
+  __shared__ uint32_t s_left[TDP_WARPS][K], s_right[TDP_WARPS][K];
+  __shared__ uint16_t s_bfs[TDP_WARPS][K], s_lvl[TDP_WARPS][K];   // nodes in breadth-first order; first position of every level
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  const uint32_t tIdx = blockIdx.x * TDP_WARPS + (uint32_t)warp;
+  if (tIdx >= T) return;                                        // warps are independent: no block-wide barrier below
+  const uint32_t a0 = treeletStart[tIdx], m0 = sizeAt[a0];
+  if (m0 < 2u || m0 > (uint32_t)K) return;
+  const uint32_t base = (T - 1u) + (a0 - tIdx);                 // global id of the treelet's root; its m0 - 1 inner nodes are base + [0, m0 - 1)
+  const uint32_t firstLeaf = (uint32_t)(n - 1);
+  uint32_t* L = s_left[warp]; uint32_t* R = s_right[warp]; uint16_t* bfs = s_bfs[warp]; uint16_t* lvl = s_lvl[warp];
+  for (uint32_t i = lane; i < m0 - 1u; i += 32u) { L[i] = t.left[base + i]; R[i] = t.right[base + i]; }
+  if (lane == 0) { bfs[0] = 0; lvl[0] = 0; }
+  __syncwarp();
+  // ---- breadth-first order ----
+  uint32_t s = 0, e = 1, nl = 1;                                 // current level = bfs[s, e); nl levels known so far   (all warp-uniform)
+  while (s < e) {
+    uint32_t out = e;
+    for (uint32_t i0 = s; i0 < e; i0 += 32u) {
+      const uint32_t i = i0 + lane;
+      uint32_t cl = RQ_INVALID, cr = RQ_INVALID;
+      if (i < e) { const uint32_t x = bfs[i]; cl = L[x]; cr = R[x]; }
+      const bool il = cl < firstLeaf, ir = cr < firstLeaf;       // inner children (of this treelet: ids base + ...)
+      const unsigned bl = __ballot_sync(FULL, il), br = __ballot_sync(FULL, ir);
+      const unsigned below = (1u << lane) - 1u;
+      if (il) bfs[out + __popc(bl & below)] = (uint16_t)(cl - base);
+      if (ir) bfs[out + __popc(bl) + __popc(br & below)] = (uint16_t)(cr - base);
+      out += __popc(bl) + __popc(br);
+    }
+    __syncwarp();
+    s = e; e = out;
+    if (s < e) { if (lane == 0) lvl[nl] = (uint16_t)s; nl++; }
+  }
+  __syncwarp();
+  // ---- bottom-up over the levels ----
+  for (uint32_t l = nl; l-- > 0; ) {
+    const uint32_t ls = lvl[l], le = (l + 1u < nl) ? (uint32_t)lvl[l + 1u] : (m0 - 1u);
+    for (uint32_t i = ls + lane; i < le; i += 32u) {
+      const uint32_t x = bfs[i];
+      combineNode(t, base + x, L[x], R[x], costNode, costTri, maxLeafTris);
+    }
+    __threadfence_block();
+    __syncwarp();
   }
 }
 
@@ -1270,170 +1344,269 @@ __device__ __forceinline__ uint8_t expForExtent(float ext) {
   return (uint8_t)eb;
 }
 
-__device__ __forceinline__ void
-emit_one(const B2& t, int n, uint32_t q, const uint2* __restrict__ queue, uint2* __restrict__ nextQueue,
-         EmitCounters* ctr, RQNode* __restrict__ nodes, RQTri* __restrict__ trisOut,
-         const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals, uint32_t level,
-         const uint32_t* __restrict__ parentOf, uint32_t* __restrict__ nextParentOf, double sahOut[5],
-         const uint32_t* __restrict__ idxIn, RQTriC* __restrict__ trisC, uint32_t* __restrict__ metaOut) {
-  const uint32_t b = queue[q].x, w = queue[q].y;
-  const uint32_t firstLeaf = (uint32_t)(n - 1);
+// One tree level per launch, but the host does not wait for it: the level's entry count lives on the device (`lv`, written by
+// k_emit_advance after the previous level), the grid is a fixed persistent one (grid-stride over the queue), and the host reads the
+// per-level counts back once per batch of levels.  (One launch + read-back + synchronise per level cost 12 round trips = 0.3 ms of
+// the 10 M-triangle build.)
+struct EmitLevel { uint32_t count, nodeEnd; };                // queue entries of a level; nodes allocated once that level has been emitted
 
-  // ---- gather the <= 8 children by replaying the DP decisions ----
-  uint32_t child[8]; bool inner[8]; int nc = 0;
-  if (b >= firstLeaf) {                                        // degenerate scene: a single triangle
-    child[0] = b; inner[0] = false; nc = 1;
-  } else {
-    uint32_t stN[16]; int stI[16]; int sp = 0;
-    const uint32_t k8 = (t.dec[b] >> 21) & 7u;
-    stN[sp] = t.right[b]; stI[sp++] = 8 - (int)k8;
-    stN[sp] = t.left[b];  stI[sp++] = (int)k8;
-    while (sp > 0) {
-      const uint32_t m = stN[--sp]; int i = stI[sp];
-      if (m >= firstLeaf) { child[nc] = m; inner[nc++] = false; continue; }
-      const uint32_t dec = t.dec[m];
-      while (i > 1 && ((dec >> (3 * (i - 1))) & 7u) == 0u) i--;
-      if (i == 1) { child[nc] = m; inner[nc++] = (dec & 1u) != 0u; continue; }
-      const int kk = (int)((dec >> (3 * (i - 1))) & 7u);
-      stN[sp] = t.right[m]; stI[sp++] = i - kk;
-      stN[sp] = t.left[m];  stI[sp++] = kk;
-    }
-  }
+// EIGHT LANES PER 8-WIDE NODE.  Round-2 history (profiles/r02m_ncu_build.txt): with one thread per node everything below lived in
+// dynamically indexed local arrays (880 bytes of stack per thread; at 1024 threads per SM that is 0.9 MB per SM and spills to DRAM:
+// 0.73 GB written by a launch whose nodes and triangles are 0.24 GB), the greedy slot assignment alone was ~2500 instructions per
+// thread, and four counters in one 32-byte sector took an atomic per node.  Now lane k of a group first holds the k-th budget slot of
+// the collapse programme (the <= 8 children are found by splitting budget intervals in parallel), then its child: box, scores, slot,
+// quantised bytes all stay in registers; the 128-byte node is assembled in shared memory and leaves as one coalesced line; the
+// allocation counters are bumped once per BLOCK (32 nodes).
+constexpr int EMIT_THREADS = 256, EMIT_GROUPS = EMIT_THREADS / 8;
 
-  // ---- node box and child boxes ----
-  const float4 nlo = t.lo[b], nhi = t.hi[b];
-  float clo[8][3], chi[8][3]; uint32_t ctris[8];
-  for (int c = 0; c < nc; c++) {
-    const float4 a = t.lo[child[c]], h = t.hi[child[c]];
-    clo[c][0] = a.x; clo[c][1] = a.y; clo[c][2] = a.z; chi[c][0] = h.x; chi[c][1] = h.y; chi[c][2] = h.z;
-    ctris[c] = __float_as_uint(h.w);
-  }
-
-  // ---- slot assignment: slot s (bit a set = "towards +axis a") takes the child whose centre lies
-  //      furthest in that diagonal direction; greedy maximum over the 8x8 score table ----
-  const float ncx = 0.5f * (nlo.x + nhi.x), ncy = 0.5f * (nlo.y + nhi.y), ncz = 0.5f * (nlo.z + nhi.z);
-  int slotOf[8]; int childAt[8];
-  for (int s = 0; s < 8; s++) childAt[s] = -1;
-  for (int c = 0; c < nc; c++) slotOf[c] = -1;
-  for (int r = 0; r < nc; r++) {
-    float best = -FLT_MAX; int bc = -1, bs = -1;
-    for (int c = 0; c < nc; c++) {
-      if (slotOf[c] >= 0) continue;
-      const float dx = 0.5f * (clo[c][0] + chi[c][0]) - ncx, dy = 0.5f * (clo[c][1] + chi[c][1]) - ncy,
-                  dz = 0.5f * (clo[c][2] + chi[c][2]) - ncz;
-      for (int s = 0; s < 8; s++) {
-        if (childAt[s] >= 0) continue;
-        const float sc = ((s & 1) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 4) ? dz : -dz);
-        if (sc > best) { best = sc; bc = c; bs = s; }
-      }
-    }
-    slotOf[bc] = bs; childAt[bs] = bc;
-  }
-
-  // ---- allocate children / triangles ----
-  uint32_t numInner = 0, numLeafTris = 0, numLeaves = 0;
-  for (int c = 0; c < nc; c++) { if (inner[c]) numInner++; else { numLeafTris += ctris[c]; numLeaves++; } }
-  const uint32_t childBase = numInner ? atomicAdd(&ctr->nodeCount, numInner) : 0u;
-  const uint32_t triBase = numLeafTris ? atomicAdd(&ctr->triCount, numLeafTris) : 0u;
-  const uint32_t qBase = numInner ? atomicAdd(&ctr->nextCount, numInner) : 0u;
-  if (numLeaves) atomicAdd(&ctr->leafSlots, numLeaves);
-
-  // ---- quantisation grid ----
-  RQNode N;
-  N.p[0] = nlo.x; N.p[1] = nlo.y; N.p[2] = nlo.z;
-  const float ext[3] = {__fsub_ru(nhi.x, nlo.x), __fsub_ru(nhi.y, nlo.y), __fsub_ru(nhi.z, nlo.z)};
-  float inv[3], step[3];
-  for (int a = 0; a < 3; a++) {
-    uint8_t eb = expForExtent(ext[a]);
-    // make sure the far face is representable: ceil(ext / 2^e) <= 255
-    while (eb < 254 && __fmul_ru(ext[a], __uint_as_float((uint32_t)(254 - eb) << 23)) > 255.0f) eb++;
-    N.e[a] = eb;
-    step[a] = __uint_as_float((uint32_t)eb << 23);             // 2^(eb-127)
-    inv[a] = __uint_as_float((uint32_t)(254 - eb) << 23);       // 2^(127-eb)
-  }
-  N.pad0 = 0; N.pad1 = 0; N.masks = 0; N.childBase = childBase; N.triBase = triBase;
-  for (int s = 0; s < 8; s++) {
-    for (int a = 0; a < 3; a++) { N.qlo[a][s] = 255; N.qhi[a][s] = 0; }
-  }
-  uint32_t innerRank = 0, triOff = 0;
-  double sahInnerQ = 0, sahLeafQ = 0, sahInnerX = 0, sahLeafX = 0, sahLeafTrisQ = 0;
-  for (int s = 0; s < 8; s++) {
-    const int c = childAt[s];
-    if (c < 0) continue;
-    float dq[3];
-    for (int a = 0; a < 3; a++) {
-      // floor / ceil with directed rounding: decoded box always contains the exact one
-      float fl = floorf(__fmul_rd(__fsub_rd(clo[c][a], N.p[a]), inv[a]));
-      float fh = ceilf(__fmul_ru(__fsub_ru(chi[c][a], N.p[a]), inv[a]));
-      fl = fminf(fmaxf(fl, 0.f), 255.f); fh = fminf(fmaxf(fh, 0.f), 255.f);
-      N.qlo[a][s] = (uint8_t)fl; N.qhi[a][s] = (uint8_t)fh;
-      dq[a] = (fh - fl) * step[a];
-    }
-    const double Aq = (double)halfArea(dq[0], dq[1], dq[2]);
-    const double Ax = (double)halfArea(chi[c][0] - clo[c][0], chi[c][1] - clo[c][1], chi[c][2] - clo[c][2]);
-    if (inner[c]) {
-      N.masks |= 1u << (24 + s);
-      nextQueue[qBase + innerRank] = make_uint2(child[c], childBase + innerRank);
-      nextParentOf[qBase + innerRank] = w;
-      innerRank++;
-      sahInnerQ += Aq; sahInnerX += Ax;
-    } else {
-      const uint32_t nt = ctris[c];                           // 1..3
-      N.masks |= ((1u << nt) - 1u) << (3 * s);                // triangles are stored in slot order
-      // the <= 3 triangles of this leaf slot: the leaves below binary node child[c] (tiny depth-first walk;
-      // works for the radix tree and for PLOC, whose subtrees are not contiguous in Morton order)
-      uint32_t walk[4]; int wsp = 0; uint32_t j = 0;
-      walk[wsp++] = child[c];
-      while (wsp > 0 && j < nt) {
-        const uint32_t x = walk[--wsp];
-        if (x >= firstLeaf) {
-          const uint32_t tin = vals[x - firstLeaf];
-          const float4* src = (const float4*)(trisIn + tin);
-          if (trisC) {                                          // compact layout: indices + primID, geomID / quad flag on the side
-            const float4 c = src[2];
-            RQTriC r; r.v0 = idxIn[3 * (size_t)tin]; r.v1 = idxIn[3 * (size_t)tin + 1]; r.v2 = idxIn[3 * (size_t)tin + 2]; r.primID = __float_as_uint(c.y);
-            trisC[triBase + triOff + j] = r;
-            metaOut[triBase + triOff + j] = (__float_as_uint(c.z) & ~RQ_META_FLIPUV) | ((__float_as_uint(c.w) & RQ_PAD_FLIPUV) ? RQ_META_FLIPUV : 0u);
-          } else {
-            float4* dst = (float4*)(trisOut + triBase + triOff + j);
-            if ((triBase + triOff + j) & 1u) { dst[0] = src[2]; dst[1] = src[0]; dst[2] = src[1]; }   // odd records: last 16 bytes first (rq_types.h)
-            else { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
-          }
-          j++;
-        } else if (wsp < 3) { walk[wsp++] = t.right[x]; walk[wsp++] = t.left[x]; }
-      }
-      triOff += nt;
-      sahLeafQ += Aq * (double)((nt + 3) / 4); sahLeafX += Ax * (double)((nt + 3) / 4); sahLeafTrisQ += Aq * (double)nt;
-    }
-  }
-  N.lo[0] = nlo.x; N.lo[1] = nlo.y; N.lo[2] = nlo.z; N.hi[0] = nhi.x; N.hi[1] = nhi.y; N.hi[2] = nhi.z;
-  N.parent = parentOf ? parentOf[q] : RQ_INVALID;
-  N.numTris = __float_as_uint(nhi.w); N.level = level; N.pad[0] = N.pad[1] = N.pad[2] = 0;
-  {
-    const uint4* s4 = (const uint4*)&N; uint4* d4 = (uint4*)(nodes + w);
-    #pragma unroll
-    for (int i = 0; i < 8; i++) d4[i] = s4[i];
-  }
-  if (level == 0) { sahInnerQ += (double)nlo.w; sahInnerX += (double)nlo.w; }   // the root's own box
-  sahOut[0] = sahInnerQ; sahOut[1] = sahLeafQ; sahOut[2] = sahInnerX; sahOut[3] = sahLeafX; sahOut[4] = sahLeafTrisQ;
-}
-
-__global__ void __launch_bounds__(128)
-k_emit(B2 t, int n, const uint2* __restrict__ queue, uint32_t count, uint2* __restrict__ nextQueue,
+__global__ void __launch_bounds__(EMIT_THREADS)
+k_emit(B2 t, int n, const uint2* __restrict__ queue, const EmitLevel* __restrict__ lv, uint2* __restrict__ nextQueue,
        EmitCounters* ctr, RQNode* __restrict__ nodes, RQTri* __restrict__ trisOut,
        const RQTri* __restrict__ trisIn, const uint32_t* __restrict__ vals, uint32_t level,
        const uint32_t* __restrict__ parentOf /* wide parent per queue entry */, uint32_t* __restrict__ nextParentOf,
        const uint32_t* __restrict__ idxIn, RQTriC* __restrict__ trisC, uint32_t* __restrict__ metaOut) {
-  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  if (q < count)
-    emit_one(t, n, q, queue, nextQueue, ctr, nodes, trisOut, trisIn, vals, level, parentOf, nextParentOf, s, idxIn, trisC, metaOut);
+  const uint32_t count = lv[level].count;
+  if (count == 0u) return;                                      // a level launched past the bottom of the tree
+  static_assert(EMIT_GROUPS == 32, "the block-level scan below uses one warp, one lane per group");
+  __shared__ uint2 s_x[EMIT_GROUPS][8];                         // gather: inbox of every budget slot
+  __shared__ uint32_t s_cnt[3][EMIT_GROUPS], s_base[3][EMIT_GROUPS];
+  __shared__ __align__(16) uint32_t s_node[EMIT_GROUPS][32];    // the node records being assembled
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u, sub = threadIdx.x & 7u, grp = threadIdx.x >> 3, gsh = lane & 24u;
+  const uint32_t firstLeaf = (uint32_t)(n - 1);
+  double sInnerQ = 0.0, sLeafQ = 0.0, sInnerX = 0.0, sLeafX = 0.0, sLeafTrisQ = 0.0;
+
+  for (uint32_t q0 = blockIdx.x * EMIT_GROUPS; q0 < count; q0 += gridDim.x * EMIT_GROUPS) {   // block-uniform trip count
+    const uint32_t q = q0 + grp;
+    const bool valid = q < count;
+    uint32_t b = 0u, w = 0u;
+    if (valid) { const uint2 e = queue[q]; b = e.x; w = e.y; }
+
+    // ---- gather the <= 8 children by replaying the DP decisions: the item whose budget interval starts at k lives in lane k ----
+    uint32_t m = RQ_INVALID; int bud = 0, state = 0;             // state: 0 = empty, 1 = pending, 2 = child found
+    bool isInner = false, force = false;
+    if (valid && sub == 0u) { m = b; bud = 8; state = 1; force = b < firstLeaf; }   // the node itself always splits 8 ways (b >= firstLeaf: a single-triangle scene)
+    for (int round = 0; round < 16; round++) {
+      s_x[grp][sub] = make_uint2(RQ_INVALID, 0u);
+      __syncwarp();
+      if (state == 1) {
+        if (m >= firstLeaf) { state = 2; isInner = false; }
+        else {
+          const uint32_t dec = t.dec[m];
+          int i = bud;
+          if (!force) while (i > 1 && ((dec >> (3 * (i - 1))) & 7u) == 0u) i--;
+          if (i == 1) { state = 2; isInner = (dec & 1u) != 0u; }
+          else {
+            const int kk = (int)((dec >> (3 * (i - 1))) & 7u);
+            s_x[grp][sub + kk] = make_uint2(t.right[m], (uint32_t)(i - kk));
+            m = t.left[m]; bud = kk;
+          }
+        }
+        force = false;
+      }
+      __syncwarp();
+      const uint2 in = s_x[grp][sub];
+      if (in.x != RQ_INVALID) { m = in.x; bud = (int)in.y; state = 1; }
+      if (!__any_sync(FULL, state == 1)) break;
+    }
+    const bool has = state == 2;
+    const bool leaf = has && !isInner;
+    const unsigned hb = __ballot_sync(FULL, has), ib = __ballot_sync(FULL, has && isInner), lb = __ballot_sync(FULL, leaf);
+    const int nc = __popc((hb >> gsh) & 0xFFu);
+
+    // ---- node box and this lane's child box ----
+    float4 nlo = make_float4(0.f, 0.f, 0.f, 0.f), nhi = nlo, lo = nlo, hi = nlo;
+    if (valid) { nlo = t.lo[b]; nhi = t.hi[b]; }
+    if (has) { lo = t.lo[m]; hi = t.hi[m]; }
+    const uint32_t ctris = has ? __float_as_uint(hi.w) : 0u;
+
+    // ---- slot assignment: slot s (bit a set = "towards +axis a") takes the child whose centre lies furthest in that diagonal
+    //      direction; greedy maximum over the 8x8 score table (ties: first child, then first slot) ----
+    int mySlot = -1;
+    {
+      const float ncx = 0.5f * (nlo.x + nhi.x), ncy = 0.5f * (nlo.y + nhi.y), ncz = 0.5f * (nlo.z + nhi.z);
+      const float dx = 0.5f * (lo.x + hi.x) - ncx, dy = 0.5f * (lo.y + hi.y) - ncy, dz = 0.5f * (lo.z + hi.z) - ncz;
+      float sc[8];
+      #pragma unroll
+      for (int sl = 0; sl < 8; sl++) sc[sl] = ((sl & 1) ? dx : -dx) + ((sl & 2) ? dy : -dy) + ((sl & 4) ? dz : -dz);
+      // Every round: the largest score still available (a plain max: scores of taken slots and of placed children are -FLT_MAX),
+      // then the first child (lowest lane) and, within it, the first slot that attain it -- what the sequential double loop with
+      // its strict comparison picks.  ~40 instructions per round instead of ~110 for an arg-max carried through the shuffles.
+      uint32_t freeS = 0xFFu;
+      if (!has) {
+        #pragma unroll
+        for (int sl = 0; sl < 8; sl++) sc[sl] = -FLT_MAX;
+      }
+      for (int r = 0; r < 8; r++) {
+        if (__all_sync(FULL, r >= nc)) break;
+        float best = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), fmaxf(fmaxf(sc[4], sc[5]), fmaxf(sc[6], sc[7])));
+        #pragma unroll
+        for (int o = 1; o < 8; o <<= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, o));
+        uint32_t eq = 0u;
+        #pragma unroll
+        for (int sl = 0; sl < 8; sl++) eq |= (sc[sl] == best) ? (1u << sl) : 0u;
+        const bool none = !(best > -FLT_MAX);                   // no comparable score left (NaN boxes cannot occur; be safe): first child, first slot
+        if (none) eq = (has && mySlot < 0) ? freeS : 0u;
+        const unsigned cand = (__ballot_sync(FULL, eq != 0u) >> gsh) & 0xFFu;
+        const int kl = __ffs(cand) - 1;                          // group-uniform; >= 0 while r < nc
+        const int ks = __shfl_sync(FULL, __ffs(eq) - 1, (int)gsh + (kl < 0 ? 0 : kl));
+        if (r < nc && kl >= 0) {
+          const bool mine = (int)sub == kl;
+          if (mine) mySlot = ks;
+          freeS &= ~(1u << ks);
+          #pragma unroll
+          for (int sl = 0; sl < 8; sl++) if (mine || sl == ks) sc[sl] = -FLT_MAX;
+        }
+      }
+    }
+
+    // ---- allocate children / triangles: one atomic per counter per block ----
+    const uint32_t numInner = __popc((ib >> gsh) & 0xFFu), numLeaves = __popc((lb >> gsh) & 0xFFu);
+    uint32_t numLeafTris = leaf ? ctris : 0u;
+    #pragma unroll
+    for (int o = 1; o < 8; o <<= 1) numLeafTris += __shfl_xor_sync(FULL, numLeafTris, o);
+    if (sub == 0u) { s_cnt[0][grp] = numInner; s_cnt[1][grp] = numLeafTris; s_cnt[2][grp] = numLeaves; }
+    __syncthreads();
+    if (threadIdx.x < 32u) {
+      const uint32_t a = s_cnt[0][lane], c = s_cnt[1][lane], d = s_cnt[2][lane];
+      uint32_t si = a, st = c, sl = d;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(FULL, si, o), y = __shfl_up_sync(FULL, st, o), z = __shfl_up_sync(FULL, sl, o);
+        if ((int)lane >= o) { si += x; st += y; sl += z; }
+      }
+      uint32_t bi = 0u, bt = 0u, bq = 0u;
+      if (lane == 31u) {
+        if (si) { bi = atomicAdd(&ctr->nodeCount, si); bq = atomicAdd(&ctr->nextCount, si); }
+        if (st) bt = atomicAdd(&ctr->triCount, st);
+        if (sl) atomicAdd(&ctr->leafSlots, sl);
+      }
+      bi = __shfl_sync(FULL, bi, 31); bt = __shfl_sync(FULL, bt, 31); bq = __shfl_sync(FULL, bq, 31);
+      s_base[0][lane] = bi + si - a; s_base[1][lane] = bt + st - c; s_base[2][lane] = bq + si - a;
+    }
+    __syncthreads();
+    const uint32_t childBase = numInner ? s_base[0][grp] : 0u, triBase = numLeafTris ? s_base[1][grp] : 0u, qBase = s_base[2][grp];
+
+    // ---- rank of this child among the inner children / first triangle of its leaf slot, both in SLOT order ----
+    uint32_t innerRank = 0u, triOff = 0u;
+    {
+      const uint32_t packed = has ? ((uint32_t)mySlot | (isInner ? 0x10u : 0u) | (ctris << 8)) : 0xFu;
+      #pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint32_t pk = __shfl_sync(FULL, packed, (int)gsh + k);
+        if (has && (pk & 0xFu) < (uint32_t)mySlot) { if (pk & 0x10u) innerRank++; else triOff += pk >> 8; }
+      }
+    }
+
+    // ---- quantisation grid of the node (every lane of the group computes the same) and this child's bytes ----
+    const float np[3] = {nlo.x, nlo.y, nlo.z};
+    const float ext[3] = {__fsub_ru(nhi.x, nlo.x), __fsub_ru(nhi.y, nlo.y), __fsub_ru(nhi.z, nlo.z)};
+    const float clo[3] = {lo.x, lo.y, lo.z}, chi[3] = {hi.x, hi.y, hi.z};
+    uint32_t ebits = 0u, qlo[3] = {0u, 0u, 0u}, qhi[3] = {0u, 0u, 0u};
+    float dq[3];
+    #pragma unroll
+    for (int a = 0; a < 3; a++) {
+      uint8_t eb = expForExtent(ext[a]);
+      // make sure the far face is representable: ceil(ext / 2^e) <= 255
+      while (eb < 254 && __fmul_ru(ext[a], __uint_as_float((uint32_t)(254 - eb) << 23)) > 255.0f) eb++;
+      ebits |= (uint32_t)eb << (8 * a);
+      const float step = __uint_as_float((uint32_t)eb << 23);            // 2^(eb-127)
+      const float inv = __uint_as_float((uint32_t)(254 - eb) << 23);      // 2^(127-eb)
+      // floor / ceil with directed rounding: decoded box always contains the exact one
+      float fl = floorf(__fmul_rd(__fsub_rd(clo[a], np[a]), inv));
+      float fh = ceilf(__fmul_ru(__fsub_ru(chi[a], np[a]), inv));
+      fl = fminf(fmaxf(fl, 0.f), 255.f); fh = fminf(fmaxf(fh, 0.f), 255.f);
+      qlo[a] = (uint32_t)fl; qhi[a] = (uint32_t)fh;
+      dq[a] = (fh - fl) * step;
+    }
+    uint32_t masks = 0u;
+    if (has) {
+      const double Aq = (double)halfArea(dq[0], dq[1], dq[2]);
+      const double Ax = (double)halfArea(chi[0] - clo[0], chi[1] - clo[1], chi[2] - clo[2]);
+      if (isInner) {
+        masks = 1u << (24 + mySlot);
+        sInnerQ += Aq; sInnerX += Ax;
+      } else {
+        masks = ((1u << ctris) - 1u) << (3 * mySlot);          // 1..3 triangles, stored in slot order
+        const double blocks = (double)((ctris + 3u) / 4u);
+        sLeafQ += Aq * blocks; sLeafX += Ax * blocks; sLeafTrisQ += Aq * (double)ctris;
+      }
+    }
+    #pragma unroll
+    for (int o = 1; o < 8; o <<= 1) masks |= __shfl_xor_sync(FULL, masks, o);
+    if (level == 0u && valid && sub == 0u) { sInnerQ += (double)nlo.w; sInnerX += (double)nlo.w; }   // the root's own box
+
+    // ---- assemble the 128-byte record in shared memory: lane k writes words 4k .. 4k+3, then the children drop their bytes in ----
+    {
+      uint4 v;
+      if (sub == 0u) v = make_uint4(__float_as_uint(nlo.x), __float_as_uint(nlo.y), __float_as_uint(nlo.z), ebits);
+      else if (sub == 1u) v = make_uint4(childBase, triBase, masks, 0u);
+      else if (sub == 2u) v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);                 // qlo of empty slots = 255 ...
+      else if (sub == 3u) v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);                                     // ... qhi = 0
+      else if (sub == 4u) v = make_uint4(0u, 0u, 0u, 0u);
+      else if (sub == 5u) v = make_uint4(__float_as_uint(nlo.x), __float_as_uint(nlo.y), __float_as_uint(nlo.z), __float_as_uint(nhi.x));
+      else if (sub == 6u) v = make_uint4(__float_as_uint(nhi.y), __float_as_uint(nhi.z), (parentOf && valid) ? parentOf[q] : RQ_INVALID, __float_as_uint(nhi.w));
+      else v = make_uint4(level, 0u, 0u, 0u);
+      ((uint4*)s_node[grp])[sub] = v;
+      __syncwarp();
+      if (has) {
+        uint8_t* nb = (uint8_t*)s_node[grp];
+        #pragma unroll
+        for (int a = 0; a < 3; a++) { nb[32 + a * 8 + mySlot] = (uint8_t)qlo[a]; nb[56 + a * 8 + mySlot] = (uint8_t)qhi[a]; }
+      }
+      __syncwarp();
+      if (valid) ((uint4*)(nodes + w))[sub] = ((const uint4*)s_node[grp])[sub];
+    }
+
+    // ---- inner child: an entry of the next level's queue ----
+    if (has && isInner) {
+      nextQueue[qBase + innerRank] = make_uint2(m, childBase + innerRank);
+      nextParentOf[qBase + innerRank] = w;
+    }
+    // ---- leaf slot: its <= 3 triangles = the leaves below binary node m (tiny depth-first walk; works for the radix tree and for
+    //      PLOC, whose subtrees are not contiguous in Morton order) ----
+    if (leaf) {
+      uint32_t walk[4]; int wsp = 0; uint32_t j = 0u;
+      walk[wsp++] = m;
+      while (wsp > 0 && j < ctris) {
+        const uint32_t x = walk[--wsp];
+        if (x >= firstLeaf) {
+          const uint32_t tin = vals[x - firstLeaf];
+          const float4* src = (const float4*)(trisIn + tin);
+          const uint32_t dsti = triBase + triOff + j;
+          if (trisC) {                                          // compact layout: indices + primID, geomID / quad flag on the side
+            const float4 c = src[2];
+            RQTriC r; r.v0 = idxIn[3 * (size_t)tin]; r.v1 = idxIn[3 * (size_t)tin + 1]; r.v2 = idxIn[3 * (size_t)tin + 2]; r.primID = __float_as_uint(c.y);
+            trisC[dsti] = r;
+            metaOut[dsti] = (__float_as_uint(c.z) & ~RQ_META_FLIPUV) | ((__float_as_uint(c.w) & RQ_PAD_FLIPUV) ? RQ_META_FLIPUV : 0u);
+          } else {
+            float4* dst = (float4*)(trisOut + dsti);
+            const float4 a0 = src[0], a1 = src[1], a2 = src[2];
+            if (dsti & 1u) { dst[0] = a2; dst[1] = a0; dst[2] = a1; }   // odd records: last 16 bytes first (rq_types.h)
+            else { dst[0] = a0; dst[1] = a1; dst[2] = a2; }
+          }
+          j++;
+        } else if (wsp < 3) { walk[wsp++] = t.right[x]; walk[wsp++] = t.left[x]; }
+      }
+    }
+  }
+
+  double s[5] = {sInnerQ, sLeafQ, sInnerX, sLeafX, sLeafTrisQ};
   #pragma unroll
   for (int k = 0; k < 5; k++)
     for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
   if ((threadIdx.x & 31) == 0) {
     atomicAdd(&ctr->sahInnerQ, s[0]); atomicAdd(&ctr->sahLeafQ, s[1]);
     atomicAdd(&ctr->sahInnerX, s[2]); atomicAdd(&ctr->sahLeafX, s[3]); atomicAdd(&ctr->sahLeafTrisQ, s[4]);
+  }
+}
+
+// between two levels: the counts of the level just emitted become the next level's work description
+__global__ void k_emit_advance(EmitCounters* ctr, EmitLevel* lv, uint32_t level) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    lv[level].nodeEnd = ctr->nodeCount;
+    lv[level + 1].count = ctr->nextCount;
+    ctr->nextCount = 0u;
   }
 }
 
@@ -1535,7 +1708,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
   DevBuf<uint32_t> cid0, cid1, nnBuf, blockCount, plocCtr; uint32_t plocIters = 0;
   DevBuf<uint32_t> rparent, rfirst, rlast, sizeAt, tlStart, tlBlock, tlTotal; uint32_t numTreelets = 0;
   DevBuf<float4> blo, bhi; DevBuf<float> cost; DevBuf<uint2> queue0, queue1; DevBuf<RQNode> nodes;
-  DevBuf<Bounds12> dBounds; DevBuf<uint32_t> dInvalid; DevBuf<EmitCounters> dCtr;
+  DevBuf<Bounds12> dBounds; DevBuf<uint32_t> dInvalid; DevBuf<EmitCounters> dCtr; DevBuf<EmitLevel> dLevels;
   DevBuf<uint32_t> idx3, metaOut; DevBuf<RQTriC> trisC; DevBuf<float4> vpool;
   DevBuf<uint32_t> pieces, tileSum, preTotal, idxSplit; DevBuf<RQTri> trisSplit; DevBuf<float4> refLo, refHi;
   bool useRefBoxes = false; uint32_t numSplitRefs = 0;
@@ -1669,7 +1842,8 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
           else { if (P.sweepBottom) RQ_TREELET_LAUNCH(256, TL_SWEEP); else RQ_TREELET_LAUNCH(256, 0); }
 #undef RQ_TREELET_LAUNCH
           CK(cudaEventRecord(ev[3], stream));
-          k_refit_dp<<<blocksFor(n, 256), 256, 0, stream>>>(t, (int)n, trisIn.p, vals0.p, P.costNode, P.costTri, P.maxLeafTris, 0);
+          if (K == 512u) k_treelet_dp<512><<<blocksFor(T, TDP_WARPS), TDP_WARPS * 32, 0, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T, P.costNode, P.costTri, P.maxLeafTris);
+          else k_treelet_dp<256><<<blocksFor(T, TDP_WARPS), TDP_WARPS * 32, 0, stream>>>(t, (int)n, tlStart.p, sizeAt.p, T, P.costNode, P.costTri, P.maxLeafTris);
           k_treelet_roots<<<blocksFor(T, 256), 256, 0, stream>>>((int)n, tlStart.p, sizeAt.p, T, cid0.p);
           rqCountLaunch(3);
           CK(cudaGetLastError());
@@ -1729,21 +1903,40 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
       const uint2 rootEntry = make_uint2(n > 1 ? 0u : 0u /* n==1: node 0 is the leaf */, 0u);
       CK(cudaMemcpyAsync(queue0.p, &rootEntry, sizeof(uint2), cudaMemcpyHostToDevice, stream));
       uint2 *qin = queue0.p, *qout = queue1.p; uint32_t *pin = qParent0.p, *pout = qParent1.p;
-      uint32_t count = 1;
-      while (count > 0) {
-        k_emit<<<blocksFor(count, 128), 128, 0, stream>>>(t, (int)n, qin, count, qout, dCtr.p, nodes.p, trisOut.p,
-                                                       trisIn.p, vals0.p, depth, depth ? pin : nullptr, pout,
-                                                       compact ? idx3.p : nullptr, compact ? trisC.p : nullptr, compact ? metaOut.p : nullptr);
-        rqCountLaunch(1);
+      {
+        constexpr uint32_t MAXL = 208, BATCH = 4;                 // levels are launched BATCH at a time without waiting for their counts
+        static int emitGrid = 0;
+        if (!emitGrid) { int dv = 0, sms = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dv); emitGrid = (sms > 0 ? sms : 148) * 4; }
+        CK(dLevels.alloc(MAXL + 1));
+        std::vector<EmitLevel> hl(MAXL + 1);
+        const EmitLevel first = {1u, 0u};
+        CK(cudaMemcpyAsync(dLevels.p, &first, sizeof(first), cudaMemcpyHostToDevice, stream));
+        uint32_t launched = 0, bound = 1; bool done = false;
+        while (!done) {
+          for (uint32_t k = 0; k < BATCH; k++, launched++) {
+            const uint32_t grid = std::min<uint32_t>(blocksFor(bound, EMIT_GROUPS), (uint32_t)emitGrid);
+            k_emit<<<grid, EMIT_THREADS, 0, stream>>>(t, (int)n, qin, dLevels.p, qout, dCtr.p, nodes.p, trisOut.p,
+                                            trisIn.p, vals0.p, launched, launched ? pin : nullptr, pout,
+                                            compact ? idx3.p : nullptr, compact ? trisC.p : nullptr, compact ? metaOut.p : nullptr);
+            k_emit_advance<<<1, 32, 0, stream>>>(dCtr.p, dLevels.p, launched);
+            rqCountLaunch(2);
+            std::swap(qin, qout); std::swap(pin, pout);
+            bound = bound > n / 8u ? n : bound * 8u;              // a level holds at most 8x the entries of the one above (and never more than n)
+          }
+          CK(cudaMemcpyAsync(hl.data(), dLevels.p, sizeof(EmitLevel) * (launched + 1), cudaMemcpyDeviceToHost, stream));
+          CK(cudaStreamSynchronize(stream));
+          CK(cudaGetLastError());
+          while (depth < launched && hl[depth].count > 0) {        // levels that had entries (an empty level launched nothing)
+            if (depth) levelEnd.push_back(hl[depth - 1].nodeEnd);  // nodes allocated while level depth-1 was emitted = level depth
+            depth++;
+          }
+          if (depth < launched) done = true;
+          else bound = std::max<uint32_t>(hl[launched].count, 1u);
+          if (!done && hl[launched].count == 0) done = true;
+          if (launched + BATCH > MAXL) { if (!done) { err = (int)cudaErrorUnknown; goto fail; } }
+        }
         CK(cudaMemcpyAsync(&hc, dCtr.p, sizeof(hc), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
-        CK(cudaGetLastError());
-        count = hc.nextCount;
-        depth++;
-        if (count) levelEnd.push_back(hc.nodeCount);              // children allocated by this launch = the next level
-        if (count) CK(cudaMemsetAsync(&dCtr.p->nextCount, 0, 4, stream));
-        std::swap(qin, qout); std::swap(pin, pout);
-        if (depth > 200) { err = (int)cudaErrorUnknown; goto fail; }
       }
       numNodes = hc.nodeCount; numTris = hc.triCount;
     } else {
@@ -1775,7 +1968,19 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
     if (!monitorAlloc(H.totalBytes)) { err = (int)cudaErrorMemoryAllocation; goto fail; }
     imageAccounted = (size_t)H.totalBytes;
     CK(cudaMallocAsync(&image, H.totalBytes, stream));
-    CK(cudaMemsetAsync(image, 0, H.totalBytes, stream));
+    {
+      // every section is written in full below; only the alignment gaps behind the sections need zeroing (the whole-image memset was 0.1 ms for 0.66 GB)
+      auto zeroGap = [&](uint64_t from, uint64_t to) -> cudaError_t {
+        return to > from ? cudaMemsetAsync((char*)image + from, 0, (size_t)(to - from), stream) : cudaSuccess;
+      };
+      if (compact) {
+        CK(zeroGap(H.trisOffset + (uint64_t)numTris * sizeof(RQTriC), H.metaOffset));
+        CK(zeroGap(H.metaOffset + (uint64_t)numTris * 4ull, H.vertsOffset));
+        CK(zeroGap(H.vertsOffset + (uint64_t)numVerts * 16ull, H.totalBytes));
+      } else {
+        CK(zeroGap(H.trisOffset + (uint64_t)numTris * sizeof(RQTri), H.totalBytes));
+      }
+    }
     CK(cudaMemcpyAsync(image, &H, sizeof(H), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync((char*)image + H.nodesOffset, nodes.p, (size_t)numNodes * sizeof(RQNode), cudaMemcpyDeviceToDevice, stream));
     if (compact) {

@@ -106,7 +106,13 @@ template <bool OCCLUDED, bool ROBUST, bool COUNT, bool ALIGNED, bool SPLIT, int 
 #ifndef RQ_MIN_CTAS
 #define RQ_MIN_CTAS 8   /* 64 registers: 8 CTAs = 32 warps per SM; (128,1) let ptxas take 95 registers and cost 20 % (profiles/r01k_ab.log) */
 #endif
-__global__ void __launch_bounds__(128, INST ? 5 : RQ_MIN_CTAS)
+// The split closest-hit loop (incoherent streams) is bound by load latency at 32 warps per SM (issue slots 71 % busy, long-scoreboard
+// stalls first): 9 CTAs per SM = 56 registers, still without spills, +4.0 % on both scenes; 10 CTAs (48 registers) spill and lose
+// 10 %; the whole-list loops (occlusion, coherent) lose 1-2 % at 9 and stay at 8 (same-box A/B: profiles/r02l_ab_ctas.log).
+#ifndef RQ_MIN_CTAS_SPLIT
+#define RQ_MIN_CTAS_SPLIT 9
+#endif
+__global__ void __launch_bounds__(128, INST ? 5 : ((SPLIT && !OCCLUDED) ? RQ_MIN_CTAS_SPLIT : RQ_MIN_CTAS))
 k_trace(const TraceParams P) {
   // Traversal stack: one 8-byte node-group entry per tree level.  The first P.sdepth levels live
   // in shared memory, entry-major ([level][thread]) so that lanes with different stack depths still

@@ -150,3 +150,14 @@ def test_nccl_replica_on_second_gpu_answers_identically(product):
     assert np.array_equal(a.view(np.uint8), b.view(np.uint8)) and (a["geomID"] != 0xFFFFFFFF).any()
     product.lib.rtcReleaseScene(sc0); product.lib.rtcReleaseScene(sc1)
     product.lib.rtcReleaseDevice(d0); product.lib.rtcReleaseDevice(d1)
+
+
+def test_bench_shard_bands_cover_the_frame_once():
+    """bench.py deals the frame rows to the ranks in 64-row bands: every row exactly once, equal shares, one GPU = the whole frame."""
+    import bench
+    for w in (1, 2, 3, 4, 8):
+        bands = [bench.shard_bands(r, w) for r in range(w)]
+        rows = sorted(x for b in bands for (a, c) in b for x in range(a, c))
+        assert rows == list(range(bench.FRAME))
+        share = [sum(c - a for a, c in b) for b in bands]
+        assert max(share) - min(share) <= bench.SHARD_ROWS

@@ -36,7 +36,7 @@ def main():
         sc, keep = lib.build_scene(dev, meshes)
         st = lib.build_stats(sc)
         if h_d is None:
-            diffuse, shadow = bench.make_streams(fx, lambda r: lib.intersect(sc, r, coherent=True), (0, bench.FRAME), a.seeds)
+            diffuse, shadow = bench.make_streams(fx, lambda r: lib.intersect(sc, r, coherent=True), bench.shard_bands(0, 1), a.seeds)
             h_d = torch.from_numpy(diffuse.view(np.uint8).reshape(len(diffuse), 80)).pin_memory()
             h_s = torch.from_numpy(shadow.view(np.uint8).reshape(len(shadow), 48)).pin_memory()
             del diffuse, shadow
