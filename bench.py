@@ -10,7 +10,7 @@ stream + one occlusion stream over the whole batch.  `value` = rays of the batch
 HBM (CUDA events on the launching stream); `e2e` = the same through the C ABI with page-locked HOST buffers (H2D, kernels,
 D2H inside the timed region; a pageable-memory figure beside it).
 N > 1 (one process per GPU under torchrun): rank 0 builds, the flat BVH image is broadcast over NCCL / NVLink, every rank
-traces its shard (64-row bands of the frame, dealt round-robin) of the SAME batch -- strong scaling -- and the hit records are gathered on
+traces its shard (16-row bands of the frame, dealt round-robin) of the SAME batch -- strong scaling -- and the hit records are gathered on
 rank 0 (timed separately: `gather`).  `--workload c2` is BASELINE configs[1] (1.0 M triangles, 33.5 M rays, L2-resident BVH),
 `--workload c5` the build benchmark of configs[4].
 
@@ -135,13 +135,13 @@ def workload_name(w, tris, rays):
             f"(diffuse closest-hit stream (rtcIntersect1M) + shadow stream (rtcOccluded1M))")
 
 
-SHARD_ROWS = 64                                                            # N > 1: frame rows are dealt to the ranks in bands of this many rows
+SHARD_ROWS = 16                                                            # N > 1: frame rows are dealt to the ranks in bands of this many rows
 
 
 def shard_bands(rank, world):
     """Row bands [(r0, r1), ...] of the frame that rank `rank` of `world` traces.  One GPU: the whole frame (in 8 pieces, to bound the
-    host memory of the generator).  N GPUs: 64-row bands dealt round-robin -- contiguous N-ths of this frame differ by 10 % in
-    cost per ray (max / mean 1.106 at N = 8, 1.026 with the bands; profiles/r02l_shard_balance.jsonl), and strong scaling is
+    host memory of the generator).  N GPUs: 16-row bands dealt round-robin -- contiguous N-ths of this frame differ by 10 % in
+    cost per ray (max / mean 1.106 at N = 8, 1.026 with 64-row bands; profiles/r02l_shard_balance.jsonl), and strong scaling is
     timed as the max over ranks."""
     if world == 1:
         return [(FRAME * b // 8, FRAME * (b + 1) // 8) for b in range(8)]

@@ -120,6 +120,7 @@ k_trace(const TraceParams P) {
   // touched one line per lane and the stack made up 27 % of all L1 sectors
   // (profiles/r01c: 192 M local of 717 M sectors).  Levels beyond P.sdepth spill to local memory.
   extern __shared__ uint2 s_stack[];
+  constexpr bool FOLD = !(SPLIT && !OCCLUDED) && !INST;       // see the slab test
   const unsigned lane = threadIdx.x & 31u;
   const unsigned FULL = 0xffffffffu;
 
@@ -430,7 +431,9 @@ k_trace(const TraceParams P) {
           const float ez = (fabsf(Az) + fabsf(bz)) * 2.384185791015625e-07f;
           const float Bx = (bx - Ax) - ex, By = (by - Ay) - ey, Bz = (bz - Az) - ez;
           const float Axf = Ax * RQ_FAR_INFLATE, Ayf = Ay * RQ_FAR_INFLATE, Azf = Az * RQ_FAR_INFLATE;
-          const float Bxf = (bx - Ax) * RQ_FAR_INFLATE + ex, Byf = (by - Ay) * RQ_FAR_INFLATE + ey, Bzf = (bz - Az) * RQ_FAR_INFLATE + ez;
+          const float Bxf = FOLD ? fmaf(bx - Ax, RQ_FAR_INFLATE, ex) : (bx - Ax) * RQ_FAR_INFLATE + ex;
+          const float Byf = FOLD ? fmaf(by - Ay, RQ_FAR_INFLATE, ey) : (by - Ay) * RQ_FAR_INFLATE + ey;
+          const float Bzf = FOLD ? fmaf(bz - Az, RQ_FAR_INFLATE, ez) : (bz - Az) * RQ_FAR_INFLATE + ez;
           // a grid step too large for the 2^16 pre-scale (absurd extents x axis-parallel ray): enter every child
           const bool overflow = !(fabsf(Ax) < 1e37f && fabsf(Ay) < 1e37f && fabsf(Az) < 1e37f);
           // near/far quantised planes per axis by ray direction sign (two words = 8 slots each)
@@ -441,6 +444,9 @@ k_trace(const TraceParams P) {
           const uint32_t nearY[2] = {ny ? qhy0 : qly0, ny ? qhy1 : qly1}, farY[2] = {ny ? qly0 : qhy0, ny ? qly1 : qhy1};
           const uint32_t nearZ[2] = {nz ? qhz0 : qlz0, nz ? qhz1 : qlz1}, farZ[2] = {nz ? qlz0 : qhz0, nz ? qlz1 : qhz1};
 
+          // FOLD (the 64-register loops: occlusion / coherent): m and M are clamped with the ray's own interval and one difference
+          // decides -- same-box A/B +1.0 ... +1.5 % occlusion rate, answers identical; in the 56-register split closest-hit kernel
+          // the same change spills and costs 7 % (profiles/r02p_ab_fold.log), so that kernel keeps the three differences.
           // Child k is hit iff  m <= M, m <= tfar, M >= tnear  with m = max of its three near
           // distances, M = min of its three far distances.  The three differences are formed on
           // the FMA pipe; the OR of their sign bits is the miss flag, shifted into `miss` by one
@@ -455,9 +461,16 @@ k_trace(const TraceParams P) {
             const float tmaxx = fmaf(byteToUnit(farX[h], j), Axf, Bxf);
             const float tmaxy = fmaf(byteToUnit(farY[h], j), Ayf, Byf);
             const float tmaxz = fmaf(byteToUnit(farZ[h], j), Azf, Bzf);
-            const float m = fmaxf(fmaxf(tminx, tminy), tminz);
-            const float M = fminf(fminf(tmaxx, tmaxy), tmaxz);
-            const uint32_t sgn = __float_as_uint(M - m) | __float_as_uint(tfarBox - m) | __float_as_uint(M - tnearBox);
+            uint32_t sgn;
+            if (FOLD) {                                         // the ray's own interval joins the min / max: 6 instead of 7 ALU instructions per child
+              const float m = fmaxf(fmaxf(fmaxf(tminx, tminy), tminz), tnearBox);
+              const float M = fminf(fminf(fminf(tmaxx, tmaxy), tmaxz), tfarBox);
+              sgn = __float_as_uint(M - m);
+            } else {
+              const float m = fmaxf(fmaxf(tminx, tminy), tminz);
+              const float M = fminf(fminf(tmaxx, tmaxy), tmaxz);
+              sgn = __float_as_uint(M - m) | __float_as_uint(tfarBox - m) | __float_as_uint(M - tnearBox);
+            }
             miss = __funnelshift_l(sgn, miss, 1);
           }
           const uint32_t masks = n1.z;

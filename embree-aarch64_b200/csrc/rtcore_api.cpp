@@ -167,6 +167,11 @@ struct Device : RefCounted {
     }
     return *pool;
   }
+  // staged upload of pageable geometry buffers at commit (stagedUpload below): page-locked chunks + the event of their last DMA
+  static const int kGeoRing = 3; static const size_t kGeoChunk = (size_t)8 << 20;
+  void* geoStage[kGeoRing] = {nullptr, nullptr, nullptr}; cudaEvent_t geoEvent[kGeoRing] = {nullptr, nullptr, nullptr};
+  std::mutex geoMutex;
+  int stageGeometry = 1;                  // stage_geometry=0: plain cudaMemcpyAsync from the caller's pages
   int refitEnabled = 1;                   // refit=0: RTC_BUILD_QUALITY_REFIT geometries are rebuilt like any other
   // Multi-GPU ("gpus=N"): this device object drives GPU `ordinal`; every further GPU is a peer device object of its
   // own (own streams, staging rings, host pool).  A commit builds here and replicates the flat image to the peers over
@@ -191,6 +196,7 @@ struct Device : RefCounted {
         if (packHost[i]) cudaFreeHost(packHost[i]);
       }
       for (SmallStage* s : smallAll) { if (s->buf) cudaFree(s->buf); if (s->work) cudaFree(s->work); if (s->stream) cudaStreamDestroy(s->stream); delete s; }
+      for (int i = 0; i < kGeoRing; i++) { if (geoStage[i]) cudaFreeHost(geoStage[i]); if (geoEvent[i]) cudaEventDestroy(geoEvent[i]); }
       if (countHost) cudaFreeHost(countHost);
       if (countDev) cudaFree(countDev);
       if (dCounters) cudaFree(dCounters);
@@ -260,6 +266,7 @@ void parseConfig(Device* d, const char* cfg, bool* allowNoGpu) {
     else if (k == "d2h") d->d2hMode = atoi(v.c_str());
     else if (k == "compact_min_rays") d->compactMinRays = (unsigned)std::max(0ll, atoll(v.c_str()));
     else if (k == "scatter_threads" || k == "host_threads") d->scatterThreads = atoi(v.c_str());
+    else if (k == "stage_geometry") d->stageGeometry = atoi(v.c_str());
     else if (k == "pack_rays") d->packRays = atoi(v.c_str());
     else if (k == "pack_pageable") d->packPageable = atoi(v.c_str());
     else if (k == "pack_depth") d->packDepth = std::max(1, atoi(v.c_str()));
@@ -384,6 +391,44 @@ void freeImage(Device* dev, RQDeviceImage* img) {
   if (dev->memFn) dev->memFn(dev->memPtr, -(ssize_t)bytes, true);
 }
 
+// Pageable geometry buffers (what a drop-in application attaches: malloc'ed vertex / index arrays).  cudaMemcpyAsync from pageable
+// memory bounces through the driver's own staging buffer at ~12 GB/s and made the H2D of the 180 MB of the 10 M-triangle scene
+// two thirds of rtcCommitScene's wall time (16 of 22 ms; the build kernels take 5.6).  Instead the library's host threads copy
+// 8 MB chunks into a ring of page-locked buffers and the copy engine takes them from there, chunk k+1 being filled while chunk k is
+// in flight.
+void stagedUpload(Device* dev, char* dst, const char* src, size_t bytes, cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(dev->geoMutex);
+  for (int i = 0; i < Device::kGeoRing; i++) {
+    if (!dev->geoStage[i]) {
+      cudaCheck(cudaHostAlloc(&dev->geoStage[i], Device::kGeoChunk, cudaHostAllocDefault), "geometry staging buffer");
+      cudaCheck(cudaEventCreateWithFlags(&dev->geoEvent[i], cudaEventDisableTiming), "geometry staging event");
+    }
+  }
+  HostPool& pool = dev->hostPool();
+  const size_t parts = std::max<size_t>(1, std::min<size_t>(pool.size(), 8));
+  size_t k = 0;
+  for (size_t off = 0; off < bytes; off += Device::kGeoChunk, k++) {
+    const int slot = (int)(k % Device::kGeoRing);
+    const size_t n = std::min(Device::kGeoChunk, bytes - off);
+    if (k >= (size_t)Device::kGeoRing) cudaCheck(cudaEventSynchronize(dev->geoEvent[slot]), "geometry upload (ring)");
+    std::mutex m; std::condition_variable cv; size_t left = parts;
+    const size_t per = ((n + parts - 1) / parts + 63) & ~(size_t)63;
+    for (size_t t = 0; t < parts; t++) {
+      const size_t b = std::min(n, t * per), e = std::min(n, b + per);
+      pool.submit([&, b, e, slot, off] {
+        if (e > b) memcpy((char*)dev->geoStage[slot] + b, src + off + b, e - b);
+        std::lock_guard<std::mutex> l(m);
+        if (--left == 0) cv.notify_one();
+      });
+    }
+    { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return left == 0; }); }
+    cudaCheck(cudaMemcpyAsync(dst + off, dev->geoStage[slot], n, cudaMemcpyHostToDevice, s), "geometry upload (copy)");
+    cudaCheck(cudaEventRecord(dev->geoEvent[slot], s), "geometry upload (event)");
+  }
+  // the ring slots may be refilled by the next upload only after their DMAs: wait for the ones still in flight
+  for (int i = 0; i < Device::kGeoRing && (size_t)i < k; i++) cudaCheck(cudaEventSynchronize(dev->geoEvent[i]), "geometry upload (drain)");
+}
+
 struct TempDev {                                         // device copies of host geometry buffers, freed after the build
   std::vector<void*> ptrs; std::vector<size_t> sizes; cudaStream_t stream = nullptr; Device* dev = nullptr;   // stream-ordered pool: no cudaMalloc/cudaFree stalls on re-commit
   ~TempDev() { for (size_t i = 0; i < ptrs.size(); i++) { cudaFreeAsync(ptrs[i], stream); if (dev && dev->memFn) dev->memFn(dev->memPtr, -(ssize_t)sizes[i], true); } }
@@ -395,7 +440,8 @@ struct TempDev {                                         // device copies of hos
     const int e = cudaMallocAsync(&d, want, s);
     if (e) { if (dev && dev->memFn) dev->memFn(dev->memPtr, -(ssize_t)want, true); cudaCheck(e, "geometry upload (alloc)"); }
     ptrs.push_back(d); sizes.push_back(want);
-    if (bytes) cudaCheck(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s), "geometry upload (copy)");
+    if (bytes >= ((size_t)4 << 20) && dev && dev->stageGeometry && !mappedHostPointer(src)) stagedUpload(dev, (char*)d, src, bytes, s);
+    else if (bytes) cudaCheck(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s), "geometry upload (copy)");
     return (const uint8_t*)d;
   }
 };

@@ -153,7 +153,7 @@ def test_nccl_replica_on_second_gpu_answers_identically(product):
 
 
 def test_bench_shard_bands_cover_the_frame_once():
-    """bench.py deals the frame rows to the ranks in 64-row bands: every row exactly once, equal shares, one GPU = the whole frame."""
+    """bench.py deals the frame rows to the ranks in 16-row bands: every row exactly once, equal shares, one GPU = the whole frame."""
     import bench
     for w in (1, 2, 3, 4, 8):
         bands = [bench.shard_bands(r, w) for r in range(w)]

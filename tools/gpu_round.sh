@@ -24,3 +24,6 @@ for W in c3 c2; do
     -f -o $OUT/${TAG}_trace_$W python tools/profile_trace.py --workload $W --reps 1 --meta $OUT/${TAG}_trace_$W.meta.json > $OUT/${TAG}_ncu_trace_$W.log 2>&1
   tail -3 $OUT/${TAG}_ncu_trace_$W.log
 done
+# shard balance of the bench batch at world 8 (one GPU plays every rank) and the build benchmark of configs[4] without the reference
+timeout 600 python tools/shard_balance.py --world 8 --band 16 > $OUT/${TAG}_shard_balance.jsonl 2> $OUT/${TAG}_shard_balance.err
+timeout 900 python bench.py --workload c5 --no-cpu-baseline --kinds scene > $OUT/${TAG}_bench_c5.json 2> $OUT/${TAG}_bench_c5.err
