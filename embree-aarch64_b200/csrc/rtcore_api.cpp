@@ -1285,6 +1285,22 @@ RTC_API RTCDevice rtcNewDevice(const char* config) {
           can = 0;
           if (cudaDeviceCanAccessPeer(&can, d->ordinal, pd->ordinal) == cudaSuccess && can) { if (cudaDeviceEnablePeerAccess(pd->ordinal, 0) != cudaSuccess) cudaGetLastError(); }
         }
+        // The images live in the stream-ordered pools (cudaMallocAsync), and pool memory is NOT covered by cudaDeviceEnablePeerAccess:
+        // without an explicit access grant cudaMemcpyPeerAsync between two pool allocations is staged through host memory (the
+        // replication of the 0.66 GB image took 18-22 ms = PCIe speed on NV18 boxes, profiles/r02r_cabi_gpus.jsonl).  Every GPU of the
+        // group may read and write every other GPU's pool.
+        for (int a = 0; a < d->numGpus; a++) {
+          cudaMemPool_t pool = nullptr;
+          if (cudaDeviceGetDefaultMemPool(&pool, d->ordinal + a) != cudaSuccess) { cudaGetLastError(); continue; }
+          for (int b = 0; b < d->numGpus; b++) {
+            if (a == b) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, d->ordinal + b, d->ordinal + a) != cudaSuccess || !can) { cudaGetLastError(); continue; }
+            cudaMemAccessDesc desc; memset(&desc, 0, sizeof(desc));
+            desc.location.type = cudaMemLocationTypeDevice; desc.location.id = d->ordinal + b; desc.flags = cudaMemAccessFlagsProtReadWrite;
+            if (cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) cudaGetLastError();
+          }
+        }
         d->bind();
       }
     }

@@ -41,9 +41,12 @@ def replicate_scene(lib, device, scene, src=0):
         lib.lib.rtcxCopySceneImage(scene, img.data_ptr(), nbytes.value)
     else:
         img = torch.empty(0, dtype=torch.uint8, device="cuda")
-    # NCCL sets its broadcast channels up lazily: a one-word broadcast first, so that the time reported is the transfer
-    warm = torch.zeros(1, dtype=torch.uint8, device="cuda")
-    dist.broadcast(warm, src)
+    # NCCL sets its broadcast channels (and, per message size class, its protocol buffers) up lazily: a one-word and a 32 MB
+    # broadcast first, so that the time reported is the transfer
+    for n in (1, 32 << 20):
+        warm = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        dist.broadcast(warm, src)
+    del warm
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
