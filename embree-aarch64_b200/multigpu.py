@@ -47,11 +47,18 @@ def replicate_scene(lib, device, scene, src=0):
         warm = torch.zeros(n, dtype=torch.uint8, device="cuda")
         dist.broadcast(warm, src)
     del warm
+    # size first, receive buffers allocated before the clock starts (a fresh 0.66 GB cudaMalloc in eight processes at once took
+    # tens of ms and was being reported as transfer time: 46 ms at N = 8 against 2.2 ms at N = 4, profiles/r02t_bench_8gpu.json)
+    n = torch.tensor([img.numel() if rank == src else 0], dtype=torch.int64, device="cuda")
+    dist.broadcast(n, src)
+    if rank != src:
+        img = torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
+        img.zero_()
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    img = broadcast_bytes(img, src, device="cuda")
+    dist.broadcast(img, src)
     e1.record()
     torch.cuda.synchronize()
     if rank != src:

@@ -55,6 +55,45 @@ def test_sah_statistic_and_image_structure(product, gpu_device, quality):
         L.rtcReleaseScene(sc)
 
 
+def test_degenerate_inputs_build_and_answer(product, gpu_device):
+    """Inputs that stress the hierarchy stages: 70 000 copies of one triangle (all Morton codes equal: the radix tree falls back to
+    splits by position, every SAH bin but one is empty), 60 000 tiny triangles on a line (one-dimensional centroid bounds, long
+    chains of one-sided splits) and two triangles spanning the whole scene.  The build must terminate within its depth bound, keep
+    every primitive exactly once, and rays aimed at known triangles must report them."""
+    from oracle import rq_image
+    n_same, n_line = 70000, 60000
+    tri = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]], dtype=np.float32) + np.float32([5.0, 0.0, 5.0])
+    v_same = np.tile(tri, (n_same, 1)); t_same = np.arange(3 * n_same, dtype=np.uint32).reshape(-1, 3)
+    k = np.arange(n_line, dtype=np.float32)
+    base = np.stack([k * np.float32(1e-3), np.zeros(n_line, np.float32), np.zeros(n_line, np.float32)], 1)
+    v_line = (base[:, None, :] + np.float32([[0, 0, 0], [8e-4, 0, 0], [0, 0, 8e-4]])[None, :, :]).reshape(-1, 3).astype(np.float32)
+    t_line = np.arange(3 * n_line, dtype=np.uint32).reshape(-1, 3)
+    v_big = np.float32([[-100, -1, -100], [100, -1, -100], [-100, -1, 100], [100, -1, 100]]); t_big = np.uint32([[0, 1, 2], [2, 1, 3]])
+    meshes = [(v_same, t_same), (v_line, t_line), (v_big, t_big)]
+    sc, keep = product.build_scene(gpu_device, meshes)
+    assert product.lib.rtcGetDeviceError(gpu_device) == 0
+    st = product.build_stats(sc)
+    assert st["numPrimsValid"] == n_same + n_line + 2 and 1 <= st["depth"] <= 200
+    assert rq_image.fetch(product, sc).check_structure(_prim_keys(meshes))
+    # rays straight down at the centroid of every 97th line triangle: that triangle, from above, at t = 1
+    idx = np.arange(0, n_line, 97)
+    r = rt.new_rays(len(idx))
+    c = v_line.reshape(-1, 3, 3)[idx].mean(axis=1)
+    fx._set(r, c + np.float32([0, 1, 0]), np.broadcast_to(np.float32([0, -1, 0]), c.shape), 0.0, np.inf)
+    product.intersect(sc, r)
+    assert np.array_equal(r["geomID"], np.full(len(idx), 1, np.uint32)) and np.array_equal(r["primID"], idx.astype(np.uint32))
+    assert np.allclose(r["tfar"], 1.0, rtol=1e-5)
+    # a ray into the stack of identical triangles hits one of them at the right distance; one beside everything hits the big floor
+    r2 = rt.new_rays(2)
+    fx._set(r2, np.float32([[5.25, 2.0, 5.25], [50.0, 2.0, 50.0]]), np.float32([[0, -1, 0], [0, -1, 0]]), 0.0, np.inf)
+    product.intersect(sc, r2)
+    assert r2["geomID"][0] == 0 and abs(r2["tfar"][0] - 2.0) < 1e-5 and r2["geomID"][1] == 2 and abs(r2["tfar"][1] - 3.0) < 1e-5
+    s2 = fx.to_ray(r2); s2["tfar"] = np.inf
+    product.occluded(sc, s2)
+    assert np.all(np.isneginf(s2["tfar"]))
+    product.lib.rtcReleaseScene(sc)
+
+
 def test_sah_close_to_the_reference_builder(product, reflib):
     """Tree quality against the reference's binned-SAH BVH8 builder on the same input (BENCHMARK_BUILD figure):
     the blocks-of-4-equivalent SAH of our tree must stay within 15 % of it."""
