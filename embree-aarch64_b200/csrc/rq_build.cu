@@ -19,6 +19,7 @@
 //                      nodes, octant-ordered child slots, leaf triangles copied into leaf order
 // All traffic is streaming/coalesced except the unavoidable gathers (vertex fetch, leaf copy).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <float.h>
 #include <vector>
@@ -720,7 +721,11 @@ k_ploc_nn(B2 t, const uint32_t* __restrict__ cid, const uint32_t* __restrict__ m
     const int sj = j - b0;
     const float d = halfArea(fmaxf(hx, sb[sj][3]) - fminf(lx, sb[sj][0]), fmaxf(hy, sb[sj][4]) - fminf(ly, sb[sj][1]),
                              fmaxf(hz, sb[sj][5]) - fminf(lz, sb[sj][2]));
-    if (d < best) { best = d; bj = j; }                        // ties: the lower position wins on both sides => still mutual
+    // ties go to the "buddy" position i ^ 1, else to the lower position.  With the lower position alone, a run of identical boxes
+    // (70 000 copies of one triangle: tests/test_gpu_scale.py::test_degenerate_inputs_build_and_answer) produced ONE mutual pair
+    // per iteration -- everybody pointed at the start of the run -- and the build gave up at its iteration bound; with the buddy rule
+    // positions 2k and 2k+1 choose each other and such a run halves every iteration.
+    if (d < best || (d == best && j == (i ^ 1))) { best = d; bj = j; }
   }
   nn[i] = (uint32_t)bj;
 }
@@ -823,7 +828,7 @@ k_ploc_tail(B2 t, uint32_t* __restrict__ cidA, uint32_t* __restrict__ cidB, uint
         if (j == (int)i) continue;
         const float4 l2 = __ldcg(t.lo + cin[j]), h2 = __ldcg(t.hi + cin[j]);
         const float d = halfArea(fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z));
-        if (d < best) { best = d; bj = j; }
+        if (d < best || (d == best && j == (i ^ 1))) { best = d; bj = j; }   // tie rule of k_ploc_nn
       }
       nn[i] = (uint32_t)bj;
     }
@@ -1861,6 +1866,8 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
         CK(cudaMemcpyAsync(plocCtr.p, initCtr, sizeof(initCtr), cudaMemcpyHostToDevice, stream));
         uint32_t m = m0; uint32_t *cin = cid0.p, *cout = cid1.p;
         uint32_t it = 0;
+        uint32_t plocCap = 4096;                                  // iteration bound of the grid-level loop (RQ_B200_PLOC_CAP: test hook for the stall fallback)
+        if (const char* ev = getenv("RQ_B200_PLOC_CAP")) plocCap = (uint32_t)atoi(ev);
         while (m > PLOC_TAIL_MAX) {                                 // large cluster counts: one grid per step
           const unsigned nb = blocksFor(m, PLOC_THREADS);
           const uint32_t window = m > (1u << 20) ? 2u : (m > (1u << 16) ? 4u : 8u);
@@ -1879,7 +1886,7 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
           CK(cudaStreamSynchronize(stream));
           if (next >= m || next == 0) { err = (int)cudaErrorUnknown; goto fail; }   // every iteration merges at least the globally closest pair
           m = next;
-          if (it > 4096) { err = (int)cudaErrorUnknown; goto fail; }
+          if (it > plocCap) { err = RQ_BUILD_STALLED; goto fail; }
         }
         if (m > 1) {                                                // the tail (or everything, for treelet roots): one block, no host round trips
           k_ploc_tail<<<1, PLOC_TAIL_THREADS, 0, stream>>>(t, cin, cout, nnBuf.p, plocCtr.p + 1 + (it & 1u), plocCtr.p, plocCtr.p + 3, radius,

@@ -35,6 +35,10 @@ struct RQDeviceImage {
 
 // Builds the BVH for the given meshes on `stream` (geoms is a HOST array whose index/vertex
 // pointers must be device-readable).  On success *out owns a new device allocation.
+// RQ_BUILD_STALLED: the PLOC stage did not converge within its iteration bound (adversarial input: e.g. boxes whose nearest
+// neighbour is always the one to their left merge ONE pair per iteration); nothing was allocated, the caller may retry with the
+// radix-tree front end (params->builder = 0), which has no such bound.
+#define RQ_BUILD_STALLED (-1001)
 int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const RQBuildParams* params,
                rqStream stream, RQDeviceImage* out, RQBuildStats* stats);
 void rqFreeImage(RQDeviceImage* img);

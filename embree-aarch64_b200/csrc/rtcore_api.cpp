@@ -627,7 +627,13 @@ void commitScene(Scene* sc) {
     if (!insts.empty()) bp.maxLeafTris = 1;                  // every instance gets its own child box: entering one costs a ray transform + a root fetch
     if (sc->quality == RTC_BUILD_QUALITY_LOW) bp.builder = 0;
     else if (sc->quality == RTC_BUILD_QUALITY_HIGH) { bp.plocRadius = std::max(bp.plocRadius, 16); bp.treeletSize = 512; bp.sweepBottom = 1; bp.presplit = 1; if (bp.builder == 0) bp.builder = 2; }
-    cudaCheck(rqBuildBVH(descs.data(), (int)descs.size(), (uint32_t)sc->flags, &bp, (rqStream)s, &img, &st), "BVH build");
+    int be = rqBuildBVH(descs.data(), (int)descs.size(), (uint32_t)sc->flags, &bp, (rqStream)s, &img, &st);
+    if (be == RQ_BUILD_STALLED) {                            // PLOC made no progress on this input: the radix tree always terminates
+      if (dev->verbose >= 1) fprintf(stderr, "b200-rayquery: PLOC stage stalled, rebuilding with the radix-tree front end\n");
+      bp.builder = 0;
+      be = rqBuildBVH(descs.data(), (int)descs.size(), (uint32_t)sc->flags, &bp, (rqStream)s, &img, &st);
+    }
+    cudaCheck(be, "BVH build");
     if (sc->image.base) { if (sc->accounted) freeImage(dev, &sc->image); else rqFreeImage(&sc->image); }
     sc->image = img; sc->stats = st; sc->accounted = true;
     // instance table (traversal reads it through TraceParams::instances)

@@ -94,6 +94,33 @@ def test_degenerate_inputs_build_and_answer(product, gpu_device):
     product.lib.rtcReleaseScene(sc)
 
 
+def test_ploc_stall_falls_back_to_the_radix_tree(product, oracle):
+    """A PLOC stage that does not converge within its iteration bound (adversarial input) must not fail the commit: the scene is
+    rebuilt with the radix-tree front end.  The bound is lowered through the test hook RQ_B200_PLOC_CAP to force the path."""
+    import os
+    meshes = [fx.displaced_plane(128, extent=3.0), fx.triangle_sphere((0, 1, 0), 0.7, 48)]     # ~42 k triangles: several grid-level PLOC iterations
+    dev = product.new_device("gpu_builder=ploc")
+    os.environ["RQ_B200_PLOC_CAP"] = "1"
+    try:
+        sc, keep = product.build_scene(dev, meshes)
+    finally:
+        del os.environ["RQ_B200_PLOC_CAP"]
+    assert product.lib.rtcGetDeviceError(dev) == 0
+    st = product.build_stats(sc)
+    assert st["builderIterations"] == 0 and st["numPrimsValid"] == fx.num_tris(meshes)      # the radix tree built it
+    sc2, keep2 = product.build_scene(dev, meshes)                                              # same device, bound back to normal: PLOC
+    assert product.build_stats(sc2)["builderIterations"] > 0
+    h = oracle.build(meshes)
+    rays = fx.incoherent_rays(20000, org=(0.2, 2.0, 0.1), seed=5)
+    want = rays.copy(); oracle.intersect(h, want)
+    for s in (sc, sc2):
+        a = rays.copy(); product.intersect(s, a)
+        assert parity.compare_closest(a, want)["pass"]
+        product.lib.rtcReleaseScene(s)
+    oracle.free(h)
+    product.lib.rtcReleaseDevice(dev)
+
+
 def test_sah_close_to_the_reference_builder(product, reflib):
     """Tree quality against the reference's binned-SAH BVH8 builder on the same input (BENCHMARK_BUILD figure):
     the blocks-of-4-equivalent SAH of our tree must stay within 15 % of it."""
