@@ -94,6 +94,80 @@ def test_degenerate_inputs_build_and_answer(product, gpu_device):
     product.lib.rtcReleaseScene(sc)
 
 
+def _random_scene(rng, n):
+    """n triangles of mixed scale in [-1, 1]^3 (sizes from 1e-3 to 1), split over 1-3 meshes; a few repeated, flat or needle-shaped."""
+    c = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
+    size = (10.0 ** rng.uniform(-3, 0, (n, 1, 1))).astype(np.float32)
+    tri = (c + size * rng.uniform(-1, 1, (n, 3, 3)).astype(np.float32)).astype(np.float32)
+    k = max(1, n // 16)
+    tri[rng.integers(0, n, k)] = tri[rng.integers(0, n, k)]                   # duplicates
+    flat = rng.integers(0, n, k); tri[flat, 2] = tri[flat, 1]                 # zero-area (never hit, still stored)
+    needle = rng.integers(0, n, k); tri[needle, 1] = tri[needle, 0] + np.float32(1e-6)
+    parts = np.array_split(np.arange(n), int(rng.integers(1, 4)))
+    return [(tri[p].reshape(-1, 3).copy(), np.arange(3 * len(p), dtype=np.uint32).reshape(-1, 3)) for p in parts if len(p)]
+
+
+def test_random_scenes_around_the_builder_thresholds(product, gpu_device, oracle):
+    """Seeded differential test against the oracle on random triangle soups whose sizes sit on the builder's internal thresholds
+    (leaf slots of 3, thread phase <= 32, treelets of 256 / 512, PLOC tail of 4096 clusters, emission batches of 4 levels)."""
+    from oracle import rq_image
+    rng = np.random.default_rng(20261017)
+    sizes = [1, 2, 3, 4, 7, 8, 9, 24, 25, 31, 32, 33, 64, 65, 255, 256, 257, 511, 512, 513, 1000, 4095, 4096, 4097, 9000, 33000]
+    for n in sizes:
+        meshes = _random_scene(rng, n)
+        sc, keep = product.build_scene(gpu_device, meshes)
+        assert product.lib.rtcGetDeviceError(gpu_device) == 0, n
+        assert product.build_stats(sc)["numPrimsValid"] == n
+        assert rq_image.fetch(product, sc).check_structure(_prim_keys(meshes)), n
+        h = oracle.build(meshes)
+        m = 4096
+        o = rng.uniform(-1.5, 1.5, (m, 3)).astype(np.float32)
+        d = rng.normal(size=(m, 3)).astype(np.float32)
+        r = fx._set(rt.new_rays(m), o, d, 0.0, np.inf)
+        a, b = r.copy(), r.copy()
+        product.intersect(sc, a); oracle.intersect(h, b)
+        res = parity.compare_closest(a, b)
+        assert res["pass"], (n, res)
+        sa = fx.to_ray(r); sa["tfar"] = np.float32(1.0); sb = sa.copy()
+        product.occluded(sc, sa); oracle.occluded(h, sb)
+        assert parity.compare_occluded(sa, sb)["pass"], n
+        oracle.free(h)
+        product.lib.rtcReleaseScene(sc)
+
+
+@pytest.mark.parametrize("flags,quality", [(rt.RTC_SCENE_FLAG_ROBUST, rt.RTC_BUILD_QUALITY_MEDIUM), (rt.RTC_SCENE_FLAG_COMPACT, rt.RTC_BUILD_QUALITY_MEDIUM),
+                                           (0, rt.RTC_BUILD_QUALITY_HIGH), (rt.RTC_SCENE_FLAG_COMPACT | rt.RTC_SCENE_FLAG_ROBUST, rt.RTC_BUILD_QUALITY_LOW)])
+def test_random_scenes_with_scene_flags_and_qualities(product, oracle, flags, quality):
+    """The same differential test through the Pluecker test (ROBUST), the indexed leaf layout (COMPACT) and the LOW / HIGH build
+    qualities (radix tree / pre-split + 512-triangle treelets with sweep bottom)."""
+    rng = np.random.default_rng(7 + flags * 16 + quality)
+    dev = product.new_device("")
+    L = product.lib
+    for n in (1, 5, 33, 300, 513, 2049, 4097, 20000):
+        meshes = _random_scene(rng, n)
+        sc = L.rtcNewScene(dev)
+        L.rtcSetSceneFlags(sc, flags); L.rtcSetSceneBuildQuality(sc, quality)
+        keep = []
+        for v, t in meshes:
+            _, g = product.add_mesh(dev, sc, v, t, keep)
+            L.rtcReleaseGeometry(g)
+        L.rtcCommitScene(sc)
+        assert L.rtcGetDeviceError(dev) == 0, n
+        h = oracle.build(meshes, robust=bool(flags & rt.RTC_SCENE_FLAG_ROBUST))
+        m = 4096
+        r = fx._set(rt.new_rays(m), rng.uniform(-1.5, 1.5, (m, 3)).astype(np.float32), rng.normal(size=(m, 3)).astype(np.float32), 0.0, np.inf)
+        a, b = r.copy(), r.copy()
+        product.intersect(sc, a); oracle.intersect(h, b)
+        res = parity.compare_closest(a, b)
+        assert res["pass"], (n, res)
+        sa = fx.to_ray(r); sa["tfar"] = np.float32(1.0); sb = sa.copy()
+        product.occluded(sc, sa); oracle.occluded(h, sb)
+        assert parity.compare_occluded(sa, sb)["pass"], n
+        oracle.free(h)
+        L.rtcReleaseScene(sc)
+    L.rtcReleaseDevice(dev)
+
+
 def test_ploc_stall_falls_back_to_the_radix_tree(product, oracle):
     """A PLOC stage that does not converge within its iteration bound (adversarial input) must not fail the commit: the scene is
     rebuilt with the radix-tree front end.  The bound is lowered through the test hook RQ_B200_PLOC_CAP to force the path."""
