@@ -819,16 +819,27 @@ k_ploc_tail(B2 t, uint32_t* __restrict__ cidA, uint32_t* __restrict__ cidB, uint
   uint32_t m = *mPtr;
   uint32_t* cin = cidA; uint32_t* cout = cidB;
   uint32_t its = 0;
+  // the boxes of the current clusters, by position (SoA, 6 x PLOC_TAIL_MAX floats of dynamic shared memory): every iteration loads
+  // them once from L2 and the neighbour search (2 x radius candidates per cluster) runs out of shared memory -- the search used to
+  // fetch both float4 of every candidate through L2, ~30 latency-bound iterations = 0.32 ms of the 10 M-triangle build
+  extern __shared__ float s_box[];
   while (m > 1u) {
     for (uint32_t i = tid; i < m; i += PLOC_TAIL_THREADS) {
       const float4 lo = __ldcg(t.lo + cin[i]), hi = __ldcg(t.hi + cin[i]);
+      s_box[i] = lo.x; s_box[PLOC_TAIL_MAX + i] = lo.y; s_box[2 * PLOC_TAIL_MAX + i] = lo.z;
+      s_box[3 * PLOC_TAIL_MAX + i] = hi.x; s_box[4 * PLOC_TAIL_MAX + i] = hi.y; s_box[5 * PLOC_TAIL_MAX + i] = hi.z;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < m; i += PLOC_TAIL_THREADS) {
+      const float lx = s_box[i], ly = s_box[PLOC_TAIL_MAX + i], lz = s_box[2 * PLOC_TAIL_MAX + i];
+      const float hx = s_box[3 * PLOC_TAIL_MAX + i], hy = s_box[4 * PLOC_TAIL_MAX + i], hz = s_box[5 * PLOC_TAIL_MAX + i];
       float best = FLT_MAX; int bj = -1;
       const int j0 = max((int)i - radius, 0), j1 = min((int)i + radius, (int)m - 1);
       for (int j = j0; j <= j1; j++) {
         if (j == (int)i) continue;
-        const float4 l2 = __ldcg(t.lo + cin[j]), h2 = __ldcg(t.hi + cin[j]);
-        const float d = halfArea(fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z));
-        if (d < best || (d == best && j == (i ^ 1))) { best = d; bj = j; }   // tie rule of k_ploc_nn
+        const float d = halfArea(fmaxf(hx, s_box[3 * PLOC_TAIL_MAX + j]) - fminf(lx, s_box[j]), fmaxf(hy, s_box[4 * PLOC_TAIL_MAX + j]) - fminf(ly, s_box[PLOC_TAIL_MAX + j]),
+                                 fmaxf(hz, s_box[5 * PLOC_TAIL_MAX + j]) - fminf(lz, s_box[2 * PLOC_TAIL_MAX + j]));
+        if (d < best || (d == best && j == (int)(i ^ 1u))) { best = d; bj = j; }   // tie rule of k_ploc_nn
       }
       nn[i] = (uint32_t)bj;
     }
@@ -1889,7 +1900,9 @@ int rqBuildBVH(const RQGeomDesc* geoms, int numGeoms, uint32_t sceneFlags, const
           if (it > plocCap) { err = RQ_BUILD_STALLED; goto fail; }
         }
         if (m > 1) {                                                // the tail (or everything, for treelet roots): one block, no host round trips
-          k_ploc_tail<<<1, PLOC_TAIL_THREADS, 0, stream>>>(t, cin, cout, nnBuf.p, plocCtr.p + 1 + (it & 1u), plocCtr.p, plocCtr.p + 3, radius,
+          constexpr size_t tailSmem = 6 * (size_t)PLOC_TAIL_MAX * sizeof(float);
+          CK(cudaFuncSetAttribute(k_ploc_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tailSmem));
+          k_ploc_tail<<<1, PLOC_TAIL_THREADS, tailSmem, stream>>>(t, cin, cout, nnBuf.p, plocCtr.p + 1 + (it & 1u), plocCtr.p, plocCtr.p + 3, radius,
                                                            P.costNode, P.costTri, P.maxLeafTris);
           rqCountLaunch(1);
         }

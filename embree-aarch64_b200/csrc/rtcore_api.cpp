@@ -622,8 +622,9 @@ void commitScene(Scene* sc) {
     RQBuildStats st;
     RQBuildParams bp = dev->build;
     // scene build quality: LOW = the fast radix-tree front end (role of the reference's Morton builder for
-    // RTC_BUILD_QUALITY_LOW, scene.cpp:118-124), HIGH = PLOC with a wide search radius (the reference adds
-    // spatial splits here, which this builder does not do)
+    // RTC_BUILD_QUALITY_LOW, scene.cpp:118-124), HIGH = large triangles pre-split into clipped references (role of the
+    // reference's spatial-split builder, bvh_builder_sah_spatial.cpp), 512-triangle treelets with an exact sweep at the
+    // bottom, PLOC search radius >= 16
     if (!insts.empty()) bp.maxLeafTris = 1;                  // every instance gets its own child box: entering one costs a ray transform + a root fetch
     if (sc->quality == RTC_BUILD_QUALITY_LOW) bp.builder = 0;
     else if (sc->quality == RTC_BUILD_QUALITY_HIGH) { bp.plocRadius = std::max(bp.plocRadius, 16); bp.treeletSize = 512; bp.sweepBottom = 1; bp.presplit = 1; if (bp.builder == 0) bp.builder = 2; }
