@@ -135,6 +135,32 @@ def test_oracle_matches_live_reference(oracle, reflib, scale, seed):
     reflib.lib.rtcReleaseDevice(dev)
 
 
+@pytest.mark.parametrize("robust", [False, True])
+def test_oracle_matches_live_reference_on_random_soups(oracle, reflib, robust):
+    """The random triangle soups of the GPU differential test (tests/test_gpu_scale.py::_random_scene: mixed scales, duplicates,
+    zero-area and needle triangles), restatement against the real library: this pins the checker the GPU tests rely on."""
+    import test_gpu_scale as T
+    rng = np.random.default_rng(99 + int(robust))
+    flags = rt.RTC_SCENE_FLAG_ROBUST if robust else 0
+    dev = reflib.new_device("")
+    for n in (1, 3, 33, 257, 1000, 4097, 20000):
+        meshes = T._random_scene(rng, n)
+        sc, keep = reflib.build_scene(dev, meshes, flags)
+        h = oracle.build(meshes, robust=robust)
+        m = 8192
+        r = fx._set(rt.new_rays(m), rng.uniform(-1.5, 1.5, (m, 3)).astype(np.float32), rng.normal(size=(m, 3)).astype(np.float32), 0.0, np.inf)
+        a, b = r.copy(), r.copy()
+        oracle.intersect(h, a); reflib.intersect(sc, b)
+        res = parity.compare_closest(a, b)
+        assert res["pass"], (n, res)
+        sa = fx.to_ray(r); sa["tfar"] = np.float32(1.0); sb = sa.copy()
+        oracle.occluded(h, sa); reflib.occluded(sc, sb)
+        assert parity.compare_occluded(sa, sb)["pass"], n
+        oracle.free(h)
+        reflib.lib.rtcReleaseScene(sc)
+    reflib.lib.rtcReleaseDevice(dev)
+
+
 @pytest.mark.parametrize("name", ["inst_forest", "inst_forest_robust", "inst_only"])
 def test_instancing_restatement_matches_reference_golden(oracle, name):
     """Single-level instancing (instance_intersector.cpp:48-105): the restatement against vectors of the real library."""
