@@ -171,7 +171,7 @@ struct Device : RefCounted {
   static const int kGeoRing = 3; static const size_t kGeoChunk = (size_t)8 << 20;
   void* geoStage[kGeoRing] = {nullptr, nullptr, nullptr}; cudaEvent_t geoEvent[kGeoRing] = {nullptr, nullptr, nullptr};
   std::mutex geoMutex;
-  int stageGeometry = 1;                  // stage_geometry=0: plain cudaMemcpyAsync from the caller's pages
+  int stageGeometry = 32;                 // stage_geometry=<MB>: smallest pageable buffer that takes the staged route (0 = never: plain cudaMemcpyAsync from the caller's pages)
   int refitEnabled = 1;                   // refit=0: RTC_BUILD_QUALITY_REFIT geometries are rebuilt like any other
   // Multi-GPU ("gpus=N"): this device object drives GPU `ordinal`; every further GPU is a peer device object of its
   // own (own streams, staging rings, host pool).  A commit builds here and replicates the flat image to the peers over
@@ -395,7 +395,9 @@ void freeImage(Device* dev, RQDeviceImage* img) {
 // memory bounces through the driver's own staging buffer at ~12 GB/s and made the H2D of the 180 MB of the 10 M-triangle scene
 // two thirds of rtcCommitScene's wall time (16 of 22 ms; the build kernels take 5.6).  Instead the library's host threads copy
 // 8 MB chunks into a ring of page-locked buffers and the copy engine takes them from there, chunk k+1 being filled while chunk k is
-// in flight.
+// in flight.  The hand-offs to the thread pool cost ~1.2 ms per buffer, so the route pays from ~20 MB on (a 6 MB vertex buffer:
+// 1.2 ms plain, 2.6 ms staged; 180 MB: 16 ms plain, 6 ms staged -- profiles/r02final_ab_stage_small.log, r02r_build_c3_*.jsonl);
+// the default threshold is 32 MB (device option stage_geometry=<MB>, 0 = never).
 void stagedUpload(Device* dev, char* dst, const char* src, size_t bytes, cudaStream_t s) {
   std::lock_guard<std::mutex> lock(dev->geoMutex);
   for (int i = 0; i < Device::kGeoRing; i++) {
@@ -440,7 +442,7 @@ struct TempDev {                                         // device copies of hos
     const int e = cudaMallocAsync(&d, want, s);
     if (e) { if (dev && dev->memFn) dev->memFn(dev->memPtr, -(ssize_t)want, true); cudaCheck(e, "geometry upload (alloc)"); }
     ptrs.push_back(d); sizes.push_back(want);
-    if (bytes >= ((size_t)4 << 20) && dev && dev->stageGeometry && !mappedHostPointer(src)) stagedUpload(dev, (char*)d, src, bytes, s);
+    if (dev && dev->stageGeometry > 0 && bytes >= ((size_t)dev->stageGeometry << 20) && !mappedHostPointer(src)) stagedUpload(dev, (char*)d, src, bytes, s);
     else if (bytes) cudaCheck(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s), "geometry upload (copy)");
     return (const uint8_t*)d;
   }

@@ -99,11 +99,12 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--cfg", default="", help="device options of our library (e.g. stage_geometry=0)")
     a = ap.parse_args()
     meshes = fx.scene_c2(a.scale)
     ntris = fx.num_tris(meshes)
     lib = rt.RTCore()
-    dev = lib.new_device("")
+    dev = lib.new_device(a.cfg)
     res = {"workload": f"configs[1] scene, {ntris} triangles, wave deformation of every vertex per commit", "reps": a.reps}
     res["ours_rebuild_host_buffers"] = run(lib, dev, meshes, a.reps, rt.RTC_BUILD_QUALITY_MEDIUM, 0)
     res["ours_refit_host_buffers"] = run(lib, dev, meshes, a.reps, rt.RTC_BUILD_QUALITY_REFIT, 0)
