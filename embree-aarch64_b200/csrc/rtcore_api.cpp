@@ -409,10 +409,14 @@ void stagedUpload(Device* dev, char* dst, const char* src, size_t bytes, cudaStr
   HostPool& pool = dev->hostPool();
   const size_t parts = std::max<size_t>(1, std::min<size_t>(pool.size(), 8));
   size_t k = 0;
+  const auto tStart = std::chrono::steady_clock::now();
+  double msCopy = 0.0, msRing = 0.0;
   for (size_t off = 0; off < bytes; off += Device::kGeoChunk, k++) {
     const int slot = (int)(k % Device::kGeoRing);
     const size_t n = std::min(Device::kGeoChunk, bytes - off);
+    const auto t0 = std::chrono::steady_clock::now();
     if (k >= (size_t)Device::kGeoRing) cudaCheck(cudaEventSynchronize(dev->geoEvent[slot]), "geometry upload (ring)");
+    const auto t1 = std::chrono::steady_clock::now();
     std::mutex m; std::condition_variable cv; size_t left = parts;
     const size_t per = ((n + parts - 1) / parts + 63) & ~(size_t)63;
     for (size_t t = 0; t < parts; t++) {
@@ -424,11 +428,19 @@ void stagedUpload(Device* dev, char* dst, const char* src, size_t bytes, cudaStr
       });
     }
     { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return left == 0; }); }
+    const auto t2 = std::chrono::steady_clock::now();
+    msRing += std::chrono::duration<double, std::milli>(t1 - t0).count(); msCopy += std::chrono::duration<double, std::milli>(t2 - t1).count();
     cudaCheck(cudaMemcpyAsync(dst + off, dev->geoStage[slot], n, cudaMemcpyHostToDevice, s), "geometry upload (copy)");
     cudaCheck(cudaEventRecord(dev->geoEvent[slot], s), "geometry upload (event)");
   }
   // the ring slots may be refilled by the next upload only after their DMAs: wait for the ones still in flight
+  const auto tDrain = std::chrono::steady_clock::now();
   for (int i = 0; i < Device::kGeoRing && (size_t)i < k; i++) cudaCheck(cudaEventSynchronize(dev->geoEvent[i]), "geometry upload (drain)");
+  if (dev->verbose >= 2) {
+    const auto tEnd = std::chrono::steady_clock::now();
+    fprintf(stderr, "  staged upload %.1f MB: total %.3f ms (host copies %.3f, ring waits %.3f, drain %.3f)\n", bytes / 1e6,
+            std::chrono::duration<double, std::milli>(tEnd - tStart).count(), msCopy, msRing, std::chrono::duration<double, std::milli>(tEnd - tDrain).count());
+  }
 }
 
 struct TempDev {                                         // device copies of host geometry buffers, freed after the build
